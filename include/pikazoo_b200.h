@@ -1,0 +1,140 @@
+/* pikazoo_b200 — C ABI of the B200-native batched Pikachu-Volleyball simulator.
+ *
+ * This is the drop-in boundary for the reference's hot path. The reference
+ * (helpingstar/pika-zoo) is pure Python and has no FFI of its own; the interface replaced
+ * is the PettingZoo ParallelEnv surface of `raw_env`, so each entry point below cites the
+ * reference method whose work it performs for a whole batch of independent envs:
+ *
+ *   pz_seed / pz_seed_array   raw_env.__init__ + _seed            pikazoo/env/pikazoo_env.py:79-147,570-571
+ *                             (+ protocol S0 generator overwrite)
+ *   pz_reset                  raw_env.reset                       pikazoo/env/pikazoo_env.py:149-173
+ *   pz_step                   raw_env.step                        pikazoo/env/pikazoo_env.py:175-240
+ *                             -> physics_engine and callees       pikazoo/env/physics.py:59-99,280-884
+ *                             + SimplifyAction.step               pikazoo/wrappers/simplify_action.py:16-25
+ *                             + RewardByBallPosition.step         pikazoo/wrappers/reward_by_ball_position.py:20-31
+ *                             + raw_env._get_obs                  pikazoo/env/pikazoo_env.py:576-624
+ *   pz_rollout                K x raw_env.step with the state held in registers
+ *   pz_step_host              raw_env.step for callers holding HOST buffers (numpy users)
+ *   pz_export_state / pz_import_state   the Python object graph <-> packed device state
+ *
+ * Conventions: every pointer named *_dev is device memory owned by the caller (the library
+ * allocates nothing except inside pz_host_ctx); `stream` is a cudaStream_t passed as void*;
+ * all calls are asynchronous on that stream and re-entrant; return value 0 = success,
+ * > 0 = cudaError_t, < 0 = PZ_E_*; nothing throws across the boundary.
+ * Binary is sm_100a only. There is no CPU fallback.
+ */
+#ifndef PIKAZOO_B200_H
+#define PIKAZOO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PZ_VERSION 1
+
+/* packed device state: int32 words per env (structure-of-arrays) */
+#define PZ_STATE_WORDS 17
+/* unpacked parity state: int32 words per env (layout of oracle/pika_oracle.h pk_env) */
+#define PZ_UNPACKED_WORDS 53
+#define PZ_OBS_WORDS 35 /* per agent, pikazoo_env.py:481-565 */
+#define PZ_NUM_STATS 16
+
+enum { PZ_SERVE_WINNER = 0, PZ_SERVE_ALTERNATE = 1, PZ_SERVE_RANDOM = 2 }; /* pikazoo_env.py:104 */
+enum { PZ_ACT_I32 = 0, PZ_ACT_I64 = 1, PZ_ACT_U8 = 2 };
+enum { PZ_REW_F32 = 0, PZ_REW_F64 = 1 };
+enum { PZ_ACTIONS_NOOP = 0, PZ_ACTIONS_SYNTH = 1 }; /* pz_rollout action source */
+
+enum {
+    PZ_E_BADARG = -1,    /* null pointer, n < 0, K < 1 ... */
+    PZ_E_BADCONFIG = -2, /* winning_score outside [1,1023], unknown serve/dtype code */
+    PZ_E_ALIGN = -3,     /* state/obs pointer not 16-byte aligned */
+    PZ_E_NODEVICE = -4   /* no sm_100 device / kernel image unusable */
+};
+
+/* indices into the int64 statistics vector (all counters are += over calls) */
+enum {
+    PZ_STAT_ENV_STEPS = 0,   /* raw_env.step calls executed */
+    PZ_STAT_EPISODES = 1,    /* games terminated */
+    PZ_STAT_EPISODE_FRAMES = 2, /* sum of episode lengths of terminated games */
+    PZ_STAT_P1_WINS = 3,
+    PZ_STAT_P2_WINS = 4,
+    PZ_STAT_P1_POINTS = 5,
+    PZ_STAT_P2_POINTS = 6,
+    PZ_STAT_RESETS = 7,      /* raw_env.reset calls executed by auto-reset */
+    PZ_STAT_BAD_ACTIONS = 8  /* actions outside the action space (treated as action 0) */
+};
+
+typedef struct pz_config {
+    int32_t winning_score;           /* pikazoo_env.py:81,102; 1..1023 */
+    int32_t serve;                   /* PZ_SERVE_*; pikazoo_env.py:82,104-105 */
+    int32_t is_player1_computer;     /* pikazoo_env.py:83 */
+    int32_t is_player2_computer;     /* pikazoo_env.py:84 */
+    int32_t simplify_action;         /* fuse SimplifyAction: actions in [0,13) */
+    int32_t reward_by_ball_position; /* fuse RewardByBallPosition */
+    int32_t x_line, y_line;          /* reward_by_ball_position.py:11-12 (defaults 216, 176) */
+    double additional_reward[8];     /* reward_by_ball_position.py:10 */
+    int32_t autoreset;               /* 1: a call on a terminated env performs reset() (NEXT-STEP) */
+    int32_t action_dtype;            /* PZ_ACT_*: element type of actions_dev [n][2] */
+    int32_t reward_dtype;            /* PZ_REW_*: element type of reward_dev [n][2] */
+    int32_t reserved;
+} pz_config;
+
+int pz_version(void);
+int pz_state_words(void);
+int pz_unpacked_words(void);
+size_t pz_state_bytes(int64_t n);
+const char *pz_strerror(int code);
+void pz_default_config(pz_config *cfg); /* reference defaults: ws=15, winner, no computers */
+
+/* Fresh env objects, generator of env i = numpy PCG64(SeedSequence(base_seed + first_env + i)).
+ * reset() has not been called. */
+int pz_seed(int32_t *state_dev, int64_t n, uint64_t base_seed, uint64_t first_env, void *stream);
+/* Same with explicit per-env seeds (device array of n uint64). */
+int pz_seed_array(int32_t *state_dev, int64_t n, const uint64_t *seeds_dev, void *stream);
+
+/* reset() on every env. obs_dev: int32 [n][2][35] or NULL. */
+int pz_reset(int32_t *state_dev, int64_t n, const pz_config *cfg, int32_t *obs_dev, void *stream);
+
+/* One frame of every env.
+ *   actions_dev [n][2] (cfg->action_dtype), obs_dev int32 [n][2][35] (may be NULL),
+ *   reward_dev [n][2] (cfg->reward_dtype, may be NULL), done_dev uint8 [n] (may be NULL),
+ *   stats_dev int64 [PZ_NUM_STATS] (may be NULL).
+ * Env terminated before the call: autoreset ? reset() (reward 0, done 0) : frozen (done 1). */
+int pz_step(int32_t *state_dev, int64_t n, const pz_config *cfg, const void *actions_dev,
+            int32_t *obs_dev, void *reward_dev, uint8_t *done_dev, int64_t *stats_dev, void *stream);
+
+/* K frames of every env in one launch, state register-resident, auto-reset always on.
+ * action_source PZ_ACTIONS_NOOP: both actions 0 (computer players decide for themselves);
+ * PZ_ACTIONS_SYNTH: uniform actions from the counter-based stream
+ *   synth(action_seed, first_env + i, frame0 + k, agent)   (DESIGN.md "synthetic actions").
+ * obs_dev (optional): observation after the last frame. stats_dev (optional) as above. */
+int pz_rollout(int32_t *state_dev, int64_t n, const pz_config *cfg, int32_t K, int32_t action_source,
+               uint64_t action_seed, uint64_t first_env, uint64_t frame0, int32_t *obs_dev,
+               int64_t *stats_dev, void *stream);
+
+/* packed <-> unpacked (int32 [n][53]) conversions, for checkpoints, tests and debugging */
+int pz_export_state(const int32_t *state_dev, int64_t n, int32_t *unpacked_dev, void *stream);
+int pz_import_state(int32_t *state_dev, int64_t n, const int32_t *unpacked_dev, void *stream);
+
+/* ---- host-buffer path (what a numpy caller of the reference would bind) ---------------
+ * A context owns the device state, staging buffers, streams and events for n envs on the
+ * current device; pz_host_step copies actions host->device, runs pz_step and copies
+ * obs/reward/done device->host, chunked so that copies overlap the kernel. Host buffers
+ * should be pinned (cudaHostAlloc / torch pin_memory) for full PCIe speed; pageable works. */
+typedef struct pz_host_ctx pz_host_ctx;
+int pz_host_create(pz_host_ctx **out, int64_t n, const pz_config *cfg, uint64_t base_seed,
+                   uint64_t first_env, int32_t chunks);
+int pz_host_reset(pz_host_ctx *ctx, int32_t *obs_host);
+int pz_host_step(pz_host_ctx *ctx, const void *actions_host, int32_t *obs_host, void *reward_host,
+                 uint8_t *done_host);
+int pz_host_stats(pz_host_ctx *ctx, int64_t stats_host[PZ_NUM_STATS]);
+int32_t *pz_host_state_dev(pz_host_ctx *ctx);
+void pz_host_destroy(pz_host_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

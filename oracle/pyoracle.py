@@ -1,0 +1,154 @@
+"""TEST INFRASTRUCTURE — ctypes binding of the C oracle (oracle/pika_oracle.c).
+
+May be imported only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` legs. The product package never imports it.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libpika_oracle.so")
+
+ENV_WORDS = 53
+SERVE_CODES = {"winner": 0, "alternate": 1, "random": 2}
+
+
+class PkConfig(ctypes.Structure):
+    _fields_ = [
+        ("winning_score", ctypes.c_int32),
+        ("serve", ctypes.c_int32),
+        ("is_player1_computer", ctypes.c_int32),
+        ("is_player2_computer", ctypes.c_int32),
+        ("simplify_action", ctypes.c_int32),
+        ("reward_by_ball_position", ctypes.c_int32),
+        ("x_line", ctypes.c_int32),
+        ("y_line", ctypes.c_int32),
+        ("additional_reward", ctypes.c_double * 8),
+    ]
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with gcc (a few hundred ms). Returns the .so path."""
+    src = os.path.join(_HERE, "pika_oracle.c")
+    hdr = os.path.join(_HERE, "pika_oracle.h")
+    if (
+        force
+        or not os.path.exists(LIB_PATH)
+        or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr))
+    ):
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i64, u64, i32, u32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int32, ctypes.c_uint32
+        cfgp = ctypes.POINTER(PkConfig)
+        L.pk_env_words.restype = ctypes.c_int
+        L.pk_pcg64_seed.argtypes = [u64, vp, vp]
+        L.pk_integers.argtypes = [vp, u32]
+        L.pk_integers.restype = i32
+        L.pk_init.argtypes = [vp, u64]
+        L.pk_reset.argtypes = [vp, cfgp, vp]
+        L.pk_step.argtypes = [vp, cfgp, i32, i32, vp, vp, vp]
+        L.pk_step.restype = ctypes.c_int
+        L.pk_vec_step.argtypes = [vp, i64, cfgp, vp, vp, vp, vp, ctypes.c_int]
+        L.pk_vec_step.restype = ctypes.c_int
+        L.pk_vec_init.argtypes = [vp, i64, u64]
+        L.pk_vec_reset.argtypes = [vp, i64, cfgp, vp]
+        L.pk_synth_action.argtypes = [u64, u64, u64, ctypes.c_int, u32]
+        L.pk_synth_action.restype = i32
+        L.pk_vec_rollout.argtypes = [vp, i64, cfgp, ctypes.c_int, ctypes.c_int, u64, u64, u64, vp]
+        L.pk_vec_rollout.restype = i64
+        assert L.pk_env_words() == ENV_WORDS
+        _lib = L
+    return _lib
+
+
+def make_config(
+    winning_score=15,
+    serve="winner",
+    is_player1_computer=False,
+    is_player2_computer=False,
+    simplify_action=False,
+    reward_by_ball_position=None,
+) -> PkConfig:
+    c = PkConfig()
+    c.winning_score = int(winning_score)
+    c.serve = SERVE_CODES[serve]
+    c.is_player1_computer = int(bool(is_player1_computer))
+    c.is_player2_computer = int(bool(is_player2_computer))
+    c.simplify_action = int(bool(simplify_action))
+    c.x_line, c.y_line = 216, 176
+    if reward_by_ball_position is not None:
+        add, x_line, y_line = reward_by_ball_position
+        assert len(add) == 8
+        c.reward_by_ball_position = 1
+        c.x_line, c.y_line = int(x_line), int(y_line)
+        for k in range(8):
+            c.additional_reward[k] = float(add[k])
+    return c
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class OracleVecEnv:
+    """N independent oracle envs with the product's batched NEXT-STEP auto-reset semantics."""
+
+    def __init__(self, num_envs, seed=0, autoreset=True, **cfg):
+        self.n = int(num_envs)
+        self.cfg = make_config(**cfg)
+        self.autoreset = bool(autoreset)
+        self.state = np.zeros((self.n, ENV_WORDS), dtype=np.int32)
+        self.obs = np.zeros((self.n, 2, 35), dtype=np.int32)
+        self.reward = np.zeros((self.n, 2), dtype=np.float64)
+        self.done = np.zeros((self.n,), dtype=np.uint8)
+        lib().pk_vec_init(_p(self.state), self.n, int(seed))
+
+    def reset(self):
+        lib().pk_vec_reset(_p(self.state), self.n, ctypes.byref(self.cfg), _p(self.obs))
+        return self.obs
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.int32).reshape(self.n, 2)
+        rc = lib().pk_vec_step(
+            _p(self.state), self.n, ctypes.byref(self.cfg), _p(a), _p(self.obs), _p(self.reward), _p(self.done),
+            int(self.autoreset),
+        )
+        if rc != 0:
+            raise IndexError("action out of range")
+        return self.obs, self.reward, self.done
+
+    def rollout(self, K, action_mode=0, action_seed=0, first_env=0, frame0=0, stats=None):
+        if stats is None:
+            stats = np.zeros(8, dtype=np.int64)
+        lib().pk_vec_rollout(
+            _p(self.state), self.n, ctypes.byref(self.cfg), int(K), int(action_mode), int(action_seed),
+            int(first_env), int(frame0), _p(stats),
+        )
+        return stats
+
+
+def pcg64_seed(seed: int):
+    st = np.zeros(4, dtype=np.uint32)
+    inc = np.zeros(4, dtype=np.uint32)
+    lib().pk_pcg64_seed(int(seed), _p(st), _p(inc))
+    return st, inc
+
+
+def synth_action(action_seed, global_env, frame, agent, n_actions=18) -> int:
+    return int(lib().pk_synth_action(int(action_seed), int(global_env), int(frame), int(agent), int(n_actions)))
