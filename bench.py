@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: env-steps/sec of the batched Pikachu-Volleyball simulator.
+
+    python bench.py --gpus 1 --steps 3000 --warmup 100
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the CPU implementation of the path on the host cores
+
+Workload (BASELINE.json `metric`: env-steps/sec at 1/2/4/8 B200, 1 M envs/GPU, % of HBM roofline):
+configs[1]'s per-step path scaled to 1,048,576 envs per GPU — uniform random Discrete(18) actions
+for both agents, winning_score 15, serve "winner", device-tensor obs/reward/done, auto-reset on
+game end. One "step" = one pz_step launch over the whole per-GPU batch. Envs shard over GPUs with
+no communication on the step path (weak scaling); NCCL all-reduces the statistics vector once,
+outside the timed region.
+
+One JSON line is printed by rank 0 (see the task contract): value (device-resident inputs),
+e2e (host buffers through the C ABI's pz_host_step), roofline, cpu_baseline, clocks, gpu_launches.
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_ENV_STEP = 425  # 8 actions + 280 obs + 8 reward + 1 done + 72 state R + 56 state W
+ENVS_PER_GPU = 1 << 20
+WORKLOAD = ("per-step path (configs[1] scaled to 1,048,576 envs/GPU): uniform random Discrete(18) actions for both "
+            "agents, winning_score=15, serve=winner, device obs/reward/done, NEXT-STEP auto-reset")
+ENV_KW = dict(winning_score=15, serve="winner")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-rollout", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (oracle/pika_oracle.c — the reference is pure Python and cannot travel
+# to the GPU box, so `kind` is "port"), one batch of envs per host thread.
+# ---------------------------------------------------------------------------------------------
+class CpuPort:
+    """The C oracle over all host cores on the bench workload.
+
+    Every thread owns `envs_per_thread` envs and repeatedly executes batched steps (obs, reward,
+    done written to host arrays, random actions pre-generated). ctypes releases the GIL, so the
+    threads run in parallel."""
+
+    def __init__(self, envs_per_thread: int = 4096, steps_per_call: int = 16):
+        import numpy as np
+
+        from oracle import pyoracle as po
+
+        po.build()
+        self.cores = len(os.sched_getaffinity(0))
+        self.envs_per_thread, self.steps_per_call = envs_per_thread, steps_per_call
+        rng = np.random.default_rng(0)
+        self.envs, self.acts = [], []
+        for t in range(self.cores):
+            e = po.OracleVecEnv(envs_per_thread, seed=10_000_000 + t * envs_per_thread, autoreset=True, **ENV_KW)
+            e.reset()
+            self.envs.append(e)
+            self.acts.append(rng.integers(0, 18, size=(steps_per_call, envs_per_thread, 2), dtype=np.int32))
+
+    def sample(self, seconds: float) -> float:
+        """env-steps/sec over one wall-clock window of `seconds`."""
+        counts = [0] * self.cores
+        deadline = time.perf_counter() + seconds
+
+        def work(t):
+            e, a, n = self.envs[t], self.acts[t], 0
+            while time.perf_counter() < deadline:
+                for k in range(self.steps_per_call):
+                    e.step(a[k])
+                n += self.steps_per_call * self.envs_per_thread
+            counts[t] = n
+
+        th = [threading.Thread(target=work, args=(t,)) for t in range(self.cores)]
+        t0 = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return sum(counts) / (time.perf_counter() - t0)
+
+
+def cpu_port_throughput(seconds: float):
+    port = CpuPort()
+    port.sample(1.0)  # warm-up
+    value = port.sample(seconds)
+    sample = (f"{port.cores} threads x {port.envs_per_thread} envs, random Discrete(18) actions, ws=15 winner, "
+              f"auto-reset, {seconds:.0f} s wall after 1 s warm-up")
+    return value, port.cores, sample
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # each "step" of this arm is a bounded sample: all host cores stepping their env batches for a
+    # fixed wall time; value = env-steps/sec averaged over the K timed samples.
+    steps = max(1, min(args.steps, 20))
+    warmup = max(1, min(args.warmup, 3))
+    per_step_seconds = 1.0
+    port = CpuPort()
+    for _ in range(warmup):
+        port.sample(per_step_seconds)
+    vals = [port.sample(per_step_seconds) for _ in range(steps)]
+    value = sum(vals) / len(vals)
+    cores = port.cores
+    sample = (f"{steps} timed samples of {per_step_seconds:.1f} s each: {cores} threads x {port.envs_per_thread} envs "
+              f"stepping the C port of the reference path (oracle/pika_oracle.c); the pure-Python reference cannot "
+              f"travel to the GPU box (DESIGN.md)")
+    line = {
+        "impl": "reference",
+        "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": per_step_seconds * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs_per_gpu},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
+
+    REASONS = {
+        0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+        0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost",
+    }
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop = [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES remapping via the PCI bus id of the torch device
+            import torch
+
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            if bus is not None:
+                for k in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(k)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        self.h = h
+                        break
+            self.nv = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv, self.err = None, repr(e)
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop.wait(0.005)
+
+    def __enter__(self):
+        if self.nv:
+            self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        if self.nv:
+            self.thread.join()
+
+    def summary(self):
+        if not self.nv or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import pikazoo_b200
+    from pikazoo_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.envs_per_gpu
+    total = n * world
+    K, W = args.steps, args.warmup
+    env = pikazoo_b200.make_sharded_env(total, rank, world, dev, seed=2026, **ENV_KW)
+    assert env.num_envs == n
+    env.reset()
+
+    # device-resident synthetic actions: a ring of R different [n, 2] int32 tensors
+    R = 8
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    ring = [torch.randint(0, 18, (n, 2), generator=gen, device=dev, dtype=torch.int32) for _ in range(R)]
+
+    for k in range(W):
+        env.step(ring[k % R])
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    with ClockSampler(local_rank) as clocks:
+        ev[0].record()
+        for k in range(K):
+            env.step(ring[k % R])
+            ev[k + 1].record()
+        torch.cuda.synchronize()
+    barrier()
+    elapsed_ms = ev[0].elapsed_time(ev[K])
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_ms = float(t.item())
+    value = total * K / (t_ms * 1e-3)
+    # per-launch durations of the step kernel (back-to-back launches on one stream)
+    per_launch_ms = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(K))
+    launch_ms = elapsed_ms / K
+
+    # episode statistics: the one collective of the design, off the step path
+    stats = env.stats.clone()
+    pikazoo_b200.allreduce_stats(stats)
+    stats_dict = {name: int(stats[i]) for i, name in enumerate(_lib.STAT_NAMES)}
+
+    # ---- e2e: host buffers through the C ABI (pz_host_step): H2D actions + D2H obs/reward/done ----
+    e2e = None
+    if not args.no_e2e:
+        L = _lib.load()
+        cfg = pikazoo_b200.make_config(**ENV_KW)
+        ctx = ctypes.c_void_p()
+        first, _ = pikazoo_b200.shard_range(total, world, rank)
+        _lib.check(L.pz_host_create(ctypes.byref(ctx), n, ctypes.byref(cfg), 2026, first, 8), "pz_host_create")
+        h_act = [torch.randint(0, 18, (n, 2), dtype=torch.int32).pin_memory() for _ in range(2)]
+        h_obs = torch.empty((n, 2, 35), dtype=torch.int32).pin_memory()
+        h_rew = torch.empty((n, 2), dtype=torch.float32).pin_memory()
+        h_done = torch.empty((n,), dtype=torch.uint8).pin_memory()
+        _lib.check(L.pz_host_reset(ctx, h_obs.data_ptr()), "pz_host_reset")
+        E = max(1, args.e2e_steps)
+        for k in range(3):
+            _lib.check(L.pz_host_step(ctx, h_act[k % 2].data_ptr(), h_obs.data_ptr(), h_rew.data_ptr(),
+                                      h_done.data_ptr()), "pz_host_step")
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(E):
+            _lib.check(L.pz_host_step(ctx, h_act[k % 2].data_ptr(), h_obs.data_ptr(), h_rew.data_ptr(),
+                                      h_done.data_ptr()), "pz_host_step")
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        L.pz_host_destroy(ctx)
+        e2e = {
+            "value": total * E / float(te.item()), "unit": "env-steps/s",
+            "h2d_bytes_per_step": n * 2 * 4, "d2h_bytes_per_step": n * (280 + 8 + 1),
+            "steps": E, "api": "pz_host_step (C ABI, pinned host buffers, 8 chunks on 8 streams; "
+                               "host-blocking call timed with perf_counter, max over ranks)",
+        }
+        del h_obs, h_rew, h_done, h_act
+
+    # ---- config 4: K = 64 register-resident rollout, computer vs computer (not HBM-bound) ----
+    rollout = None
+    if not args.no_rollout:
+        ai = pikazoo_b200.make_sharded_env(total, rank, world, dev, seed=4040, winning_score=15, serve="winner",
+                                           is_player1_computer=True, is_player2_computer=True)
+        ai.reset()
+        for _ in range(3):
+            ai.rollout(64)
+        barrier()
+        reps = 10
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            ai.rollout(64)
+        b.record()
+        torch.cuda.synchronize()
+        tr = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        rollout = {"workload": "configs[3]: 1,048,576 envs/GPU computer-vs-computer, K=64 frames per launch, "
+                               "state register-resident", "value": total * 64 * reps / (float(tr.item()) * 1e-3),
+                   "unit": "env-steps/s", "ms_per_launch": float(tr.item()) / reps}
+        del ai
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        achieved = ALGO_BYTES_PER_ENV_STEP * n / (launch_ms * 1e-3) / 1e9
+        line = {
+            "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "total_envs": total, "parallelism": f"env-shard x{world}",
+                       "l2": f"inputs larger than L2: {ALGO_BYTES_PER_ENV_STEP * n / 1e6:.0f} MB touched per step vs 126 MB L2",
+                       "actions": f"ring of {R} device-resident int32 [n,2] tensors"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "pz_step_kernel<0>", "algorithmic_bytes_per_env_step":
+                             ALGO_BYTES_PER_ENV_STEP, "launch_ms_avg": launch_ms,
+                         "launch_ms_p50": per_launch_ms[len(per_launch_ms) // 2], "peak_source": peak_src},
+            "e2e": e2e, "gpu_launches": K, "clocks": clocks.summary(), "episode_stats": stats_dict,
+        }
+        if rollout:
+            line["rollout"] = rollout
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample = cpu_port_throughput(args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                    "sample": sample}
+        traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(traffic_path):
+            with open(traffic_path) as f:
+                line["roofline"]["traffic"] = json.load(f).get("pz_step_kernel_bytes_per_launch")
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

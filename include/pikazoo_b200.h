@@ -56,15 +56,17 @@ enum {
 
 /* indices into the int64 statistics vector (all counters are += over calls) */
 enum {
-    PZ_STAT_ENV_STEPS = 0,   /* raw_env.step calls executed */
+    PZ_STAT_CALLS = 0,       /* env calls issued (n per pz_step, n*K per pz_rollout);
+                                raw_env.step calls executed = CALLS - RESETS - FROZEN */
     PZ_STAT_EPISODES = 1,    /* games terminated */
     PZ_STAT_EPISODE_FRAMES = 2, /* sum of episode lengths of terminated games */
     PZ_STAT_P1_WINS = 3,
     PZ_STAT_P2_WINS = 4,
-    PZ_STAT_P1_POINTS = 5,
+    PZ_STAT_P1_POINTS = 5,   /* points of terminated games (sum of final scores) */
     PZ_STAT_P2_POINTS = 6,
     PZ_STAT_RESETS = 7,      /* raw_env.reset calls executed by auto-reset */
-    PZ_STAT_BAD_ACTIONS = 8  /* actions outside the action space (treated as action 0) */
+    PZ_STAT_BAD_ACTIONS = 8, /* actions outside the action space (treated as action 0) */
+    PZ_STAT_FROZEN = 9       /* calls on terminated envs with autoreset off (no-ops) */
 };
 
 typedef struct pz_config {

@@ -1,0 +1,11 @@
+"""pika-zoo_b200: B200-native batched Pikachu Volleyball (drop-in for the hot path of
+helpingstar/pika-zoo). The directory name contains a hyphen; import it as `pikazoo_b200`
+(alias package at the repo root) or via importlib.import_module("pika-zoo_b200")."""
+
+from . import pikazoo_v0, wrappers  # noqa: F401
+from ._lib import PikaLibraryError, load as load_library  # noqa: F401
+from .dist import allreduce_stats, make_sharded_env, shard_range  # noqa: F401
+from .vec_env import PikaVecEnv, make_config  # noqa: F401
+from .wrappers import RewardByBallPosition, SimplifyAction  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,111 @@
+"""ctypes binding of the C ABI declared in include/pikazoo_b200.h.
+
+The product has no CPU path: if the CUDA library is missing this module raises, loudly.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libpikazoo_b200.so")
+
+STATE_WORDS = 17
+UNPACKED_WORDS = 53
+OBS_WORDS = 35
+NUM_STATS = 16
+
+SERVE_CODES = {"winner": 0, "alternate": 1, "random": 2}
+ACT_I32, ACT_I64, ACT_U8 = 0, 1, 2
+REW_F32, REW_F64 = 0, 1
+ACTIONS_NOOP, ACTIONS_SYNTH = 0, 1
+
+STAT_NAMES = (
+    "calls", "episodes", "episode_frames", "p1_wins", "p2_wins", "p1_points", "p2_points", "resets",
+    "bad_actions", "frozen",
+)
+
+
+class PzConfig(ctypes.Structure):
+    """struct pz_config (include/pikazoo_b200.h)."""
+
+    _fields_ = [
+        ("winning_score", ctypes.c_int32),
+        ("serve", ctypes.c_int32),
+        ("is_player1_computer", ctypes.c_int32),
+        ("is_player2_computer", ctypes.c_int32),
+        ("simplify_action", ctypes.c_int32),
+        ("reward_by_ball_position", ctypes.c_int32),
+        ("x_line", ctypes.c_int32),
+        ("y_line", ctypes.c_int32),
+        ("additional_reward", ctypes.c_double * 8),
+        ("autoreset", ctypes.c_int32),
+        ("action_dtype", ctypes.c_int32),
+        ("reward_dtype", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+class PikaLibraryError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load csrc/libpikazoo_b200.so (build it with `python pika-zoo_b200/build.py`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PikaLibraryError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built "
+            "(run `python pika-zoo_b200/build.py` or __graft_entry__.build()). There is no CPU fallback."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i64, u64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int32
+    cfgp = ctypes.POINTER(PzConfig)
+    L.pz_version.restype = ctypes.c_int
+    L.pz_state_words.restype = ctypes.c_int
+    L.pz_unpacked_words.restype = ctypes.c_int
+    L.pz_state_bytes.argtypes = [i64]
+    L.pz_state_bytes.restype = ctypes.c_size_t
+    L.pz_strerror.argtypes = [ctypes.c_int]
+    L.pz_strerror.restype = ctypes.c_char_p
+    L.pz_default_config.argtypes = [cfgp]
+    L.pz_default_config.restype = None
+    L.pz_seed.argtypes = [vp, i64, u64, u64, vp]
+    L.pz_seed_array.argtypes = [vp, i64, vp, vp]
+    L.pz_reset.argtypes = [vp, i64, cfgp, vp, vp]
+    L.pz_step.argtypes = [vp, i64, cfgp, vp, vp, vp, vp, vp, vp]
+    L.pz_rollout.argtypes = [vp, i64, cfgp, i32, i32, u64, u64, u64, vp, vp, vp]
+    L.pz_export_state.argtypes = [vp, i64, vp, vp]
+    L.pz_import_state.argtypes = [vp, i64, vp, vp]
+    for name in ("pz_seed", "pz_seed_array", "pz_reset", "pz_step", "pz_rollout", "pz_export_state",
+                 "pz_import_state"):
+        getattr(L, name).restype = ctypes.c_int
+    # host-buffer path
+    L.pz_host_create.argtypes = [ctypes.POINTER(vp), i64, cfgp, u64, u64, i32]
+    L.pz_host_create.restype = ctypes.c_int
+    L.pz_host_reset.argtypes = [vp, vp]
+    L.pz_host_reset.restype = ctypes.c_int
+    L.pz_host_step.argtypes = [vp, vp, vp, vp, vp]
+    L.pz_host_step.restype = ctypes.c_int
+    L.pz_host_stats.argtypes = [vp, vp]
+    L.pz_host_stats.restype = ctypes.c_int
+    L.pz_host_state_dev.argtypes = [vp]
+    L.pz_host_state_dev.restype = vp
+    L.pz_host_destroy.argtypes = [vp]
+    L.pz_host_destroy.restype = None
+    if L.pz_state_words() != STATE_WORDS or L.pz_unpacked_words() != UNPACKED_WORDS:
+        raise PikaLibraryError("libpikazoo_b200.so does not match this Python package (rebuild it)")
+    _lib = L
+    return L
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = load().pz_strerror(code).decode()
+        raise PikaLibraryError(f"{what or 'pikazoo_b200'} failed: {msg} (code {code})")

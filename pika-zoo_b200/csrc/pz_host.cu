@@ -1,0 +1,161 @@
+// Host-buffer path of the C ABI (pz_host_*): what a numpy caller of the reference binds.
+// One context owns the device state and staging buffers of n envs; a step is split into
+// `chunks` env ranges, each on its own stream: H2D(actions) -> pz_step_kernel -> D2H(obs,
+// reward, done), so the PCIe copies of one chunk overlap the kernel and copies of the others.
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "pz_kernels.cuh"
+
+struct pz_host_ctx {
+    int64_t n = 0;
+    pz_config cfg{};
+    int device = 0;
+    int32_t *state = nullptr;
+    void *actions = nullptr;
+    int32_t *obs = nullptr;
+    void *reward = nullptr;
+    uint8_t *done = nullptr;
+    int64_t *stats = nullptr;
+    std::vector<cudaStream_t> streams;
+    std::vector<int64_t> bounds;  // chunk c = [bounds[c], bounds[c+1])
+    size_t act_elem = 4, rew_elem = 4;
+};
+
+namespace {
+
+#define PZ_CUDA(x)                           \
+    do {                                     \
+        cudaError_t e_ = (x);                \
+        if (e_ != cudaSuccess) return (int)e_; \
+    } while (0)
+
+int sync_all(pz_host_ctx *c) {
+    for (cudaStream_t s : c->streams) PZ_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pz_host_create(pz_host_ctx **out, int64_t n, const pz_config *cfg, uint64_t base_seed, uint64_t first_env,
+                   int32_t chunks) {
+    if (!out || !cfg || n < 1) return PZ_E_BADARG;
+    if (cfg->winning_score < 1 || cfg->winning_score > 1023) return PZ_E_BADCONFIG;
+    pz_host_ctx *c = new (std::nothrow) pz_host_ctx();
+    if (!c) return (int)cudaErrorMemoryAllocation;
+    c->n = n;
+    c->cfg = *cfg;
+    c->act_elem = cfg->action_dtype == PZ_ACT_I64 ? 8 : (cfg->action_dtype == PZ_ACT_U8 ? 1 : 4);
+    c->rew_elem = cfg->reward_dtype == PZ_REW_F64 ? 8 : 4;
+    if (chunks < 1) chunks = 1;
+    // chunk boundaries on multiples of 128 envs (whole CTAs, 16-byte aligned slices of every array)
+    int64_t blocks = (n + 127) / 128;
+    if (chunks > blocks) chunks = (int32_t)blocks;
+    c->bounds.resize(chunks + 1);
+    for (int k = 0; k <= chunks; k++) {
+        int64_t b = (blocks * k / chunks) * 128;
+        c->bounds[k] = b > n ? n : b;
+    }
+    c->bounds[chunks] = n;
+    int rc = 0;
+    do {
+        if ((rc = (int)cudaGetDevice(&c->device))) break;
+        if ((rc = (int)cudaMalloc(&c->state, pz_state_bytes(n)))) break;
+        if ((rc = (int)cudaMalloc(&c->actions, (size_t)n * 2 * c->act_elem))) break;
+        if ((rc = (int)cudaMalloc(&c->obs, (size_t)n * 2 * PZ_OBS_WORDS * sizeof(int32_t)))) break;
+        if ((rc = (int)cudaMalloc(&c->reward, (size_t)n * 2 * c->rew_elem))) break;
+        if ((rc = (int)cudaMalloc(&c->done, (size_t)n))) break;
+        if ((rc = (int)cudaMalloc(&c->stats, PZ_NUM_STATS * sizeof(int64_t)))) break;
+        if ((rc = (int)cudaMemset(c->stats, 0, PZ_NUM_STATS * sizeof(int64_t)))) break;
+        c->streams.resize(chunks);
+        for (int k = 0; k < chunks && !rc; k++)
+            rc = (int)cudaStreamCreateWithFlags(&c->streams[k], cudaStreamNonBlocking);
+        if (rc) break;
+        if ((rc = pz_seed(c->state, n, base_seed, first_env, c->streams[0]))) break;
+        rc = (int)cudaStreamSynchronize(c->streams[0]);
+    } while (0);
+    if (rc) {
+        pz_host_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+
+int pz_host_reset(pz_host_ctx *c, int32_t *obs_host) {
+    if (!c) return PZ_E_BADARG;
+    const int chunks = (int)c->streams.size();
+    for (int k = 0; k < chunks; k++) {
+        const int64_t b = c->bounds[k], e = c->bounds[k + 1];
+        if (e <= b) continue;
+        int rc = pz::launch_reset(c->state, c->n, b, e, &c->cfg, obs_host ? c->obs : nullptr, c->streams[k]);
+        if (rc) return rc;
+        if (obs_host)
+            PZ_CUDA(cudaMemcpyAsync(obs_host + b * 2 * PZ_OBS_WORDS, c->obs + b * 2 * PZ_OBS_WORDS,
+                                    (size_t)(e - b) * 2 * PZ_OBS_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                    c->streams[k]));
+    }
+    return sync_all(c);
+}
+
+int pz_host_step(pz_host_ctx *c, const void *actions_host, int32_t *obs_host, void *reward_host,
+                 uint8_t *done_host) {
+    if (!c) return PZ_E_BADARG;
+    const bool both_ai = c->cfg.is_player1_computer && c->cfg.is_player2_computer;
+    if (!actions_host && !both_ai) return PZ_E_BADARG;
+    const int chunks = (int)c->streams.size();
+    for (int k = 0; k < chunks; k++) {
+        const int64_t b = c->bounds[k], e = c->bounds[k + 1];
+        if (e <= b) continue;
+        cudaStream_t s = c->streams[k];
+        const size_t cnt = (size_t)(e - b);
+        if (actions_host)
+            PZ_CUDA(cudaMemcpyAsync((char *)c->actions + (size_t)b * 2 * c->act_elem,
+                                    (const char *)actions_host + (size_t)b * 2 * c->act_elem, cnt * 2 * c->act_elem,
+                                    cudaMemcpyHostToDevice, s));
+        int rc = pz::launch_step(c->state, c->n, b, e, &c->cfg, actions_host ? c->actions : nullptr,
+                                 obs_host ? c->obs : nullptr, reward_host ? c->reward : nullptr,
+                                 done_host ? c->done : nullptr, c->stats, s);
+        if (rc) return rc;
+        if (obs_host)
+            PZ_CUDA(cudaMemcpyAsync(obs_host + b * 2 * PZ_OBS_WORDS, c->obs + b * 2 * PZ_OBS_WORDS,
+                                    cnt * 2 * PZ_OBS_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if (reward_host)
+            PZ_CUDA(cudaMemcpyAsync((char *)reward_host + (size_t)b * 2 * c->rew_elem,
+                                    (const char *)c->reward + (size_t)b * 2 * c->rew_elem, cnt * 2 * c->rew_elem,
+                                    cudaMemcpyDeviceToHost, s));
+        if (done_host) PZ_CUDA(cudaMemcpyAsync(done_host + b, c->done + b, cnt, cudaMemcpyDeviceToHost, s));
+    }
+    return sync_all(c);
+}
+
+int pz_host_stats(pz_host_ctx *c, int64_t stats_host[PZ_NUM_STATS]) {
+    if (!c || !stats_host) return PZ_E_BADARG;
+    int rc = sync_all(c);
+    if (rc) return rc;
+    PZ_CUDA(cudaMemcpy(stats_host, c->stats, PZ_NUM_STATS * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int32_t *pz_host_state_dev(pz_host_ctx *c) { return c ? c->state : nullptr; }
+
+void pz_host_destroy(pz_host_ctx *c) {
+    if (!c) return;
+    for (cudaStream_t s : c->streams)
+        if (s) cudaStreamDestroy(s);
+    cudaFree(c->state);
+    cudaFree(c->actions);
+    cudaFree(c->obs);
+    cudaFree(c->reward);
+    cudaFree(c->done);
+    cudaFree(c->stats);
+    delete c;
+}
+
+}  // extern "C"

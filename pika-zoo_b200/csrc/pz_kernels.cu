@@ -1,0 +1,613 @@
+// sm_100a kernels + C ABI (include/pikazoo_b200.h) of the batched Pikachu-Volleyball simulator.
+//
+//   pz_step_kernel     one frame per env per launch; HBM-bound: 2x128-bit state
+//                      loads, 2x128-bit state stores, observation rows staged in shared memory
+//                      and written with one bulk async copy (TMA engine, cp.async.bulk) per warp.
+//   pz_rollout_kernel  K frames per launch with the env and its PCG64 stream in registers.
+//   pz_reset_kernel / pz_seed_kernel / export / import.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+
+#include "../../include/pikazoo_b200.h"
+#include "pz_kernels.cuh"
+#include "pz_physics.cuh"
+
+namespace pz {
+
+constexpr int kThreads = 128;  // 4 warps; 4 x 8960 B of observation staging per CTA
+constexpr int kWarps = kThreads / 32;
+constexpr int kObsRow = 70;                      // int32 per env: [obs_p1 | obs_p2]
+constexpr int kWarpObsBytes = 32 * kObsRow * 4;  // 8960, multiple of 16
+
+struct KParams {
+    int32_t *state;
+    int64_t n;           // envs in the state buffer (SoA stride)
+    int64_t begin, end;  // env range processed by this launch (begin % 32 == 0)
+    const void *actions;
+    int32_t *obs;
+    void *reward;
+    uint8_t *done;
+    unsigned long long *stats;
+    StepCfg cfg;
+    int autoreset, simplify, shaped, act_dtype, rew_dtype;
+    int x_line, y_line;
+    // rollout only
+    int K, action_source;
+    uint64_t action_seed, first_env, frame0;
+    // RewardByBallPosition fused: table[agent][own base reward + 1][zone], evaluated on the host in
+    // double exactly as Python evaluates `int + float` (reward_by_ball_position.py:28-29)
+    double table[24];
+};
+
+// ---- observation output ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Whole warps write their 32 x 280 B of observations as ONE contiguous 8960-byte bulk copy
+// shared -> global issued by lane 0 (cp.async.bulk; no per-thread strided stores). Rows are staged
+// with 64-bit shared stores (row stride 280 B => conflict-free per half-warp).
+__device__ __forceinline__ void stage_obs_row(const Env &e, int *row) {
+    int u[35];
+    obs_values(e, u);
+    int2 *r2 = reinterpret_cast<int2 *>(row);
+#pragma unroll
+    for (int j = 0; j < 35; j++) r2[j] = make_int2(u[obs_src(2 * j)], u[obs_src(2 * j + 1)]);
+}
+
+__device__ __forceinline__ void bulk_store_issue(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(ssrc)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// Returns true if this lane issued a bulk copy it must wait for before the CTA's smem dies.
+__device__ __forceinline__ bool emit_obs(const Env &e, bool valid, int32_t *obs, int64_t env_idx, int64_t end,
+                                         int *warp_stage, int lane) {
+    const int64_t warp_first = env_idx - lane;
+    if (warp_first + 32 <= end) {  // warp-uniform: full warp
+        stage_obs_row(e, warp_stage + lane * kObsRow);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            bulk_store_issue(obs + warp_first * kObsRow, warp_stage, kWarpObsBytes);
+            return true;
+        }
+    } else if (valid) {  // ragged tail: plain 64-bit stores (rows are 8-byte aligned)
+        int u[35];
+        obs_values(e, u);
+        int2 *g = reinterpret_cast<int2 *>(obs + env_idx * kObsRow);
+#pragma unroll
+        for (int j = 0; j < 35; j++) g[j] = make_int2(u[obs_src(2 * j)], u[obs_src(2 * j + 1)]);
+    }
+    return false;
+}
+
+// ---- statistics ------------------------------------------------------------------------------------
+__device__ __forceinline__ void stat_add(unsigned long long *stats, int slot, unsigned v) {
+    if (v) atomicAdd(stats + slot, (unsigned long long)v);
+}
+
+// Episode-granular events only (rare), aggregated per warp before touching L2 atomics.
+__device__ __forceinline__ void accumulate_stats(unsigned long long *stats, const Env &e, bool terminated,
+                                                 bool was_reset, bool bad, bool frozen, int lane) {
+    const unsigned tm = __ballot_sync(kFullMask, terminated);
+    const unsigned rm = __ballot_sync(kFullMask, was_reset);
+    const unsigned bm = __ballot_sync(kFullMask, bad);
+    const unsigned fm = __ballot_sync(kFullMask, frozen);
+    if ((tm | rm | bm | fm) == 0) return;
+    unsigned frames = 0, s1 = 0, s2 = 0, w1 = 0;
+    if (tm) {
+        frames = __reduce_add_sync(kFullMask, terminated ? (unsigned)e.ep_frames : 0u);
+        s1 = __reduce_add_sync(kFullMask, terminated ? (unsigned)e.score[0] : 0u);
+        s2 = __reduce_add_sync(kFullMask, terminated ? (unsigned)e.score[1] : 0u);
+        w1 = __popc(__ballot_sync(kFullMask, terminated && e.score[0] > e.score[1]));
+    }
+    if (lane == 0) {
+        stat_add(stats, PZ_STAT_EPISODES, __popc(tm));
+        stat_add(stats, PZ_STAT_EPISODE_FRAMES, frames);
+        stat_add(stats, PZ_STAT_P1_WINS, w1);
+        stat_add(stats, PZ_STAT_P2_WINS, __popc(tm) - w1);
+        stat_add(stats, PZ_STAT_P1_POINTS, s1);
+        stat_add(stats, PZ_STAT_P2_POINTS, s2);
+        stat_add(stats, PZ_STAT_RESETS, __popc(rm));
+        stat_add(stats, PZ_STAT_BAD_ACTIONS, __popc(bm));
+        stat_add(stats, PZ_STAT_FROZEN, __popc(fm));
+    }
+}
+
+__device__ __forceinline__ void load_actions(const KParams &P, int64_t i, int &a1, int &a2) {
+    if (P.act_dtype == PZ_ACT_I32) {
+        int2 a = reinterpret_cast<const int2 *>(P.actions)[i];
+        a1 = a.x;
+        a2 = a.y;
+    } else if (P.act_dtype == PZ_ACT_I64) {
+        longlong2 a = reinterpret_cast<const longlong2 *>(P.actions)[i];
+        a1 = (a.x < -1 || a.x > 1000) ? -1 : (int)a.x;
+        a2 = (a.y < -1 || a.y > 1000) ? -1 : (int)a.y;
+    } else {
+        uchar2 a = reinterpret_cast<const uchar2 *>(P.actions)[i];
+        a1 = a.x;
+        a2 = a.y;
+    }
+}
+
+// RewardByBallPosition zone (reward_by_ball_position.py:22-26) from the post-step ball
+__device__ __forceinline__ int ball_zone(const Env &e, const KParams &P) {
+    return (e.b.y > P.y_line ? 1 : 0) + 2 * (e.b.x >= P.x_line ? 1 : 0);
+}
+
+__device__ __forceinline__ void store_reward(const KParams &P, int64_t i, const Env &e, int base, bool stepped) {
+    double r1 = 0.0, r2 = 0.0;
+    if (stepped) {
+        if (P.shaped) {
+            const int z = ball_zone(e, P);
+            r1 = P.table[(base + 1) * 4 + z];
+            r2 = P.table[12 + (1 - base) * 4 + z];
+        } else {
+            r1 = (double)base;
+            r2 = (double)(-base);
+        }
+    }
+    if (P.rew_dtype == PZ_REW_F32)
+        reinterpret_cast<float2 *>(P.reward)[i] = make_float2((float)r1, (float)r2);
+    else
+        reinterpret_cast<double2 *>(P.reward)[i] = make_double2(r1, r2);
+}
+
+// ---- per-step kernel ---------------------------------------------------------------------------
+template <int AI_MASK>
+__global__ void __launch_bounds__(kThreads) pz_step_kernel(const __grid_constant__ KParams P) {
+    __shared__ __align__(128) int stage[kWarps][32 * kObsRow];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = P.begin + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool valid = i < P.end;
+
+    DrawCtx d;
+    d.s = state_ptrs(P.state, P.n);
+    d.idx = i;
+    d.r.loaded = false;
+    d.r.dirty = false;
+    Env e;
+    int a1 = 0, a2 = 0;
+    if (valid) {
+        load_env(e, d.s, i);
+        if (P.actions) load_actions(P, i, a1, a2);
+        if (AI_MASK != 0) rng_load(d.r, d.s, i);  // computer players draw on most frames
+    } else {
+        fresh_env(e);
+        e.game_ended = 1;
+    }
+
+    const bool run = valid && !e.game_ended;
+    const bool do_reset = valid && e.game_ended && P.autoreset;
+    const bool frozen = valid && e.game_ended && !P.autoreset;
+    const unsigned mask = __ballot_sync(kFullMask, run);
+    int base = 0;
+    bool bad = false;
+    if (run) {
+        bool bad1, bad2;
+        uint32_t k1, k2;
+        if (P.simplify) {
+            k1 = decode_keys<0, true>(a1, bad1);
+            k2 = decode_keys<1, true>(a2, bad2);
+        } else {
+            k1 = decode_keys<0, false>(a1, bad1);
+            k2 = decode_keys<1, false>(a2, bad2);
+        }
+        bad = bad1 || bad2;
+        base = step_frame<AI_MASK>(mask, e, d, P.cfg, k1, k2);
+    } else if (do_reset) {
+        reset_env(e, d, P.cfg);
+    }
+
+    bool pending = false;
+    if (P.obs) pending = emit_obs(e, valid, P.obs, i, P.end, stage[warp], lane);
+    if (valid) {
+        if (run || do_reset) {
+            store_env(e, d.s, i);
+            if (d.r.dirty) rng_store(d.r, d.s, i);
+        }
+        if (P.reward) store_reward(P, i, e, base, run);
+        if (P.done) P.done[i] = (uint8_t)((run && e.game_ended) || frozen);
+    }
+    if (P.stats) {
+        accumulate_stats(P.stats, e, run && e.game_ended, do_reset, bad, frozen, lane);
+        if (i == P.begin) atomicAdd(P.stats + PZ_STAT_CALLS, (unsigned long long)(P.end - P.begin));
+    }
+    if (pending) bulk_store_wait_read();
+}
+
+// ---- K-frame register-resident rollout -------------------------------------------------------
+template <int AI_MASK>
+__global__ void __launch_bounds__(kThreads) pz_rollout_kernel(const __grid_constant__ KParams P) {
+    __shared__ __align__(128) int stage[kWarps][32 * kObsRow];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = P.begin + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool valid = i < P.end;
+
+    DrawCtx d;
+    d.s = state_ptrs(P.state, P.n);
+    d.idx = i;
+    d.r.loaded = false;
+    d.r.dirty = false;
+    Env e;
+    if (valid) {
+        load_env(e, d.s, i);
+        rng_load(d.r, d.s, i);
+    } else {
+        fresh_env(e);
+    }
+    const uint32_t n_actions = P.simplify ? 13u : 18u;
+    const uint64_t genv = P.first_env + (uint64_t)i;
+
+    // episode-granular statistics accumulated per thread, reduced once at the end
+    unsigned st_ep = 0, st_frames = 0, st_w1 = 0, st_s1 = 0, st_s2 = 0, st_resets = 0;
+
+#pragma unroll 1
+    for (int k = 0; k < P.K; k++) {
+        const bool run = valid && !e.game_ended;
+        const unsigned mask = __ballot_sync(kFullMask, run);
+        if (run) {
+            uint32_t k1 = 0, k2 = 0;
+            if (P.action_source == PZ_ACTIONS_SYNTH) {
+                bool b1, b2;
+                const int a1 = synth_action(P.action_seed, genv, P.frame0 + (uint64_t)k, 0, n_actions);
+                const int a2 = synth_action(P.action_seed, genv, P.frame0 + (uint64_t)k, 1, n_actions);
+                if (P.simplify) {
+                    k1 = decode_keys<0, true>(a1, b1);
+                    k2 = decode_keys<1, true>(a2, b2);
+                } else {
+                    k1 = decode_keys<0, false>(a1, b1);
+                    k2 = decode_keys<1, false>(a2, b2);
+                }
+            }
+            step_frame<AI_MASK>(mask, e, d, P.cfg, k1, k2);
+            if (e.game_ended) {
+                st_ep += 1;
+                st_frames += (unsigned)e.ep_frames;
+                st_w1 += (e.score[0] > e.score[1]) ? 1u : 0u;
+                st_s1 += (unsigned)e.score[0];
+                st_s2 += (unsigned)e.score[1];
+            }
+        } else if (valid) {
+            reset_env(e, d, P.cfg);
+            st_resets += 1;
+        }
+    }
+
+    bool pending = false;
+    if (P.obs) pending = emit_obs(e, valid, P.obs, i, P.end, stage[warp], lane);
+    if (valid) {
+        store_env(e, d.s, i);
+        if (d.r.dirty) rng_store(d.r, d.s, i);
+    }
+    if (P.stats) {
+        const unsigned ep = __reduce_add_sync(kFullMask, st_ep);
+        const unsigned rs = __reduce_add_sync(kFullMask, st_resets);
+        if (ep | rs) {
+            const unsigned fr = __reduce_add_sync(kFullMask, st_frames);
+            const unsigned w1 = __reduce_add_sync(kFullMask, st_w1);
+            const unsigned s1 = __reduce_add_sync(kFullMask, st_s1);
+            const unsigned s2 = __reduce_add_sync(kFullMask, st_s2);
+            if (lane == 0) {
+                stat_add(P.stats, PZ_STAT_EPISODES, ep);
+                stat_add(P.stats, PZ_STAT_EPISODE_FRAMES, fr);
+                stat_add(P.stats, PZ_STAT_P1_WINS, w1);
+                stat_add(P.stats, PZ_STAT_P2_WINS, ep - w1);
+                stat_add(P.stats, PZ_STAT_P1_POINTS, s1);
+                stat_add(P.stats, PZ_STAT_P2_POINTS, s2);
+                stat_add(P.stats, PZ_STAT_RESETS, rs);
+            }
+        }
+        if (i == P.begin)
+            atomicAdd(P.stats + PZ_STAT_CALLS, (unsigned long long)(P.end - P.begin) * (unsigned long long)P.K);
+    }
+    if (pending) bulk_store_wait_read();
+}
+
+// ---- reset / seed / export / import -----------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) pz_reset_kernel(const __grid_constant__ KParams P) {
+    __shared__ __align__(128) int stage[kWarps][32 * kObsRow];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = P.begin + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool valid = i < P.end;
+    DrawCtx d;
+    d.s = state_ptrs(P.state, P.n);
+    d.idx = i;
+    d.r.loaded = false;
+    d.r.dirty = false;
+    Env e;
+    if (valid) {
+        load_env(e, d.s, i);
+        reset_env(e, d, P.cfg);
+        store_env(e, d.s, i);
+        if (d.r.dirty) rng_store(d.r, d.s, i);
+    } else {
+        fresh_env(e);
+    }
+    bool pending = false;
+    if (P.obs) pending = emit_obs(e, valid, P.obs, i, P.end, stage[warp], lane);
+    if (pending) bulk_store_wait_read();
+}
+
+__global__ void __launch_bounds__(kThreads)
+    pz_seed_kernel(int32_t *state, int64_t n, uint64_t base_seed, uint64_t first_env, const uint64_t *seeds) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    StatePtrs s = state_ptrs(state, n);
+    Env e;
+    fresh_env(e);
+    Rng r;
+    pcg64_seed(seeds ? seeds[i] : base_seed + first_env + (uint64_t)i, r);
+    store_env(e, s, i);
+    rng_store(r, s, i);
+    int4 ic;
+    ic.x = (int)(uint32_t)r.inc_lo;
+    ic.y = (int)(uint32_t)(r.inc_lo >> 32);
+    ic.z = (int)(uint32_t)r.inc_hi;
+    ic.w = (int)(uint32_t)(r.inc_hi >> 32);
+    s.g3[i] = ic;
+}
+
+// unpacked layout = oracle/pika_oracle.h pk_env (53 words)
+__global__ void __launch_bounds__(kThreads) pz_export_kernel(const int32_t *state, int64_t n, int32_t *out) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    StatePtrs s = state_ptrs(const_cast<int32_t *>(state), n);
+    Env e;
+    load_env(e, s, i);
+    int32_t *o = out + i * PZ_UNPACKED_WORDS;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const Player &p = e.p[k];
+        int32_t *q = o + 13 * k;
+        q[0] = p.x, q[1] = p.y, q[2] = p.yv, q[3] = p.state, q[4] = p.frame, q[5] = p.delay, q[6] = p.arm;
+        q[7] = p.dive, q[8] = p.lying, q[9] = p.coll, q[10] = p.bold, q[11] = p.standby, q[12] = p.keyprev;
+    }
+    const Ball &b = e.b;
+    int32_t *q = o + 26;
+    q[0] = b.x, q[1] = b.y, q[2] = b.xv, q[3] = b.yv, q[4] = b.px, q[5] = b.py, q[6] = b.ppx, q[7] = b.ppy;
+    q[8] = b.pow, q[9] = b.land, q[10] = b.punch;
+    o[37] = e.score[0], o[38] = e.score[1], o[39] = e.round_ended, o[40] = e.game_ended, o[41] = e.p2serve;
+    const int4 st = s.g2[i], ic = s.g3[i];
+    o[42] = st.x, o[43] = st.y, o[44] = st.z, o[45] = st.w;
+    o[46] = ic.x, o[47] = ic.y, o[48] = ic.z, o[49] = ic.w;
+    o[50] = e.has32;
+    o[51] = (int32_t)s.u[i];
+    o[52] = e.ep_frames;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// Values outside the packed field ranges are clamped (they cannot occur in a state produced
+// by the simulator itself).
+__global__ void __launch_bounds__(kThreads) pz_import_kernel(int32_t *state, int64_t n, const int32_t *in) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    StatePtrs s = state_ptrs(state, n);
+    const int32_t *o = in + i * PZ_UNPACKED_WORDS;
+    Env e;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        Player &p = e.p[k];
+        const int32_t *q = o + 13 * k;
+        p.x = clampi(q[0], 0, 511), p.y = clampi(q[1], 0, 255), p.yv = clampi(q[2], -32, 31);
+        p.state = clampi(q[3], 0, 7), p.frame = clampi(q[4], 0, 7), p.delay = clampi(q[5], 0, 7);
+        p.arm = q[6] > 0 ? 1 : -1, p.dive = clampi(q[7], -1, 1), p.lying = clampi(q[8], -4, 3);
+        p.coll = q[9] != 0, p.bold = clampi(q[10], 0, 7), p.standby = q[11] != 0, p.keyprev = q[12] != 0;
+    }
+    Ball &b = e.b;
+    const int32_t *q = o + 26;
+    b.x = clampi(q[0], 0, 511), b.y = clampi(q[1], 0, 255), b.xv = clampi(q[2], -32, 31);
+    b.yv = clampi(q[3], -32768, 32767), b.px = clampi(q[4], 0, 511), b.py = clampi(q[5], 0, 255);
+    b.ppx = clampi(q[6], 0, 511), b.ppy = clampi(q[7], 0, 255), b.pow = q[8] != 0;
+    b.land = clampi(q[9], 0, 511), b.punch = clampi(q[10], 0, 511);
+    e.score[0] = clampi(o[37], 0, 1023), e.score[1] = clampi(o[38], 0, 1023);
+    e.round_ended = o[39] != 0, e.game_ended = o[40] != 0, e.p2serve = o[41] != 0;
+    e.has32 = o[50] != 0;
+    e.ep_frames = o[52];
+    store_env(e, s, i);
+    s.g2[i] = make_int4(o[42], o[43], o[44], o[45]);
+    s.g3[i] = make_int4(o[46], o[47], o[48], o[49]);
+    s.u[i] = (uint32_t)o[51];
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+static int check_config(const pz_config *c) {
+    if (!c) return PZ_E_BADARG;
+    if (c->winning_score < 1 || c->winning_score > 1023) return PZ_E_BADCONFIG;
+    if (c->serve < 0 || c->serve > 2) return PZ_E_BADCONFIG;
+    if (c->action_dtype < 0 || c->action_dtype > 2) return PZ_E_BADCONFIG;
+    if (c->reward_dtype < 0 || c->reward_dtype > 1) return PZ_E_BADCONFIG;
+    return 0;
+}
+
+static void fill_params(KParams &P, int32_t *state, int64_t n, const pz_config *c) {
+    memset(&P, 0, sizeof(P));
+    P.state = state;
+    P.n = n;
+    P.begin = 0;
+    P.end = n;
+    P.cfg.winning_score = c->winning_score;
+    P.cfg.serve = c->serve;
+    P.autoreset = c->autoreset != 0;
+    P.simplify = c->simplify_action != 0;
+    P.shaped = c->reward_by_ball_position != 0;
+    P.act_dtype = c->action_dtype;
+    P.rew_dtype = c->reward_dtype;
+    P.x_line = c->x_line;
+    P.y_line = c->y_line;
+    for (int agent = 0; agent < 2; agent++)
+        for (int b = 0; b < 3; b++)
+            for (int z = 0; z < 4; z++) {
+                // Python: rews[agent] (int) += additional_reward[agent*4 + zone]
+                double r = (double)(b - 1);
+                if (c->reward_by_ball_position) r = r + c->additional_reward[agent * 4 + z];
+                P.table[agent * 12 + b * 4 + z] = r;
+            }
+}
+
+static inline int ai_mask(const pz_config *c) {
+    return (c->is_player1_computer ? 1 : 0) | (c->is_player2_computer ? 2 : 0);
+}
+
+static inline unsigned grid_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int launch_status() {
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? 0 : (int)err;
+}
+
+int launch_reset(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const pz_config *cfg, int32_t *obs_dev,
+                 cudaStream_t stream) {
+    if (!state_dev || n < 0 || begin < 0 || end > n || begin > end || (begin & 31)) return PZ_E_BADARG;
+    if (int rc = check_config(cfg)) return rc;
+    if (!aligned16(state_dev) || !aligned16(obs_dev)) return PZ_E_ALIGN;
+    if (end == begin) return 0;
+    KParams P;
+    fill_params(P, state_dev, n, cfg);
+    P.begin = begin;
+    P.end = end;
+    P.obs = obs_dev;
+    pz_reset_kernel<<<grid_for(end - begin), kThreads, 0, stream>>>(P);
+    return launch_status();
+}
+
+int launch_step(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const pz_config *cfg,
+                const void *actions_dev, int32_t *obs_dev, void *reward_dev, uint8_t *done_dev, int64_t *stats_dev,
+                cudaStream_t st) {
+    if (!state_dev || n < 0 || begin < 0 || end > n || begin > end || (begin & 31)) return PZ_E_BADARG;
+    if (int rc = check_config(cfg)) return rc;
+    const int am = ai_mask(cfg);
+    if (!actions_dev && am != 3) return PZ_E_BADARG;  // actions may be omitted only when both play themselves
+    if (!aligned16(state_dev) || !aligned16(obs_dev) || !aligned16(actions_dev) || !aligned16(reward_dev))
+        return PZ_E_ALIGN;
+    if (end == begin) return 0;
+    KParams P;
+    fill_params(P, state_dev, n, cfg);
+    P.begin = begin;
+    P.end = end;
+    P.actions = actions_dev;
+    P.obs = obs_dev;
+    P.reward = reward_dev;
+    P.done = done_dev;
+    P.stats = reinterpret_cast<unsigned long long *>(stats_dev);
+    const unsigned grid = grid_for(end - begin);
+    switch (am) {
+        case 0: pz_step_kernel<0><<<grid, kThreads, 0, st>>>(P); break;
+        case 1: pz_step_kernel<1><<<grid, kThreads, 0, st>>>(P); break;
+        case 2: pz_step_kernel<2><<<grid, kThreads, 0, st>>>(P); break;
+        default: pz_step_kernel<3><<<grid, kThreads, 0, st>>>(P); break;
+    }
+    return launch_status();
+}
+
+}  // namespace pz
+
+using namespace pz;
+
+extern "C" {
+
+int pz_version(void) { return PZ_VERSION; }
+int pz_state_words(void) { return PZ_STATE_WORDS; }
+int pz_unpacked_words(void) { return PZ_UNPACKED_WORDS; }
+size_t pz_state_bytes(int64_t n) { return n < 0 ? 0 : (size_t)n * PZ_STATE_WORDS * sizeof(int32_t); }
+
+const char *pz_strerror(int code) {
+    switch (code) {
+        case 0: return "success";
+        case PZ_E_BADARG: return "pikazoo_b200: bad argument";
+        case PZ_E_BADCONFIG: return "pikazoo_b200: bad config (winning_score must be in [1,1023]; serve/dtype codes)";
+        case PZ_E_ALIGN: return "pikazoo_b200: state/obs pointers must be 16-byte aligned";
+        case PZ_E_NODEVICE: return "pikazoo_b200: no usable sm_100 device";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "pikazoo_b200: unknown error";
+    }
+}
+
+void pz_default_config(pz_config *c) {
+    if (!c) return;
+    memset(c, 0, sizeof(*c));
+    c->winning_score = 15;
+    c->serve = PZ_SERVE_WINNER;
+    c->x_line = 216;
+    c->y_line = 176;
+    c->autoreset = 1;
+}
+
+int pz_seed(int32_t *state_dev, int64_t n, uint64_t base_seed, uint64_t first_env, void *stream) {
+    if (!state_dev || n < 0) return PZ_E_BADARG;
+    if (!aligned16(state_dev)) return PZ_E_ALIGN;
+    if (n == 0) return 0;
+    pz_seed_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state_dev, n, base_seed, first_env, nullptr);
+    return launch_status();
+}
+
+int pz_seed_array(int32_t *state_dev, int64_t n, const uint64_t *seeds_dev, void *stream) {
+    if (!state_dev || !seeds_dev || n < 0) return PZ_E_BADARG;
+    if (!aligned16(state_dev)) return PZ_E_ALIGN;
+    if (n == 0) return 0;
+    pz_seed_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state_dev, n, 0, 0, seeds_dev);
+    return launch_status();
+}
+
+int pz_reset(int32_t *state_dev, int64_t n, const pz_config *cfg, int32_t *obs_dev, void *stream) {
+    return pz::launch_reset(state_dev, n, 0, n, cfg, obs_dev, (cudaStream_t)stream);
+}
+
+int pz_step(int32_t *state_dev, int64_t n, const pz_config *cfg, const void *actions_dev, int32_t *obs_dev,
+            void *reward_dev, uint8_t *done_dev, int64_t *stats_dev, void *stream) {
+    return pz::launch_step(state_dev, n, 0, n, cfg, actions_dev, obs_dev, reward_dev, done_dev, stats_dev,
+                           (cudaStream_t)stream);
+}
+
+int pz_rollout(int32_t *state_dev, int64_t n, const pz_config *cfg, int32_t K, int32_t action_source,
+               uint64_t action_seed, uint64_t first_env, uint64_t frame0, int32_t *obs_dev, int64_t *stats_dev,
+               void *stream) {
+    if (!state_dev || n < 0 || K < 1) return PZ_E_BADARG;
+    if (action_source != PZ_ACTIONS_NOOP && action_source != PZ_ACTIONS_SYNTH) return PZ_E_BADARG;
+    if (int rc = check_config(cfg)) return rc;
+    if (!aligned16(state_dev) || !aligned16(obs_dev)) return PZ_E_ALIGN;
+    if (n == 0) return 0;
+    KParams P;
+    fill_params(P, state_dev, n, cfg);
+    P.obs = obs_dev;
+    P.stats = reinterpret_cast<unsigned long long *>(stats_dev);
+    P.K = K;
+    P.action_source = action_source;
+    P.action_seed = action_seed;
+    P.first_env = first_env;
+    P.frame0 = frame0;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (ai_mask(cfg)) {
+        case 0: pz_rollout_kernel<0><<<grid_for(n), kThreads, 0, st>>>(P); break;
+        case 1: pz_rollout_kernel<1><<<grid_for(n), kThreads, 0, st>>>(P); break;
+        case 2: pz_rollout_kernel<2><<<grid_for(n), kThreads, 0, st>>>(P); break;
+        default: pz_rollout_kernel<3><<<grid_for(n), kThreads, 0, st>>>(P); break;
+    }
+    return launch_status();
+}
+
+int pz_export_state(const int32_t *state_dev, int64_t n, int32_t *unpacked_dev, void *stream) {
+    if (!state_dev || !unpacked_dev || n < 0) return PZ_E_BADARG;
+    if (!aligned16(state_dev)) return PZ_E_ALIGN;
+    if (n == 0) return 0;
+    pz_export_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state_dev, n, unpacked_dev);
+    return launch_status();
+}
+
+int pz_import_state(int32_t *state_dev, int64_t n, const int32_t *unpacked_dev, void *stream) {
+    if (!state_dev || !unpacked_dev || n < 0) return PZ_E_BADARG;
+    if (!aligned16(state_dev)) return PZ_E_ALIGN;
+    if (n == 0) return 0;
+    pz_import_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state_dev, n, unpacked_dev);
+    return launch_status();
+}
+
+}  // extern "C"

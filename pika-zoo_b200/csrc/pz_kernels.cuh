@@ -1,0 +1,19 @@
+// Internal launch interface shared by the C ABI (pz_kernels.cu) and the host-buffer path (pz_host.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/pikazoo_b200.h"
+
+namespace pz {
+
+// Step / reset the env range [begin, end) of a state buffer holding n envs (begin % 32 == 0).
+// actions/obs/reward/done are the base pointers of the full [n]-sized arrays.
+int launch_step(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const pz_config *cfg,
+                const void *actions_dev, int32_t *obs_dev, void *reward_dev, uint8_t *done_dev, int64_t *stats_dev,
+                cudaStream_t stream);
+int launch_reset(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const pz_config *cfg, int32_t *obs_dev,
+                 cudaStream_t stream);
+
+}  // namespace pz

@@ -1,0 +1,505 @@
+// One frame of one env, entirely in registers: the device form of
+//   raw_env.step / reset                 pikazoo/env/pikazoo_env.py:149-248
+//   PikaUserInput.get_input              pikazoo/env/physics.py:59-99
+//   physics_engine and its callees       pikazoo/env/physics.py:280-884
+// One thread owns one env. The divergent trajectory-simulation loops and the computer's
+// power-hit search are written as warp-collective loops over the mask of lanes that step
+// this frame (warp votes keep the warp converged; a lane that has finished idles predicated
+// instead of forcing a reconvergence stack).
+#pragma once
+#include "pz_rng.cuh"
+
+namespace pz {
+
+constexpr unsigned kFullMask = 0xFFFFFFFFu;
+
+__device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }
+
+// Per-launch constants (uniform over the grid)
+struct StepCfg {
+    int winning_score;
+    int serve;  // PZ_SERVE_*
+};
+
+// Lazily loaded PCG64 stream of the env owned by this thread.
+struct DrawCtx {
+    Rng r;
+    StatePtrs s;
+    int64_t idx;
+    __device__ __forceinline__ void ensure() {
+        if (!r.loaded) rng_load(r, s, idx);
+    }
+    template <uint32_t HIGH>
+    __device__ __forceinline__ int integers(int &has32) {
+        ensure();
+        return rng_integers<HIGH>(r, has32);
+    }
+};
+
+// ---- action decode -------------------------------------------------------------------------
+// action_key_map (pikazoo_env.py:119-141) as key-bit masks: bit0 left, bit1 right, bit2 up,
+// bit3 down, bit4 power_hit. Entry 0 is all-zero, entries 1..12 / 13..17 are packed 5 bits each.
+constexpr uint32_t kL = 1, kR = 2, kU = 4, kD = 8, kP = 16;
+constexpr uint32_t kKeyMap[18] = {0,       kP,      kU,      kR,           kL,           kD,
+                                  kR | kU, kL | kU, kR | kD, kL | kD,      kU | kP,      kR | kP,
+                                  kL | kP, kD | kP, kR | kU | kP, kL | kU | kP, kR | kD | kP, kL | kD | kP};
+// SimplifyAction.action_map (simplify_action.py:16-19)
+constexpr int kSimplify[2][13] = {{0, 1, 2, 3, 4, 6, 7, 10, 11, 12, 13, 14, 16},
+                                  {0, 1, 2, 4, 3, 7, 6, 10, 12, 11, 13, 15, 17}};
+
+__host__ __device__ constexpr uint64_t pack_keys_18_lo() {
+    uint64_t v = 0;
+    for (int a = 1; a <= 12; a++) v |= (uint64_t)kKeyMap[a] << (5 * (a - 1));
+    return v;
+}
+__host__ __device__ constexpr uint64_t pack_keys_18_hi() {
+    uint64_t v = 0;
+    for (int a = 13; a <= 17; a++) v |= (uint64_t)kKeyMap[a] << (5 * (a - 13));
+    return v;
+}
+__host__ __device__ constexpr uint64_t pack_keys_13(int agent) {
+    uint64_t v = 0;
+    for (int a = 1; a <= 12; a++) v |= (uint64_t)kKeyMap[kSimplify[agent][a]] << (5 * (a - 1));
+    return v;
+}
+
+// Returns the 5 key bits of `action` for player I; *bad is set when the action is outside
+// the action space (the reference would raise IndexError; here it is counted and treated as 0).
+template <int I, bool SIMPLIFY>
+__device__ __forceinline__ uint32_t decode_keys(int action, bool &bad) {
+    constexpr int n_actions = SIMPLIFY ? 13 : 18;
+    bad = (unsigned)action >= (unsigned)n_actions;
+    if (bad || action == 0) return 0;
+    if (SIMPLIFY) {
+        constexpr uint64_t t = pack_keys_13(I);
+        return (uint32_t)(t >> (5 * (action - 1))) & 31u;
+    } else {
+        constexpr uint64_t lo = pack_keys_18_lo(), hi = pack_keys_18_hi();
+        return action <= 12 ? ((uint32_t)(lo >> (5 * (action - 1))) & 31u)
+                            : ((uint32_t)(hi >> (5 * (action - 13))) & 31u);
+    }
+}
+
+struct Input {
+    int xdir, ydir, power;
+};
+
+// PikaUserInput.get_input, physics.py:59-99 (rows are 5 wide: down_right_key is None)
+__device__ __forceinline__ Input get_input(Player &p, uint32_t keys) {
+    Input in;
+    in.xdir = (keys & kL) ? -1 : ((keys & kR) ? 1 : 0);
+    in.ydir = (keys & kU) ? -1 : ((keys & kD) ? 1 : 0);
+    int down = (keys & kP) ? 1 : 0;
+    in.power = (down && !p.keyprev) ? 1 : 0;
+    p.keyprev = down;
+    return in;
+}
+
+// ---- round / game initialisation -------------------------------------------------------------
+// Player.initialize_for_new_round, physics.py:181-218
+template <int I>
+__device__ __forceinline__ void player_new_round(Env &e, DrawCtx &d) {
+    Player &p = e.p[I];
+    p.x = I ? kGroundWidth - 36 : 36;
+    p.y = kPlayerGroundY;
+    p.yv = 0;
+    p.coll = 0;
+    p.state = 0;
+    p.frame = 0;
+    p.arm = 1;
+    p.delay = 0;
+    p.bold = d.integers<5>(e.has32);
+}
+
+// Ball.initialize_for_new_round (physics.py:258-277) with raw_env.get_server (pikazoo_env.py:242-248)
+__device__ __forceinline__ void new_round(Env &e, DrawCtx &d, const StepCfg &c) {
+    player_new_round<0>(e, d);
+    player_new_round<1>(e, d);
+    int p2_serves;
+    if (c.serve == 0)
+        p2_serves = e.p2serve;
+    else if (c.serve == 2)
+        p2_serves = d.integers<2>(e.has32) == 0;
+    else
+        p2_serves = ((e.score[0] + e.score[1]) & 1);
+    Ball &b = e.b;
+    b.x = p2_serves ? kGroundWidth - 56 : 56;
+    b.y = 0;
+    b.xv = 0;
+    b.yv = 1;
+    b.pow = 0;
+}
+
+// raw_env.reset, pikazoo_env.py:149-173 — on a live object: everything not assigned here
+// carries over (previous positions, landing point, diving direction, ..., the RNG stream).
+__device__ __forceinline__ void reset_env(Env &e, DrawCtx &d, const StepCfg &c) {
+    e.game_ended = 0;
+    e.round_ended = 0;
+    e.p2serve = 0;
+    e.score[0] = 0;
+    e.score[1] = 0;
+    new_round(e, d, c);
+    e.ep_frames = 0;
+}
+
+// Constructor defaults of a fresh reference env (physics.py:43-57,143-171,224-249;
+// pikazoo_env.py:100-111). Boldness is 0 until reset() draws it.
+__device__ __forceinline__ void fresh_env(Env &e) {
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        Player &p = e.p[i];
+        p.x = i ? kGroundWidth - 36 : 36;
+        p.y = kPlayerGroundY;
+        p.yv = 0;
+        p.state = 0;
+        p.frame = 0;
+        p.delay = 0;
+        p.arm = 1;
+        p.dive = 0;
+        p.lying = -1;
+        p.coll = 0;
+        p.bold = 0;
+        p.standby = 0;
+        p.keyprev = 0;
+    }
+    Ball &b = e.b;
+    b.x = 56;
+    b.y = 0;
+    b.xv = 0;
+    b.yv = 1;
+    b.px = b.py = b.ppx = b.ppy = 0;
+    b.pow = 0;
+    b.land = 0;
+    b.punch = 0;
+    e.score[0] = e.score[1] = 0;
+    e.round_ended = e.game_ended = e.p2serve = 0;
+    e.has32 = 0;
+    e.ep_frames = 0;
+}
+
+// ---- ball ------------------------------------------------------------------------------------
+// process_collision_between_ball_and_world_and_set_ball_position, physics.py:359-436
+__device__ __forceinline__ bool ball_world(Ball &b) {
+    b.ppx = b.px;
+    b.ppy = b.py;
+    b.px = b.x;
+    b.py = b.y;
+    int fx = b.x + b.xv;
+    if (fx < kBallRadius || fx > kGroundWidth) b.xv = -b.xv;  // asymmetric on purpose (:392-404)
+    if (b.y + b.yv < 0) b.yv = 1;
+    if (iabs(b.x - kGroundHalfWidth) < kNetHalfWidth && b.y > kNetTopTopY) {
+        if (b.y <= kNetTopBottomY) {
+            if (b.yv > 0) b.yv = -b.yv;
+        } else {
+            b.xv = (b.x < kGroundHalfWidth) ? -iabs(b.xv) : iabs(b.xv);
+        }
+    }
+    int fy = b.y + b.yv;
+    if (fy > kBallGroundY) {
+        b.yv = -b.yv;
+        b.punch = b.x;
+        b.y = kBallGroundY;
+        return true;
+    }
+    b.y = fy;
+    b.x += b.xv;
+    b.yv += 1;
+    return false;
+}
+
+// Trajectory simulation shared by calculate_expected_landing_point_x_for (physics.py:643-686,
+// POWER = false: net top test is the strict y < 192) and expected_landing_point_x_when_power_hit
+// (physics.py:847-884, POWER = true: the whole net zone only bounces yv).
+// Warp-collective over `mask`: every lane of `mask` must call it; lanes with active == false
+// idle. Trip count 1..1000 per lane; the warp leaves when its slowest lane lands.
+template <bool POWER>
+__device__ __forceinline__ int simulate_landing_x(unsigned mask, int x, int y, int xv, int yv, bool active) {
+    int it = 0;
+    while (__any_sync(mask, active)) {
+        if (active) {
+            it += 1;
+            int fx = x + xv;
+            if (fx < kBallRadius || fx > kGroundWidth) xv = -xv;
+            if (y + yv < 0) yv = 1;
+            if (iabs(x - kGroundHalfWidth) < kNetHalfWidth && y > kNetTopTopY) {
+                if (POWER) {
+                    if (yv > 0) yv = -yv;
+                } else {
+                    if (y < kNetTopBottomY) {
+                        if (yv > 0) yv = -yv;
+                    } else {
+                        xv = (x < kGroundHalfWidth) ? -iabs(xv) : iabs(xv);
+                    }
+                }
+            }
+            y += yv;
+            if (y > kBallGroundY || it >= kLoopLimit) {
+                active = false;
+            } else {
+                x += xv;
+                yv += 1;
+            }
+        }
+    }
+    return x;
+}
+
+// ---- computer player ---------------------------------------------------------------------------
+// let_computer_decide_user_input (physics.py:689-771) + decide_whether_input_power_hit (:774-817).
+// Warp-collective over `mask`.
+template <int I>
+__device__ __forceinline__ void computer_decide(unsigned mask, Env &e, DrawCtx &d, Input &in) {
+    Player &p = e.p[I];
+    const Player &o = e.p[1 - I];
+    const Ball &b = e.b;
+    constexpr int left_boundary = I * kGroundHalfWidth;
+    constexpr int right_boundary = (I + 1) * kGroundHalfWidth;
+    constexpr int far_boundary = I * kGroundWidth + kGroundHalfWidth;  // :718, :801
+
+    in.xdir = 0;
+    in.ydir = 0;
+    in.power = 0;
+    const int dx = iabs(b.x - p.x);
+
+    int virt = b.land;
+    if (dx > 100 && iabs(b.xv) < p.bold + 5) {
+        if ((b.land <= left_boundary || b.land >= far_boundary) && p.standby == 0)
+            virt = left_boundary + kGroundHalfWidth / 2;
+    }
+    if (iabs(virt - p.x) > p.bold + 8) {
+        in.xdir = (p.x < virt) ? 1 : -1;
+    } else if (d.integers<20>(e.has32) == 0) {  // :728
+        p.standby = d.integers<2>(e.has32);      // :729
+    }
+
+    bool search = false;
+    if (p.state == 0) {
+        if (iabs(b.xv) < p.bold + 3 && dx < kPlayerHalfLength && b.y > -36 && b.y < 10 * p.bold + 84 && b.yv > 0)
+            in.ydir = -1;
+        if (b.land > left_boundary && b.land < right_boundary && dx > p.bold * 5 + kPlayerLength &&
+            b.x > left_boundary && b.x < right_boundary && b.y > 174) {
+            in.power = 1;  // dive
+            in.xdir = (p.x < b.x) ? 1 : -1;
+        }
+    } else if (p.state == 1 || p.state == 2) {
+        if (dx > 8) in.xdir = (p.x < b.x) ? 1 : -1;
+        search = dx < 48 && iabs(b.y - p.y) < 48;
+    }
+
+    // decide_whether_input_power_hit: up to 6 candidate hits, first acceptable one wins.
+    if (__any_sync(mask, search)) {
+        int y_first = 0;
+        if (search) y_first = (d.integers<2>(e.has32) == 0) ? -1 : 1;  // :795 scan order of y_direction
+        bool found = false;
+#pragma unroll 1
+        for (int c = 0; c < 6; c++) {
+            const bool act = search && !found;
+            if (!__any_sync(mask, act)) break;
+            const int xd = (c < 3) ? 1 : 0;               // range(1, -1, -1)
+            const int yd = y_first * (1 - (c % 3));       // -1,0,1 or 1,0,-1
+            const int xv0 = (b.x < kGroundHalfWidth) ? (xd + 1) * 10 : -(xd + 1) * 10;  // :841-844
+            const int yv0 = iabs(b.yv) * yd * 2;                                          // :845
+            const int lx = simulate_landing_x<true>(mask, b.x, b.y, xv0, yv0, act);
+            if (act && (lx <= left_boundary || lx >= far_boundary) && iabs(lx - o.x) > kPlayerLength) {
+                in.xdir = xd;
+                in.ydir = yd;
+                found = true;
+            }
+        }
+        if (found) {  // :768-771
+            in.power = 1;
+            if (iabs(o.x - p.x) < 80 && in.ydir != -1) in.ydir = -1;
+        }
+    }
+}
+
+// ---- player ------------------------------------------------------------------------------------
+// process_player_movement_and_set_player_position, physics.py:439-564 (after the AI override)
+template <int I>
+__device__ __forceinline__ void player_move(Player &p, const Input &in) {
+    if (p.state == 4) {  // lying down: don't move (:458-462)
+        p.lying -= 1;
+        if (p.lying < -1) p.state = 0;
+        return;
+    }
+    const int vx = (p.state < 3) ? in.xdir * 6 : p.dive * 8;  // state < 5 always holds before termination
+    int x = p.x + vx;
+    constexpr int lo = I ? kGroundHalfWidth + kPlayerHalfLength : kPlayerHalfLength;
+    constexpr int hi = I ? kGroundWidth - kPlayerHalfLength : kGroundHalfWidth - kPlayerHalfLength;
+    p.x = min(max(x, lo), hi);
+
+    if (p.state < 3 && in.ydir == -1 && p.y == kPlayerGroundY) {  // jump
+        p.yv = -16;
+        p.state = 1;
+        p.frame = 0;
+    }
+    const int fy = p.y + p.yv;  // gravity
+    p.y = fy;
+    if (fy < kPlayerGroundY) {
+        p.yv += 1;
+    } else if (fy > kPlayerGroundY) {  // landing
+        p.yv = 0;
+        p.y = kPlayerGroundY;
+        p.frame = 0;
+        if (p.state == 3) {
+            p.state = 4;
+            p.lying = 3;
+        } else {
+            p.state = 0;
+        }
+    }
+    if (in.power == 1) {
+        if (p.state == 1) {  // power hit
+            p.delay = 5;
+            p.frame = 0;
+            p.state = 2;
+        } else if (p.state == 0 && in.xdir != 0) {  // dive
+            p.state = 3;
+            p.frame = 0;
+            p.dive = in.xdir;
+            p.yv = -5;
+        }
+    }
+    if (p.state == 1) {
+        p.frame = (p.frame + 1) % 3;
+    } else if (p.state == 2) {
+        if (p.delay < 1) {
+            p.frame += 1;
+            if (p.frame > 4) {
+                p.frame = 0;
+                p.state = 1;
+            }
+        } else {
+            p.delay -= 1;
+        }
+    } else if (p.state == 0) {
+        p.delay += 1;
+        if (p.delay > 3) {
+            p.delay = 0;
+            const int f = p.frame + p.arm;
+            if (f < 0 || f > 4) p.arm = -p.arm;
+            p.frame = p.frame + p.arm;
+        }
+    }
+    // :554-564 (player.game_ended) cannot execute before the env terminates.
+}
+
+// is_collision_between_ball_and_player_happened (physics.py:340-356) and
+// process_collision_between_ball_and_player (physics.py:580-640). Returns true on a NEW collision.
+template <int I>
+__device__ __forceinline__ bool ball_player(Env &e, DrawCtx &d, const Input &in) {
+    Player &p = e.p[I];
+    Ball &b = e.b;
+    const bool hit = iabs(b.x - p.x) <= kPlayerHalfLength && iabs(b.y - p.y) <= kPlayerHalfLength;
+    if (!hit) {
+        p.coll = 0;
+        return false;
+    }
+    if (p.coll) return false;
+    p.coll = 1;
+    if (b.x < p.x)
+        b.xv = -(iabs(b.x - p.x) / 3);
+    else if (b.x > p.x)
+        b.xv = iabs(b.x - p.x) / 3;
+    if (b.xv == 0) b.xv = d.integers<3>(e.has32) - 1;  // :613
+    const int ayv = iabs(b.yv);
+    b.yv = (ayv < 15) ? -15 : -ayv;
+    if (p.state == 2) {  // jumping and power hitting
+        b.xv = (b.x < kGroundHalfWidth) ? (iabs(in.xdir) + 1) * 10 : -(iabs(in.xdir) + 1) * 10;
+        b.punch = b.x;
+        b.yv = iabs(b.yv) * in.ydir * 2;
+        b.pow = 1;
+    } else {
+        b.pow = 0;
+    }
+    return true;
+}
+
+// ---- one frame -----------------------------------------------------------------------------------
+// raw_env.step (pikazoo_env.py:175-240) for an env that has not terminated. keys1/keys2 are the
+// decoded key bits. AI_MASK bit I = player I+1 is a computer. Warp-collective over `mask` when
+// AI_MASK != 0. Returns player_1's base reward (-1, 0, +1).
+template <int AI_MASK>
+__device__ __forceinline__ int step_frame(unsigned mask, Env &e, DrawCtx &d, const StepCfg &c, uint32_t keys1,
+                                          uint32_t keys2) {
+    if (e.round_ended) {  // :176-180 (game_ended is false here)
+        new_round(e, d, c);
+        e.round_ended = 0;
+    }
+    Input in1 = get_input(e.p[0], keys1);  // also runs for computer players (:183-184)
+    Input in2 = get_input(e.p[1], keys2);
+
+    // physics_engine, physics.py:280-337
+    const bool touching = ball_world(e.b);
+    if (AI_MASK != 0) {
+        // :314-315 is evaluated twice per frame on an unchanged ball; once is enough.
+        e.b.land = simulate_landing_x<false>(mask, e.b.x, e.b.y, e.b.xv, e.b.yv, true);
+    }
+    if (AI_MASK & 1) computer_decide<0>(mask, e, d, in1);
+    player_move<0>(e.p[0], in1);
+    if (AI_MASK & 2) computer_decide<1>(mask, e, d, in2);
+    player_move<1>(e.p[1], in2);
+
+    bool recalc = ball_player<0>(e, d, in1);
+    recalc |= ball_player<1>(e, d, in2);
+    if (AI_MASK != 0) {
+        // :331-332 after each new collision; only the value for the final ball state survives.
+        if (__any_sync(mask, recalc)) {
+            const int lx = simulate_landing_x<false>(mask, e.b.x, e.b.y, e.b.xv, e.b.yv, recalc);
+            if (recalc) e.b.land = lx;
+        }
+    }
+
+    // scoring, :190-210
+    if (touching) {
+        if (e.b.punch < kGroundHalfWidth) {
+            e.p2serve = 1;
+            e.score[1] += 1;
+            if (e.score[1] >= c.winning_score) e.game_ended = 1;
+        } else {
+            e.p2serve = 0;
+            e.score[0] += 1;
+            if (e.score[0] >= c.winning_score) e.game_ended = 1;
+        }
+        e.round_ended = 1;
+    }
+    e.ep_frames += 1;
+    return e.round_ended ? (e.p2serve ? -1 : 1) : 0;  // :217-223
+}
+
+// raw_env._get_obs, pikazoo_env.py:576-624: the 35 distinct values (p1 block 13, p2 block 13,
+// ball block 9); obs_p1 = u[0..34], obs_p2 = u[13..25] u[0..12] u[26..34].
+__device__ __forceinline__ void obs_values(const Env &e, int (&u)[35]) {
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const Player &p = e.p[i];
+        int *o = u + 13 * i;
+        o[0] = p.x;
+        o[1] = p.y;
+        o[2] = p.yv;
+        o[3] = p.dive;
+        o[4] = p.lying;
+        o[5] = p.frame;
+        o[6] = p.delay;
+#pragma unroll
+        for (int s = 0; s < 5; s++) o[7 + s] = (p.state == s) ? 1 : 0;
+        o[12] = p.keyprev;
+    }
+    const Ball &b = e.b;
+    u[26] = b.x;
+    u[27] = b.y;
+    u[28] = b.px;
+    u[29] = b.py;
+    u[30] = b.ppx;
+    u[31] = b.ppy;
+    u[32] = b.xv;
+    u[33] = b.yv;
+    u[34] = b.pow;
+}
+
+// index into u[] of element k (0..69) of the [obs_p1 | obs_p2] row
+__host__ __device__ constexpr int obs_src(int k) {
+    return k < 35 ? k : (k < 48 ? k - 35 + 13 : (k < 61 ? k - 48 : k - 35));
+}
+
+}  // namespace pz

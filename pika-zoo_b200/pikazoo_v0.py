@@ -1,0 +1,160 @@
+"""`pikazoo_v0.env / raw_env / parallel_env`: the reference's single-env PettingZoo-style
+surface (pikazoo/pikazoo_v0.py:1-3, pikazoo/env/pikazoo_env.py:27-29,72-240,481-574) on top of
+a 1-env batch of the CUDA simulator. Same kwargs, agents, spaces, dict-in / five-dicts-out
+protocol and termination bookkeeping; observations come back as numpy arrays like the
+reference's. `parallel_env` does not exist upstream and is an alias of `env`.
+
+Differences, all deliberate: `reset(seed=...)` DOES seed the env (the reference ignores it,
+pikazoo_env.py:149); rendering is not provided (render_mode must be None); an out-of-range
+action raises IndexError (the reference lets numpy wrap negative indices).
+"""
+
+from __future__ import annotations
+
+import functools
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import spaces
+from .vec_env import AGENTS, PikaVecEnv
+
+__all__ = ["env", "raw_env", "parallel_env"]
+
+# observation_space bounds, pikazoo_env.py:481-565
+_P_LOW = [32, 108, -15, -1, -2, 0, 0, 0, 0, 0, 0, 0, 0]
+_P_HIGH = [400, 244, 16, 1, 3, 4, 4, 1, 1, 1, 1, 1, 1]
+_B_LOW = [20, 0, 0, 0, 0, 0, -20, -124, 0]
+_B_HIGH = [432, 252, 432, 252, 432, 252, 20, 124, 1]
+OBS_LOW = np.array(_P_LOW + _P_LOW + _B_LOW)
+OBS_HIGH = np.array(_P_HIGH + _P_HIGH + _B_HIGH)
+
+
+def env(**kwargs):
+    return raw_env(**kwargs)
+
+
+def parallel_env(**kwargs):
+    return raw_env(**kwargs)
+
+
+class raw_env:
+    metadata = {"render_modes": ["human", "rgb_array"], "name": "pikazoo_v0", "render_fps": 20}
+
+    def __init__(
+        self,
+        winning_score=15,
+        serve="winner",
+        is_player1_computer=False,
+        is_player2_computer=False,
+        render_mode=None,
+        device="cuda",
+        seed: Optional[int] = None,
+    ):
+        assert serve in ("winner", "alternate", "random")  # pikazoo_env.py:104
+        if render_mode is not None:
+            raise NotImplementedError("rendering is out of scope of the batched simulator (DESIGN.md §7)")
+        self.possible_agents: List[str] = list(AGENTS)
+        self.agents: List[str] = self.possible_agents[:]
+        self.action_spaces = dict(zip(self.agents, [spaces.Discrete(18)] * 2))
+        self.winning_score = winning_score
+        self.serve = serve
+        self.render_mode = None
+        self._device = device
+        self._kwargs = dict(
+            winning_score=winning_score, serve=serve, is_player1_computer=is_player1_computer,
+            is_player2_computer=is_player2_computer,
+        )
+        # fused wrapper options, set by pikazoo.wrappers.* before the first reset
+        self._simplify_action = False
+        self._reward_by_ball_position = None
+        self._seed_value = int(np.random.SeedSequence().entropy % (2**63)) if seed is None else int(seed)
+        self._vec: Optional[PikaVecEnv] = None
+        self.scores: List[int] = [0, 0]
+        self._actions = None
+
+    # -- internals ---------------------------------------------------------------------------
+    def _build(self):
+        self._vec = PikaVecEnv(
+            1, device=self._device, seed=self._seed_value, autoreset=False, reward_dtype=torch.float64,
+            simplify_action=self._simplify_action, reward_by_ball_position=self._reward_by_ball_position,
+            **self._kwargs,
+        )
+        self._actions = torch.zeros((1, 2), dtype=torch.int32, device=self._vec.device)
+
+    def _configure(self, **opts):
+        """Used by the wrappers to fuse themselves into the kernel configuration."""
+        for k, v in opts.items():
+            setattr(self, "_" + k, v)
+        if self._vec is not None:  # keep the live state, swap the config
+            state = self._vec.state_dict()
+            self._build()
+            self._vec.load_state_dict(state)
+
+    def _obs_dict(self, obs: torch.Tensor) -> Dict[str, np.ndarray]:
+        o = obs[0].cpu().numpy().astype(np.int64)  # the reference returns np.array of Python ints
+        return {self.possible_agents[0]: o[0], self.possible_agents[1]: o[1]}
+
+    def _get_infos(self):
+        return {agent: {"score": self.scores} for agent in self.agents}
+
+    # -- reference API ---------------------------------------------------------------------------
+    def reset(self, seed=None, options=None):
+        if seed is not None:
+            self._seed_value = int(seed)
+            self._vec = None
+        if self._vec is None:
+            self._build()
+        self.agents = self.possible_agents[:]
+        obs = self._vec.reset()
+        self.scores[0] = self.scores[1] = 0
+        return self._obs_dict(obs), self._get_infos()
+
+    def step(self, actions):
+        if not self.agents:
+            raise IndexError("step() called on a terminated env; call reset() (reference: pikazoo_env.py:237-238)")
+        if self._vec is None:
+            raise RuntimeError("call reset() before step()")
+        n = 13 if self._simplify_action else 18
+        a = [int(actions[agent]) for agent in self.agents]
+        for v in a:
+            if not 0 <= v < n:
+                raise IndexError(f"action {v} is out of range for Discrete({n})")
+        self._actions.copy_(torch.tensor([a], dtype=torch.int32))
+        obs, reward, term = self._vec.step(self._actions)
+        r = reward[0].cpu().tolist()
+        terminated = bool(term[0].item())
+        s = self._vec.scores()[0].cpu().tolist()
+        self.scores[0], self.scores[1] = int(s[0]), int(s[1])
+        observations = self._obs_dict(obs)
+        if self._reward_by_ball_position is None:
+            r = [int(r[0]), int(r[1])]  # the reference's base rewards are Python ints
+        rewards = {self.agents[0]: r[0], self.agents[1]: r[1]}
+        terminations = {agent: terminated for agent in self.agents}
+        truncations = {agent: False for agent in self.agents}
+        infos = self._get_infos()
+        if terminated:
+            self.agents = []
+        return observations, rewards, terminations, truncations, infos
+
+    @functools.lru_cache(maxsize=None)
+    def observation_space(self, agent=None):
+        return spaces.Box(low=OBS_LOW, high=OBS_HIGH, shape=(35,), dtype=np.int32)
+
+    def action_space(self, agent):
+        return self.action_spaces[agent]
+
+    def render(self):
+        raise NotImplementedError("rendering is out of scope of the batched simulator (DESIGN.md §7)")
+
+    def close(self):
+        self._vec = None
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def state_words(self) -> np.ndarray:
+        """52-word hidden state (oracle/pika_oracle.h layout) of this env, for tests."""
+        return self._vec.export_state()[0, :52].cpu().numpy()

@@ -1,0 +1,227 @@
+"""Batched device-tensor entry point: N independent Pikachu-Volleyball envs on one B200.
+
+`PikaVecEnv` keeps the reference constructor arguments (pikazoo/env/pikazoo_env.py:79-86:
+winning_score, serve, is_player1_computer, is_player2_computer) and fuses the two wrappers
+north_star names (SimplifyAction, simplify_action.py:7-28; RewardByBallPosition,
+reward_by_ball_position.py:6-31) into the step kernel. All tensors live on the CUDA device;
+every call is asynchronous on the current torch stream. PyTorch is used for device memory
+and streams only — the simulation is the hand-written sm_100a library behind the C ABI
+(include/pikazoo_b200.h). There is no CPU fallback.
+
+Semantics of one `step(actions)` call per env (NEXT-STEP auto-reset):
+  * env not terminated: exactly one reference `env.step({"player_1": a1, "player_2": a2})`;
+  * env terminated by an earlier call and autoreset=True: exactly one reference `env.reset()`
+    on the same object (carry-over semantics), obs = reset obs, reward 0, done False, action ignored;
+  * env terminated and autoreset=False: no-op, obs re-emitted, reward 0, done True.
+Env i's random stream is numpy `Generator(PCG64(seed + first_env + i))` (protocol S0).
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+_ACT_DTYPES = {torch.int32: _lib.ACT_I32, torch.int64: _lib.ACT_I64, torch.uint8: _lib.ACT_U8}
+_REW_DTYPES = {torch.float32: _lib.REW_F32, torch.float64: _lib.REW_F64}
+
+AGENTS = ("player_1", "player_2")
+
+
+def make_config(
+    winning_score: int = 15,
+    serve: str = "winner",
+    is_player1_computer: bool = False,
+    is_player2_computer: bool = False,
+    simplify_action: bool = False,
+    reward_by_ball_position: Optional[Tuple[Sequence[float], int, int]] = None,
+    autoreset: bool = True,
+    action_dtype: torch.dtype = torch.int32,
+    reward_dtype: torch.dtype = torch.float32,
+) -> _lib.PzConfig:
+    assert serve in ("winner", "alternate", "random")  # pikazoo_env.py:104
+    if not 1 <= int(winning_score) <= 1023:
+        raise ValueError("winning_score must be in [1, 1023] (10-bit packed score field)")
+    c = _lib.PzConfig()
+    c.winning_score = int(winning_score)
+    c.serve = _lib.SERVE_CODES[serve]
+    c.is_player1_computer = int(bool(is_player1_computer))
+    c.is_player2_computer = int(bool(is_player2_computer))
+    c.simplify_action = int(bool(simplify_action))
+    c.x_line, c.y_line = 216, 176
+    if reward_by_ball_position is not None:
+        add, x_line, y_line = reward_by_ball_position
+        assert len(add) == 8  # reward_by_ball_position.py:15
+        c.reward_by_ball_position = 1
+        c.x_line, c.y_line = int(x_line), int(y_line)
+        for k in range(8):
+            c.additional_reward[k] = float(add[k])
+    c.autoreset = int(bool(autoreset))
+    c.action_dtype = _ACT_DTYPES[action_dtype]
+    c.reward_dtype = _REW_DTYPES[reward_dtype]
+    return c
+
+
+class PikaVecEnv:
+    """N envs stepped by one kernel launch; observations [N, 2, 35] int32 on the device."""
+
+    possible_agents = list(AGENTS)
+    num_agents = 2
+    obs_dim = _lib.OBS_WORDS
+
+    def __init__(
+        self,
+        num_envs: int,
+        device: "torch.device | str | int" = "cuda",
+        seed: int = 0,
+        winning_score: int = 15,
+        serve: str = "winner",
+        is_player1_computer: bool = False,
+        is_player2_computer: bool = False,
+        simplify_action: bool = False,
+        reward_by_ball_position: Optional[Tuple[Sequence[float], int, int]] = None,
+        autoreset: bool = True,
+        action_dtype: torch.dtype = torch.int32,
+        reward_dtype: torch.dtype = torch.float32,
+        first_env: int = 0,
+        track_stats: bool = True,
+    ):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.PikaLibraryError("PikaVecEnv runs on CUDA devices only (there is no CPU path)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_envs = int(num_envs)
+        if self.num_envs < 1:
+            raise ValueError("num_envs must be >= 1")
+        self.seed = int(seed)
+        self.first_env = int(first_env)
+        self._kw = dict(
+            winning_score=winning_score, serve=serve, is_player1_computer=is_player1_computer,
+            is_player2_computer=is_player2_computer, simplify_action=simplify_action,
+            reward_by_ball_position=reward_by_ball_position, autoreset=autoreset,
+            action_dtype=action_dtype, reward_dtype=reward_dtype,
+        )
+        self.cfg = make_config(**self._kw)
+        self.action_dtype = action_dtype
+        self.reward_dtype = reward_dtype
+        self.num_actions = 13 if simplify_action else 18
+        n = self.num_envs
+        with torch.cuda.device(self.device):
+            self.state = torch.zeros(_lib.STATE_WORDS * n, dtype=torch.int32, device=self.device)
+            self.obs = torch.zeros((n, 2, _lib.OBS_WORDS), dtype=torch.int32, device=self.device)
+            self.reward = torch.zeros((n, 2), dtype=reward_dtype, device=self.device)
+            self.done_u8 = torch.zeros((n,), dtype=torch.uint8, device=self.device)
+            self.stats = torch.zeros(_lib.NUM_STATS, dtype=torch.int64, device=self.device) if track_stats else None
+            _lib.check(
+                self.lib.pz_seed(self.state.data_ptr(), n, self.seed & (2**64 - 1), self.first_env, self._stream()),
+                "pz_seed",
+            )
+        self.frame = 0  # calls issued so far (drives the synthetic action stream of rollout())
+
+    # ---- plumbing ------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _cfg_ref(self):
+        return ctypes.byref(self.cfg)
+
+    def _stats_ptr(self):
+        return self.stats.data_ptr() if self.stats is not None else None
+
+    # ---- reference-shaped API --------------------------------------------------------------
+    def reset(self) -> torch.Tensor:
+        """reference reset() on every env; returns obs [N, 2, 35] int32 (a view reused by step)."""
+        with torch.cuda.device(self.device):
+            _lib.check(
+                self.lib.pz_reset(self.state.data_ptr(), self.num_envs, self._cfg_ref(), self.obs.data_ptr(),
+                                  self._stream()),
+                "pz_reset",
+            )
+        return self.obs
+
+    def step(self, actions: Optional[torch.Tensor]):
+        """actions [N, 2] (int32/int64/uint8 as configured) -> (obs, reward [N,2], terminated [N] bool).
+
+        The returned tensors are the env's own output buffers, overwritten by the next call.
+        `actions` may be None only when both players are computers.
+        """
+        if actions is not None:
+            if actions.dtype != self.action_dtype:
+                raise TypeError(f"actions must be {self.action_dtype} (got {actions.dtype}); "
+                                "pass action_dtype= to the constructor")
+            if actions.device != self.device or tuple(actions.shape) != (self.num_envs, 2):
+                raise ValueError(f"actions must be a [{self.num_envs}, 2] tensor on {self.device}")
+            if not actions.is_contiguous():
+                actions = actions.contiguous()
+            a_ptr = actions.data_ptr()
+        else:
+            a_ptr = None
+        with torch.cuda.device(self.device):
+            _lib.check(
+                self.lib.pz_step(self.state.data_ptr(), self.num_envs, self._cfg_ref(), a_ptr, self.obs.data_ptr(),
+                                 self.reward.data_ptr(), self.done_u8.data_ptr(), self._stats_ptr(), self._stream()),
+                "pz_step",
+            )
+        self.frame += 1
+        return self.obs, self.reward, self.done_u8.view(torch.bool)
+
+    def rollout(self, K: int, actions: str = "noop", action_seed: int = 0, write_obs: bool = False):
+        """K frames in one launch with the state in registers (auto-reset always on).
+
+        actions: "noop" (both 0; computer players decide for themselves) or "synth" (uniform
+        actions from the counter-based device stream keyed by (action_seed, global env, frame)).
+        """
+        src = {"noop": _lib.ACTIONS_NOOP, "synth": _lib.ACTIONS_SYNTH}[actions]
+        with torch.cuda.device(self.device):
+            _lib.check(
+                self.lib.pz_rollout(self.state.data_ptr(), self.num_envs, self._cfg_ref(), int(K), src,
+                                    int(action_seed) & (2**64 - 1), self.first_env, self.frame,
+                                    self.obs.data_ptr() if write_obs else None, self._stats_ptr(), self._stream()),
+                "pz_rollout",
+            )
+        self.frame += int(K)
+        return self.obs if write_obs else None
+
+    # ---- state access ------------------------------------------------------------------------
+    def export_state(self) -> torch.Tensor:
+        """Unpacked parity state int32 [N, 53] (layout: oracle/pika_oracle.h pk_env)."""
+        out = torch.empty((self.num_envs, _lib.UNPACKED_WORDS), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pz_export_state(self.state.data_ptr(), self.num_envs, out.data_ptr(), self._stream()),
+                       "pz_export_state")
+        return out
+
+    def import_state(self, unpacked: torch.Tensor) -> None:
+        u = unpacked.to(device=self.device, dtype=torch.int32).contiguous()
+        assert tuple(u.shape) == (self.num_envs, _lib.UNPACKED_WORDS)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pz_import_state(self.state.data_ptr(), self.num_envs, u.data_ptr(), self._stream()),
+                       "pz_import_state")
+
+    def scores(self) -> torch.Tensor:
+        """[N, 2] current scores (info["score"] of the reference, pikazoo_env.py:573-574)."""
+        return self.export_state()[:, 37:39]
+
+    def stats_dict(self) -> dict:
+        """Episode statistics accumulated on the device (one D2H sync)."""
+        if self.stats is None:
+            return {}
+        v = self.stats.tolist()
+        d = {name: int(v[i]) for i, name in enumerate(_lib.STAT_NAMES)}
+        d["env_steps"] = d["calls"] - d["resets"] - d["frozen"]
+        return d
+
+    def state_dict(self) -> dict:
+        """The packed SoA state tensor is the checkpoint."""
+        return {"state": self.state.clone(), "frame": self.frame, "kw": dict(self._kw), "seed": self.seed,
+                "first_env": self.first_env, "num_envs": self.num_envs}
+
+    def load_state_dict(self, sd: dict) -> None:
+        assert sd["num_envs"] == self.num_envs
+        self.state.copy_(sd["state"])
+        self.frame = int(sd["frame"])

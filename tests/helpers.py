@@ -1,0 +1,152 @@
+"""Shared test machinery: replay golden sessions through any batched stepper and hash the
+per-env streams exactly as oracle/make_golden.py did with the reference."""
+
+from __future__ import annotations
+
+import hashlib
+
+import numpy as np
+
+from oracle.synth import synth_actions_numpy
+
+
+def group_kwargs(group):
+    cfg = dict(group["config"])
+    if "reward_by_ball_position" in cfg:
+        add, xl, yl = cfg["reward_by_ball_position"]
+        cfg["reward_by_ball_position"] = (tuple(add), xl, yl)
+    return cfg
+
+
+class SessionRecorder:
+    """Per-env sha256 / episode bookkeeping for a batch stepped in lock-step with auto-reset."""
+
+    def __init__(self, n, episodes_per_env, max_calls):
+        self.n = n
+        self.h = [hashlib.sha256() for _ in range(n)]
+        self.episodes = [[] for _ in range(n)]
+        self.calls = np.zeros(n, dtype=np.int64)
+        self.ep_frames = np.zeros(n, dtype=np.int64)
+        self.pending_reset = np.zeros(n, dtype=bool)  # this env's next call is its auto-reset
+        self.active = np.ones(n, dtype=bool)
+        self.episodes_per_env = episodes_per_env
+        self.max_calls = max_calls
+
+    def on_reset(self, obs):
+        obs = np.ascontiguousarray(obs, dtype="<i4")
+        for i in range(self.n):
+            self.h[i].update(obs[i].tobytes())
+
+    def on_step(self, obs, reward, done, scores_fn):
+        """obs [n,2,35] int32, reward [n,2] float64, done [n] bool — outputs of one batched call."""
+        obs = np.ascontiguousarray(obs, dtype="<i4")
+        reward = np.ascontiguousarray(reward, dtype="<f8")
+        scores = None
+        for i in np.nonzero(self.active)[0]:
+            self.calls[i] += 1
+            if self.pending_reset[i]:
+                self.h[i].update(obs[i].tobytes())
+                self.pending_reset[i] = False
+            else:
+                self.ep_frames[i] += 1
+                self.h[i].update(obs[i].tobytes())
+                self.h[i].update(reward[i].tobytes())
+                self.h[i].update(bytes([int(done[i])]))
+                if done[i]:
+                    if scores is None:
+                        scores = scores_fn()
+                    self.episodes[i].append({"frames": int(self.ep_frames[i]),
+                                             "scores": [int(scores[i][0]), int(scores[i][1])]})
+                    self.ep_frames[i] = 0
+                    self.pending_reset[i] = True
+            if self.calls[i] >= self.max_calls:
+                self.active[i] = False
+            elif len(self.episodes[i]) >= self.episodes_per_env:
+                # the golden generator stops right after the terminating step
+                self.active[i] = False
+
+    def all_done(self):
+        return not self.active.any()
+
+
+def replay_group(group, make_stepper, check_final_state=True):
+    """make_stepper(n, base_seed, cfg_kwargs) -> object with
+         reset() -> obs ; step(actions int32 [n,2]) -> (obs, reward f64, done) ; scores() -> [n,2];
+         final_state() -> [n, >=52] int32 (optional)
+    Returns a list of mismatch descriptions (empty = parity)."""
+    n = group["num_envs"]
+    cfg = group_kwargs(group)
+    n_actions = 13 if cfg.get("simplify_action") else 18
+    stepper = make_stepper(n, group["base_seed"], cfg)
+    rec = SessionRecorder(n, group["episodes_per_env"], group["max_calls"])
+    rec.on_reset(stepper.reset())
+    frame = 0
+    final_states = [None] * n
+    while not rec.all_done():
+        if group["action_mode"] == "noop":
+            actions = np.zeros((n, 2), dtype=np.int32)
+        else:
+            actions = synth_actions_numpy(0x5EED, 0, n, frame, n_actions)
+        was_active = rec.active.copy()
+        obs, reward, done = stepper.step(actions)
+        rec.on_step(obs, reward, done, stepper.scores)
+        frame += 1
+        finished_now = was_active & ~rec.active
+        if check_final_state and finished_now.any():
+            st = stepper.final_state()
+            for i in np.nonzero(finished_now)[0]:
+                final_states[i] = np.array(st[i][:52], dtype=np.int32)
+    bad = []
+    for i, sess in enumerate(group["sessions"]):
+        if rec.episodes[i] != sess["episodes"]:
+            bad.append(f"{group['name']} env {i}: episodes {rec.episodes[i]} != {sess['episodes']}")
+        elif rec.h[i].hexdigest() != sess["sha256"]:
+            bad.append(f"{group['name']} env {i}: sha256 differs")
+        elif check_final_state and final_states[i] is not None:
+            ref = np.array(sess["final_state"], dtype=np.int64).astype(np.uint32).view(np.int32)
+            if not np.array_equal(final_states[i], ref):
+                bad.append(f"{group['name']} env {i}: final state words {np.nonzero(final_states[i] != ref)[0]}")
+    return bad
+
+
+class OracleStepper:
+    def __init__(self, n, base_seed, cfg):
+        from oracle import pyoracle as po
+
+        self.env = po.OracleVecEnv(n, seed=base_seed, autoreset=True, **cfg)
+
+    def reset(self):
+        return self.env.reset()
+
+    def step(self, actions):
+        return self.env.step(actions)
+
+    def scores(self):
+        return self.env.state[:, 37:39]
+
+    def final_state(self):
+        return self.env.state
+
+
+class CudaStepper:
+    def __init__(self, n, base_seed, cfg):
+        import torch
+        import pikazoo_b200
+
+        self.torch = torch
+        self.env = pikazoo_b200.PikaVecEnv(n, device="cuda", seed=base_seed, autoreset=True,
+                                           reward_dtype=torch.float64, **cfg)
+
+    def reset(self):
+        return self.env.reset().cpu().numpy()
+
+    def step(self, actions):
+        a = self.torch.from_numpy(np.ascontiguousarray(actions, dtype=np.int32)).to(self.env.device)
+        obs, reward, done = self.env.step(a)
+        return obs.cpu().numpy(), reward.cpu().numpy(), done.cpu().numpy()
+
+    def scores(self):
+        return self.env.scores().cpu().numpy()
+
+    def final_state(self):
+        return self.env.export_state().cpu().numpy()

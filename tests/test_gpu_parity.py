@@ -1,0 +1,209 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against
+  (1) the golden sessions recorded from the unmodified reference (1,039 full games), and
+  (2) the C oracle on the same seeded inputs,
+bit-exact on every observation, reward, termination, score and the 52-word hidden state
+(PCG64 stream included). Integer work: the bar is equality, no tolerance."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pyoracle as po
+from oracle.synth import synth_actions_numpy
+from tests.helpers import CudaStepper, replay_group
+
+pytestmark = pytest.mark.gpu
+
+SHAPED = ((0.1, 0.2, 0.3, 0.4, -0.1, -0.2, -0.3, -0.4), 216, 176)
+
+
+@pytest.fixture(scope="module")
+def pz(cuda_lib):
+    import pikazoo_b200
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return pikazoo_b200
+
+
+@pytest.mark.parametrize("name", [
+    "ai_vs_ai_ws15_winner", "random_ws15_winner", "simplify_shaped_ws15", "random_ws5_serve_random",
+    "ai_p1_vs_random_ws7_alternate", "random_vs_ai_p2_ws7_random", "ai_vs_ai_ws3_random_multi",
+])
+def test_cuda_replays_reference_golden_games(pz, golden, name):
+    group = next(g for g in golden["groups"] if g["name"] == name)
+    bad = replay_group(group, CudaStepper)
+    assert not bad, bad[:5]
+
+
+CONFIGS = {
+    "random18": dict(winning_score=15, serve="winner"),
+    "ai_vs_ai": dict(winning_score=15, serve="winner", is_player1_computer=True, is_player2_computer=True),
+    "ai_p1": dict(winning_score=3, serve="alternate", is_player1_computer=True),
+    "ai_p2_random_serve": dict(winning_score=5, serve="random", is_player2_computer=True),
+    "wrappers": dict(winning_score=15, serve="winner", simplify_action=True, reward_by_ball_position=SHAPED),
+    "ws5_random": dict(winning_score=5, serve="random"),
+    "ws1": dict(winning_score=1, serve="random", is_player1_computer=True, is_player2_computer=True),
+}
+
+
+def _lockstep(pz, n, steps, cfg, seed, autoreset=True, check_every=1, action_dtype=torch.int32,
+              reward_dtype=torch.float64):
+    env = pz.PikaVecEnv(n, seed=seed, autoreset=autoreset, action_dtype=action_dtype, reward_dtype=reward_dtype,
+                        **cfg)
+    orc = po.OracleVecEnv(n, seed=seed, autoreset=autoreset, **cfg)
+    n_actions = 13 if cfg.get("simplify_action") else 18
+    assert np.array_equal(env.reset().cpu().numpy(), orc.reset())
+    np_dtype = {torch.int32: np.int32, torch.int64: np.int64, torch.uint8: np.uint8}[action_dtype]
+    for t in range(steps):
+        a = synth_actions_numpy(seed + 77, 0, n, t, n_actions)
+        obs, rew, done = env.step(torch.from_numpy(a.astype(np_dtype)).cuda())
+        o_obs, o_rew, o_done = orc.step(a)
+        if t % check_every == 0 or t == steps - 1:
+            assert np.array_equal(obs.cpu().numpy(), o_obs), f"obs differ at step {t}"
+            r = rew.cpu().numpy()
+            want = o_rew if reward_dtype == torch.float64 else o_rew.astype(np.float32)
+            assert np.array_equal(r, want), f"reward differs at step {t}"
+            assert np.array_equal(done.cpu().numpy(), o_done.astype(bool)), f"done differs at step {t}"
+    st = env.export_state().cpu().numpy()
+    assert np.array_equal(st, orc.state), f"hidden state differs: words {np.nonzero((st != orc.state).any(0))[0]}"
+    return env, orc
+
+
+@pytest.mark.parametrize("cfg_name", sorted(CONFIGS))
+def test_cuda_matches_oracle_4096_envs(pz, cfg_name):
+    # config 2 of BASELINE.json (4,096 envs) and its variants; every output compared on every step
+    _lockstep(pz, 4096, 1500, CONFIGS[cfg_name], seed=20_000)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 127, 128, 129, 1000])
+def test_ragged_batch_sizes(pz, n):
+    _lockstep(pz, n, 300, CONFIGS["ws5_random"], seed=5)
+    _lockstep(pz, n, 200, CONFIGS["ws1"], seed=6)
+
+
+@pytest.mark.parametrize("action_dtype", [torch.int32, torch.int64, torch.uint8])
+@pytest.mark.parametrize("reward_dtype", [torch.float32, torch.float64])
+def test_action_and_reward_dtypes(pz, action_dtype, reward_dtype):
+    _lockstep(pz, 777, 400, CONFIGS["wrappers"], seed=9, action_dtype=action_dtype, reward_dtype=reward_dtype)
+
+
+def test_autoreset_off_freezes_terminated_envs(pz):
+    env, orc = _lockstep(pz, 512, 900, dict(winning_score=2, serve="winner"), seed=3, autoreset=False)
+    d = env.stats_dict()
+    assert d["frozen"] > 0 and d["resets"] == 0
+    assert d["episodes"] == int((orc.state[:, 40] != 0).sum())
+
+
+def test_bad_actions_are_counted_and_treated_as_noop(pz):
+    n = 256
+    env = pz.PikaVecEnv(n, seed=1)
+    ref = pz.PikaVecEnv(n, seed=1)
+    env.reset(), ref.reset()
+    a = torch.full((n, 2), 18, dtype=torch.int32, device="cuda")
+    a[::2, 0] = -1
+    for _ in range(20):
+        o1, _, _ = env.step(a)
+        o2, _, _ = ref.step(torch.zeros_like(a))
+        assert torch.equal(o1, o2)
+    assert env.stats_dict()["bad_actions"] == 20 * n and ref.stats_dict()["bad_actions"] == 0
+    with pytest.raises(TypeError):
+        env.step(a.long())
+    with pytest.raises(ValueError):
+        env.step(a[:10])
+
+
+def test_export_import_round_trip_and_seeding(pz):
+    n = 3000
+    env = pz.PikaVecEnv(n, seed=123, **CONFIGS["ai_vs_ai"])
+    env.reset()
+    env.rollout(200)
+    st = env.export_state()
+    other = pz.PikaVecEnv(n, seed=999, **CONFIGS["ai_vs_ai"])
+    other.import_state(st)
+    assert torch.equal(other.export_state(), st)
+    assert torch.equal(other.state, env.state)  # packed form is canonical
+    a, b = env.step(None)[0].clone(), other.step(None)[0].clone()
+    assert torch.equal(a, b)
+    # device SeedSequence/PCG64 seeding against the oracle (which is checked against numpy)
+    fresh = pz.PikaVecEnv(n, seed=2**40 + 5, first_env=10).export_state().cpu().numpy()
+    for i in (0, 1, n - 1):
+        s, inc = po.pcg64_seed(2**40 + 5 + 10 + i)
+        assert np.array_equal(fresh[i, 42:46].view(np.uint32), s) and np.array_equal(fresh[i, 46:50].view(np.uint32), inc)
+
+
+@pytest.mark.parametrize("cfg_name,actions", [("ai_vs_ai", "noop"), ("random18", "synth"), ("wrappers", "synth"),
+                                              ("ai_p2_random_serve", "synth"), ("ws1", "noop")])
+def test_rollout_matches_oracle(pz, cfg_name, actions):
+    cfg = CONFIGS[cfg_name]
+    n, K, launches = 2048 + 17, 64, 12
+    env = pz.PikaVecEnv(n, seed=31, first_env=1000, **cfg)
+    orc = po.OracleVecEnv(n, seed=31 + 1000, **cfg)
+    env.reset(), orc.reset()
+    stats = np.zeros(8, dtype=np.int64)
+    for l in range(launches):
+        env.rollout(K, actions=actions, action_seed=4242)
+        orc.rollout(K, action_mode=0 if actions == "noop" else 1, action_seed=4242, first_env=1000, frame0=l * K,
+                    stats=stats)
+    st = env.export_state().cpu().numpy()
+    assert np.array_equal(st, orc.state), f"words {np.nonzero((st != orc.state).any(0))[0]}"
+    d = env.stats_dict()
+    assert d["calls"] == n * K * launches
+    assert [d["env_steps"], d["episodes"], d["episode_frames"], d["p1_wins"], d["p2_wins"], d["resets"]] == \
+        [stats[0], stats[1], stats[2], stats[3], stats[4], stats[7]]
+    # final observation of a rollout == observation the per-step path would have produced
+    obs = env.rollout(1, actions=actions, action_seed=4242, write_obs=True).cpu().numpy()
+    a = np.zeros((n, 2), np.int32) if actions == "noop" else synth_actions_numpy(
+        4242, 1000, n, launches * K, 13 if cfg.get("simplify_action") else 18)
+    o_obs, _, _ = orc.step(a)
+    assert np.array_equal(obs, o_obs)
+
+
+def test_step_statistics_match_oracle_bookkeeping(pz):
+    n, steps = 2048, 1200
+    env, orc = _lockstep(pz, n, steps, dict(winning_score=2, serve="random"), seed=77, check_every=100)
+    d = env.stats_dict()
+    assert d["calls"] == n * steps and d["frozen"] == 0 and d["bad_actions"] == 0
+    assert d["episodes"] >= n and d["p1_wins"] + d["p2_wins"] == d["episodes"]
+    assert d["p1_points"] + d["p2_points"] >= 2 * d["episodes"]
+    assert d["episode_frames"] + int(orc.state[:, 52].sum()) == d["env_steps"]
+
+
+def test_host_buffer_path_matches_device_path(pz):
+    import ctypes
+    from pikazoo_b200 import _lib, make_config
+
+    n = 5000
+    cfg = make_config(winning_score=3, serve="random", simplify_action=True, reward_by_ball_position=SHAPED)
+    ctx = ctypes.c_void_p()
+    L = _lib.load()
+    _lib.check(L.pz_host_create(ctypes.byref(ctx), n, ctypes.byref(cfg), 55, 0, 4), "pz_host_create")
+    env = pz.PikaVecEnv(n, seed=55, winning_score=3, serve="random", simplify_action=True,
+                        reward_by_ball_position=SHAPED)
+    obs_h = torch.zeros((n, 2, 35), dtype=torch.int32).pin_memory()
+    rew_h = torch.zeros((n, 2), dtype=torch.float32).pin_memory()
+    done_h = torch.zeros((n,), dtype=torch.uint8).pin_memory()
+    _lib.check(L.pz_host_reset(ctx, obs_h.data_ptr()), "pz_host_reset")
+    assert torch.equal(obs_h, env.reset().cpu())
+    for t in range(400):
+        a = torch.from_numpy(synth_actions_numpy(8, 0, n, t, 13))
+        _lib.check(L.pz_host_step(ctx, a.data_ptr(), obs_h.data_ptr(), rew_h.data_ptr(), done_h.data_ptr()),
+                   "pz_host_step")
+        obs, rew, done = env.step(a.cuda())
+        assert torch.equal(obs_h, obs.cpu()) and torch.equal(rew_h, rew.cpu())
+        assert torch.equal(done_h.bool(), done.cpu())
+    stats = (ctypes.c_int64 * 16)()
+    _lib.check(L.pz_host_stats(ctx, stats), "pz_host_stats")
+    assert list(stats)[:10] == [env.stats_dict()[k] for k in _lib.STAT_NAMES]
+    L.pz_host_destroy(ctx)
+
+
+def test_state_dict_checkpoint_resume(pz):
+    env = pz.PikaVecEnv(1024, seed=4, **CONFIGS["ai_vs_ai"])
+    env.reset()
+    env.rollout(100)
+    sd = env.state_dict()
+    a = env.rollout(50, write_obs=True).clone()
+    env2 = pz.PikaVecEnv(1024, seed=0, **CONFIGS["ai_vs_ai"])
+    env2.load_state_dict(sd)
+    b = env2.rollout(50, write_obs=True)
+    assert torch.equal(a, b)

@@ -1,0 +1,102 @@
+"""GPU: BASELINE.json's full sizes (>= 1 M envs per GPU) through size-independent properties —
+the oracle cannot replay a million games in seconds, so these check invariants of the domain
+plus exact agreement with the oracle on a strided sample of envs."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pyoracle as po
+from oracle.synth import synth_actions_numpy
+
+pytestmark = pytest.mark.gpu
+
+N = 1 << 20
+
+
+@pytest.fixture(scope="module")
+def pz(cuda_lib):
+    import pikazoo_b200
+
+    return pikazoo_b200
+
+
+def _obs_invariants(obs):
+    # player blocks are swapped between agents, ball block shared (pikazoo_env.py:585-586)
+    assert torch.equal(obs[:, 0, 0:13], obs[:, 1, 13:26]) and torch.equal(obs[:, 0, 13:26], obs[:, 1, 0:13])
+    assert torch.equal(obs[:, 0, 26:35], obs[:, 1, 26:35])
+    assert bool((obs[:, 0, 7:12].sum(1) == 1).all()) and bool((obs[:, 0, 20:25].sum(1) == 1).all())
+    assert int(obs[:, 0, 0].min()) >= 32 and int(obs[:, 0, 0].max()) <= 184   # player 1 stays in its half
+    assert int(obs[:, 0, 13].min()) >= 248 and int(obs[:, 0, 13].max()) <= 400
+    assert int(obs[:, 0, 26].min()) >= 20 and int(obs[:, 0, 26].max()) <= 432  # ball x
+    assert int(obs[:, 0, 27].min()) >= 0 and int(obs[:, 0, 27].max()) <= 252   # ball y
+
+
+def test_one_million_envs_per_step_path(pz):
+    steps, sample = 300, slice(0, N, 4099)
+    idx = np.arange(N)[sample]
+    env = pz.PikaVecEnv(N, seed=1234, winning_score=2, serve="random")
+    orcs = po.OracleVecEnv(len(idx), seed=0, winning_score=2, serve="random")
+    for j, i in enumerate(idx):  # oracle envs seeded like the sampled global envs
+        po.lib().pk_init(po._p(orcs.state[j]), 1234 + int(i))
+    obs = env.reset()
+    assert np.array_equal(obs[sample].cpu().numpy(), orcs.reset())
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    prev_total = torch.zeros(N, dtype=torch.int32, device="cuda")
+    for t in range(steps):
+        a = torch.randint(0, 18, (N, 2), generator=gen, device="cuda", dtype=torch.int32)
+        obs, rew, done = env.step(a)
+        o_obs, o_rew, o_done = orcs.step(a[sample].cpu().numpy())
+        assert np.array_equal(obs[sample].cpu().numpy(), o_obs)
+        assert np.array_equal(rew[sample].cpu().numpy(), o_rew.astype(np.float32))
+        assert np.array_equal(done[sample].cpu().numpy(), o_done.astype(bool))
+        if t % 50 == 0 or t == steps - 1:
+            _obs_invariants(obs)
+            assert torch.equal(rew[:, 0], -rew[:, 1]) and bool((rew.abs() <= 1).all())
+            assert bool((rew[done][:, 0] != 0).all())  # a game can only end on a scoring frame
+    d = env.stats_dict()
+    assert d["calls"] == N * steps and d["p1_wins"] + d["p2_wins"] == d["episodes"]
+    st = env.export_state()
+    assert np.array_equal(st[sample].cpu().numpy(), orcs.state)
+    assert int(st[:, 37:39].max()) <= 2
+
+
+def test_one_million_envs_rollout_k64_ai_vs_ai(pz):
+    # config 4: register-resident K = 64 rollout, computer vs computer
+    cfg = dict(winning_score=15, serve="winner", is_player1_computer=True, is_player2_computer=True)
+    env = pz.PikaVecEnv(N, seed=99, **cfg)
+    env.reset()
+    sample = slice(0, N, 8191)
+    idx = np.arange(N)[sample]
+    orcs = po.OracleVecEnv(len(idx), seed=0, **cfg)
+    for j, i in enumerate(idx):
+        po.lib().pk_init(po._p(orcs.state[j]), 99 + int(i))
+    orcs.reset()
+    for l in range(4):
+        env.rollout(64)
+        orcs.rollout(64)
+    st = env.export_state()
+    assert np.array_equal(st[sample].cpu().numpy(), orcs.state)
+    # determinism + equivalence of K = 64 launches and 256 per-step launches on a second instance
+    env2 = pz.PikaVecEnv(N, seed=99, **cfg)
+    env2.reset()
+    for _ in range(256):
+        env2.step(None)
+    assert torch.equal(env2.state, env.state)
+
+
+def test_sharding_is_invisible(pz):
+    # 8(e): trajectories are invariant to how the global batch is split over ranks
+    total, steps = 300_000, 120
+    whole = pz.make_sharded_env(total, 0, 1, "cuda", seed=7, winning_score=1, serve="random")
+    parts = [pz.make_sharded_env(total, r, 3, "cuda", seed=7, winning_score=1, serve="random") for r in range(3)]
+    o = whole.reset()
+    assert torch.equal(o, torch.cat([p.reset() for p in parts]))
+    for t in range(steps):
+        a = torch.from_numpy(synth_actions_numpy(3, 0, total, t, 18)).cuda()
+        o, r, d = whole.step(a)
+        outs = [p.step(a[p.first_env:p.first_env + p.num_envs].contiguous()) for p in parts]
+        assert torch.equal(o, torch.cat([x[0] for x in outs]))
+        assert torch.equal(d, torch.cat([x[2] for x in outs]))
+    tot = torch.stack([p.stats for p in parts]).sum(0)
+    assert torch.equal(tot, whole.stats)

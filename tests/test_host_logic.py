@@ -1,0 +1,109 @@
+"""CPU: host-side logic — sharding, config mirroring, facade argument behaviour, and the
+world_size-2 statistics all-reduce over gloo."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import pikazoo_b200
+from pikazoo_b200 import make_config, shard_range
+from pikazoo_b200 import pikazoo_v0
+from pikazoo_b200.wrappers import RewardByBallPosition, SimplifyAction
+
+
+def test_shard_range_partitions_exactly():
+    for total in (0, 1, 7, 8, 1000, 1 << 20, 16 * (1 << 20) + 3):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0
+            for (f0, c0), (f1, _) in zip(spans, spans[1:]):
+                assert f0 + c0 == f1
+            assert spans[-1][0] + spans[-1][1] == total
+            counts = [c for _, c in spans]
+            assert max(counts) - min(counts) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def test_make_config_mirrors_reference_arguments():
+    c = make_config(winning_score=5, serve="random", is_player2_computer=True, simplify_action=True,
+                    reward_by_ball_position=((0.1,) * 8, 200, 100), action_dtype=torch.int64,
+                    reward_dtype=torch.float64)
+    assert (c.winning_score, c.serve, c.is_player1_computer, c.is_player2_computer) == (5, 2, 0, 1)
+    assert (c.simplify_action, c.reward_by_ball_position, c.x_line, c.y_line) == (1, 1, 200, 100)
+    assert (c.action_dtype, c.reward_dtype) == (1, 1)
+    with pytest.raises(AssertionError):  # reference: assert serve in (...), pikazoo_env.py:104
+        make_config(serve="loser")
+    with pytest.raises(ValueError):
+        make_config(winning_score=0)
+    with pytest.raises(AssertionError):  # reference: assert len(additional_reward) == 8
+        make_config(reward_by_ball_position=((1, 2, 3), 216, 176))
+
+
+def test_facade_surface_matches_reference():
+    env = pikazoo_v0.env(winning_score=7, serve="alternate")
+    assert pikazoo_v0.parallel_env is not None and pikazoo_v0.raw_env is type(env)
+    assert env.possible_agents == ["player_1", "player_2"] and env.agents == env.possible_agents
+    assert env.action_space("player_1").n == 18 and env.action_space("player_2").n == 18
+    sp = env.observation_space("player_1")
+    assert sp.shape == (35,) and sp.dtype == np.int32
+    assert sp.low[0] == 32 and sp.high[0] == 400 and sp.low[33] == -124 and sp.high[26] == 432
+    assert env.metadata["name"] == "pikazoo_v0"
+    with pytest.raises(AssertionError):
+        pikazoo_v0.env(serve="nobody")
+    with pytest.raises(NotImplementedError):
+        pikazoo_v0.env(render_mode="human")
+    w = RewardByBallPosition(SimplifyAction(env), (1, 2, 3, 4, 5, 6, 7, 8))
+    assert w.action_space("player_2").n == 13
+    assert w.unwrapped is env and env._simplify_action and env._reward_by_ball_position[1:] == (216, 176)
+    with pytest.raises(AssertionError):
+        RewardByBallPosition(env, (1, 2, 3))
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(pikazoo_b200.PikaLibraryError):
+        pikazoo_b200.PikaVecEnv(4, device="cpu")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _stats_worker(rank, world, port, total_envs, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    first, count = shard_range(total_envs, world, rank)
+    # each rank contributes the statistics of its own shard: here a function of the global env ids
+    ids = torch.arange(first, first + count, dtype=torch.int64)
+    stats = torch.zeros(16, dtype=torch.int64)
+    stats[0] = count
+    stats[1] = (ids % 3 == 0).sum()
+    stats[2] = ids.sum()
+    pikazoo_b200.allreduce_stats(stats)
+    out[rank] = stats.tolist()
+    dist.destroy_process_group()
+
+
+def test_stats_allreduce_world_size_2_gloo():
+    total = 1001
+    port = _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_stats_worker, args=(2, port, total, out), nprocs=2, join=True)
+        ids = torch.arange(total)
+        want = [total, int((ids % 3 == 0).sum()), int(ids.sum())]
+        assert out[0][:3] == want and out[1][:3] == want
+
+
+def test_allreduce_is_noop_without_process_group():
+    s = torch.arange(16, dtype=torch.int64)
+    assert pikazoo_b200.allreduce_stats(s) is None
+    assert s.tolist() == list(range(16))

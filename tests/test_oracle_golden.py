@@ -1,0 +1,37 @@
+"""CPU: the C oracle reproduces every golden session recorded from the unmodified reference
+(tests/golden/sessions.json, 1,039 full games; generator: oracle/make_golden.py)."""
+
+import numpy as np
+import pytest
+
+from tests.helpers import OracleStepper, replay_group
+
+
+def test_golden_inventory(golden):
+    assert golden["total_games"] >= 1000
+    assert all(g["oracle_checked"] for g in golden["groups"])
+    names = {g["name"] for g in golden["groups"]}
+    assert {"ai_vs_ai_ws15_winner", "random_ws15_winner", "simplify_shaped_ws15",
+            "random_ws5_serve_random"} <= names
+
+
+def test_survey_known_answer(golden):
+    # config 1, seed 0 -> 13,987 frames, 15-5
+    g = next(g for g in golden["groups"] if g["name"] == "ai_vs_ai_ws15_winner")
+    assert g["sessions"][0]["episodes"] == [{"frames": 13987, "scores": [15, 5]}]
+    assert g["sessions"][1]["episodes"] == [{"frames": 11383, "scores": [15, 4]}]
+    # seed 2 never terminates (frame cap)
+    assert g["sessions"][2]["episodes"] == []
+
+
+@pytest.mark.parametrize("name", [
+    "ai_vs_ai_ws15_winner", "random_ws15_winner", "simplify_shaped_ws15", "random_ws5_serve_random",
+    "ai_p1_vs_random_ws7_alternate", "random_vs_ai_p2_ws7_random", "ai_vs_ai_ws3_random_multi",
+])
+def test_oracle_replays_golden_group(golden, name):
+    group = next(g for g in golden["groups"] if g["name"] == name)
+    if name == "ai_vs_ai_ws15_winner":
+        # 1.5 M frames of per-env hashing in Python is slow: first 12 sessions on CPU (all 100 on the GPU suite)
+        group = dict(group, num_envs=12, sessions=group["sessions"][:12])
+    bad = replay_group(group, OracleStepper)
+    assert not bad, bad[:5]
