@@ -165,7 +165,9 @@ def test_step_statistics_match_oracle_bookkeeping(pz):
     assert d["calls"] == n * steps and d["frozen"] == 0 and d["bad_actions"] == 0
     assert d["episodes"] >= n and d["p1_wins"] + d["p2_wins"] == d["episodes"]
     assert d["p1_points"] + d["p2_points"] >= 2 * d["episodes"]
-    assert d["episode_frames"] + int(orc.state[:, 52].sum()) == d["env_steps"]
+    # every step() call belongs to a finished episode or to the episode in progress
+    in_progress = orc.state[:, 40] == 0
+    assert d["episode_frames"] + int(orc.state[in_progress, 52].sum()) == d["env_steps"]
 
 
 def test_host_buffer_path_matches_device_path(pz):
