@@ -200,11 +200,12 @@ __global__ void __launch_bounds__(kThreads) pz_step_kernel(const __grid_constant
             k2 = decode_keys<1, false>(a2, bad2);
         }
         bad = bad1 || bad2;
-        base = step_frame<AI_MASK>(mask, e, d, P.cfg, k1, k2);
+        base = step_frame<AI_MASK>(mask, e, d, P.cfg, k1, k2, stage[warp]);
     } else if (do_reset) {
         reset_env(e, d, P.cfg);
     }
 
+    __syncwarp();  // the staging buffer doubled as the computer players' scratch
     bool pending = false;
     if (P.obs) pending = emit_obs(e, valid, P.obs, i, P.end, stage[warp], lane);
     if (valid) {
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(kThreads) pz_rollout_kernel(const __grid_const
                     k2 = decode_keys<1, false>(a2, b2);
                 }
             }
-            step_frame<AI_MASK>(mask, e, d, P.cfg, k1, k2);
+            step_frame<AI_MASK>(mask, e, d, P.cfg, k1, k2, stage[warp]);
             if (e.game_ended) {
                 st_ep += 1;
                 st_frames += (unsigned)e.ep_frames;
@@ -280,6 +281,7 @@ __global__ void __launch_bounds__(kThreads) pz_rollout_kernel(const __grid_const
         }
     }
 
+    __syncwarp();
     bool pending = false;
     if (P.obs) pending = emit_obs(e, valid, P.obs, i, P.end, stage[warp], lane);
     if (valid) {
@@ -410,6 +412,7 @@ __global__ void __launch_bounds__(kThreads) pz_import_kernel(int32_t *state, int
     e.score[0] = clampi(o[37], 0, 1023), e.score[1] = clampi(o[38], 0, 1023);
     e.round_ended = o[39] != 0, e.game_ended = o[40] != 0, e.p2serve = o[41] != 0;
     e.has32 = o[50] != 0;
+    e.land_ok = 0;
     e.ep_frames = o[52];
     store_env(e, s, i);
     s.g2[i] = make_int4(o[42], o[43], o[44], o[45]);

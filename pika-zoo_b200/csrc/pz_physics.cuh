@@ -128,6 +128,7 @@ __device__ __forceinline__ void new_round(Env &e, DrawCtx &d, const StepCfg &c) 
     b.xv = 0;
     b.yv = 1;
     b.pow = 0;
+    e.land_ok = 0;  // the ball was re-placed: the cached landing point is stale
 }
 
 // raw_env.reset, pikazoo_env.py:149-173 — on a live object: everything not assigned here
@@ -174,6 +175,7 @@ __device__ __forceinline__ void fresh_env(Env &e) {
     e.score[0] = e.score[1] = 0;
     e.round_ended = e.game_ended = e.p2serve = 0;
     e.has32 = 0;
+    e.land_ok = 0;
     e.ep_frames = 0;
 }
 
@@ -212,32 +214,67 @@ __device__ __forceinline__ bool ball_world(Ball &b) {
 // (physics.py:847-884, POWER = true: the whole net zone only bounces yv).
 // Warp-collective over `mask`: every lane of `mask` must call it; lanes with active == false
 // idle. Trip count 1..1000 per lane; the warp leaves when its slowest lane lands.
+//
+// Fast-forward: while the ball is in free flight the reference's loop body is the identity on
+// everything but (x += xv, y += yv, yv += 1). kSkip iterations are applied in closed form when
+// none of the loop's rules can fire in any of them:
+//   wall    (x_j + xv outside [20,432], j < m)        <=> x_1 and x_m inside [20,432] (x is monotone)
+//   ceiling (y_j + yv_j < 0, i.e. y_{j+1} < 0)        <=  yv >= 0, or y_0 - |yv|(|yv|+1)/2 >= 0
+//   net     (|x_j - 216| < 25 and y_j > 176, j < m)   <=  y_0, y_{m-1} <= 176 (y is convex in j), or
+//                                                         x_0 and x_{m-1} on one side outside (191,241)
+//   ground  (y_{j+1} > 252)                           <=> y_1 and y_m <= 252 (convex)
+//   limit   (loop_counter >= 1000)                    <=> it + m < 1000
+// so the result (x at the break and whether the break was the ground) is unchanged.
+constexpr int kSkip = 8;
+
 template <bool POWER>
-__device__ __forceinline__ int simulate_landing_x(unsigned mask, int x, int y, int xv, int yv, bool active) {
+__device__ __forceinline__ int simulate_landing_x(unsigned mask, int x, int y, int xv, int yv, bool active,
+                                                  bool &by_ground) {
     int it = 0;
+    by_ground = false;
     while (__any_sync(mask, active)) {
         if (active) {
-            it += 1;
-            int fx = x + xv;
-            if (fx < kBallRadius || fx > kGroundWidth) xv = -xv;
-            if (y + yv < 0) yv = 1;
-            if (iabs(x - kGroundHalfWidth) < kNetHalfWidth && y > kNetTopTopY) {
-                if (POWER) {
-                    if (yv > 0) yv = -yv;
-                } else {
-                    if (y < kNetTopBottomY) {
+            constexpr int m = kSkip;
+            const int x1 = x + xv, xm1 = x + (m - 1) * xv, xm = xm1 + xv;
+            const int y1 = y + yv;
+            const int ym1 = y + (m - 1) * yv + (m - 1) * (m - 2) / 2;
+            const int ym = y + m * yv + m * (m - 1) / 2;
+            const bool wall_ok = min(x1, xm) >= kBallRadius && max(x1, xm) <= kGroundWidth;
+            const bool ceil_ok = yv >= 0 || 2 * y >= yv * (yv - 1);
+            const bool net_ok = max(y, ym1) <= kNetTopTopY ||
+                                max(x, xm1) <= kGroundHalfWidth - kNetHalfWidth ||
+                                min(x, xm1) >= kGroundHalfWidth + kNetHalfWidth;
+            const bool ground_ok = max(y1, ym) <= kBallGroundY;
+            if (wall_ok && ceil_ok && net_ok && ground_ok && it + m < kLoopLimit) {
+                x = xm;
+                y = ym;
+                yv += m;
+                it += m;
+            } else {
+                it += 1;
+                if (x1 < kBallRadius || x1 > kGroundWidth) xv = -xv;
+                if (y + yv < 0) yv = 1;
+                if (iabs(x - kGroundHalfWidth) < kNetHalfWidth && y > kNetTopTopY) {
+                    if (POWER) {
                         if (yv > 0) yv = -yv;
                     } else {
-                        xv = (x < kGroundHalfWidth) ? -iabs(xv) : iabs(xv);
+                        if (y < kNetTopBottomY) {
+                            if (yv > 0) yv = -yv;
+                        } else {
+                            xv = (x < kGroundHalfWidth) ? -iabs(xv) : iabs(xv);
+                        }
                     }
                 }
-            }
-            y += yv;
-            if (y > kBallGroundY || it >= kLoopLimit) {
-                active = false;
-            } else {
-                x += xv;
-                yv += 1;
+                y += yv;
+                if (y > kBallGroundY) {
+                    active = false;
+                    by_ground = true;
+                } else if (it >= kLoopLimit) {
+                    active = false;
+                } else {
+                    x += xv;
+                    yv += 1;
+                }
             }
         }
     }
@@ -248,7 +285,7 @@ __device__ __forceinline__ int simulate_landing_x(unsigned mask, int x, int y, i
 // let_computer_decide_user_input (physics.py:689-771) + decide_whether_input_power_hit (:774-817).
 // Warp-collective over `mask`.
 template <int I>
-__device__ __forceinline__ void computer_decide(unsigned mask, Env &e, DrawCtx &d, Input &in) {
+__device__ __forceinline__ void computer_decide(unsigned mask, Env &e, DrawCtx &d, Input &in, int *scratch) {
     Player &p = e.p[I];
     const Player &o = e.p[1 - I];
     const Ball &b = e.b;
@@ -286,30 +323,57 @@ __device__ __forceinline__ void computer_decide(unsigned mask, Env &e, DrawCtx &
         search = dx < 48 && iabs(b.y - p.y) < 48;
     }
 
-    // decide_whether_input_power_hit: up to 6 candidate hits, first acceptable one wins.
-    if (__any_sync(mask, search)) {
+    // decide_whether_input_power_hit (:774-817): up to 6 candidate hits (x_direction 1,0 x three
+    // y_directions), the first acceptable one in scan order wins. The candidate simulations have no
+    // side effects, so all 6 of every searching lane are run at once, spread over the lanes of the
+    // warp (one (searcher, candidate) pair per lane and pass), and each searcher then scans its six
+    // results in the reference's order. Inputs and results travel through the warp's scratch.
+    const unsigned sm = __ballot_sync(mask, search);
+    if (sm) {  // warp-uniform
+        const int lane = threadIdx.x & 31;
+        int4 *s_in = reinterpret_cast<int4 *>(scratch);  // [32] {ball x, ball y, |ball yv|, y_first}
+        int *s_out = scratch + 128;                       // [32][6] landing x
         int y_first = 0;
-        if (search) y_first = (d.integers<2>(e.has32) == 0) ? -1 : 1;  // :795 scan order of y_direction
-        bool found = false;
+        if (search) {
+            y_first = (d.integers<2>(e.has32) == 0) ? -1 : 1;  // :795 scan order of y_direction
+            s_in[lane] = make_int4(b.x, b.y, iabs(b.yv), y_first);
+        }
+        __syncwarp(mask);
+        const int total = 6 * __popc(sm), workers = __popc(mask);
+        const int w = __popc(mask & ((1u << lane) - 1u));
 #pragma unroll 1
-        for (int c = 0; c < 6; c++) {
-            const bool act = search && !found;
-            if (!__any_sync(mask, act)) break;
-            const int xd = (c < 3) ? 1 : 0;               // range(1, -1, -1)
-            const int yd = y_first * (1 - (c % 3));       // -1,0,1 or 1,0,-1
-            const int xv0 = (b.x < kGroundHalfWidth) ? (xd + 1) * 10 : -(xd + 1) * 10;  // :841-844
-            const int yv0 = iabs(b.yv) * yd * 2;                                          // :845
-            const int lx = simulate_landing_x<true>(mask, b.x, b.y, xv0, yv0, act);
-            if (act && (lx <= left_boundary || lx >= far_boundary) && iabs(lx - o.x) > kPlayerLength) {
-                in.xdir = xd;
-                in.ydir = yd;
-                found = true;
+        for (int base = 0; base < total; base += workers) {
+            const int q = base + w;
+            const bool act = q < total;
+            const int r = act ? q / 6 : 0, c = act ? q - 6 * r : 0;
+            const int leader = __fns(sm, 0, r + 1);  // lane of the r-th searcher
+            const int4 in4 = s_in[leader];
+            const int xd = (c < 3) ? 1 : 0;             // range(1, -1, -1)
+            const int yd = in4.w * (1 - (c % 3));       // -1,0,1 or 1,0,-1
+            const int xv0 = (in4.x < kGroundHalfWidth) ? (xd + 1) * 10 : -(xd + 1) * 10;  // :841-844
+            const int yv0 = in4.z * yd * 2;                                                // :845
+            bool g;
+            const int lx = simulate_landing_x<true>(mask, in4.x, in4.y, xv0, yv0, act, g);
+            if (act) s_out[leader * 6 + c] = lx;
+        }
+        __syncwarp(mask);
+        if (search) {
+            bool found = false;
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                const int lx = s_out[lane * 6 + c];
+                if (!found && (lx <= left_boundary || lx >= far_boundary) && iabs(lx - o.x) > kPlayerLength) {
+                    in.xdir = (c < 3) ? 1 : 0;
+                    in.ydir = y_first * (1 - (c % 3));
+                    found = true;
+                }
+            }
+            if (found) {  // :768-771
+                in.power = 1;
+                if (iabs(o.x - p.x) < 80 && in.ydir != -1) in.ydir = -1;
             }
         }
-        if (found) {  // :768-771
-            in.power = 1;
-            if (iabs(o.x - p.x) < 80 && in.ydir != -1) in.ydir = -1;
-        }
+        __syncwarp(mask);  // scratch is reused by the other player's search
     }
 }
 
@@ -421,7 +485,7 @@ __device__ __forceinline__ bool ball_player(Env &e, DrawCtx &d, const Input &in)
 // AI_MASK != 0. Returns player_1's base reward (-1, 0, +1).
 template <int AI_MASK>
 __device__ __forceinline__ int step_frame(unsigned mask, Env &e, DrawCtx &d, const StepCfg &c, uint32_t keys1,
-                                          uint32_t keys2) {
+                                          uint32_t keys2, int *scratch) {
     if (e.round_ended) {  // :176-180 (game_ended is false here)
         new_round(e, d, c);
         e.round_ended = 0;
@@ -430,14 +494,29 @@ __device__ __forceinline__ int step_frame(unsigned mask, Env &e, DrawCtx &d, con
     Input in2 = get_input(e.p[1], keys2);
 
     // physics_engine, physics.py:280-337
+    // The real ball update differs from one iteration of the landing simulation only on the ground
+    // (touching) and for y == 192 inside the net zone (<= vs <, :412 vs :670).
+    const bool net192 = e.b.y == kNetTopBottomY && iabs(e.b.x - kGroundHalfWidth) < kNetHalfWidth;
     const bool touching = ball_world(e.b);
     if (AI_MASK != 0) {
-        // :314-315 is evaluated twice per frame on an unchanged ball; once is enough.
-        e.b.land = simulate_landing_x<false>(mask, e.b.x, e.b.y, e.b.xv, e.b.yv, true);
+        // :314-315 is evaluated twice per frame on an unchanged ball; once is enough. And while the
+        // ball free-flies along the trajectory that was simulated last frame (land_ok: that
+        // simulation ended on the ground), the landing point of the advanced ball is the same.
+        const bool need = !e.land_ok || touching || net192;
+        if (__any_sync(mask, need)) {
+            bool g;
+            const int lx = simulate_landing_x<false>(mask, e.b.x, e.b.y, e.b.xv, e.b.yv, need, g);
+            if (need) {
+                e.b.land = lx;
+                e.land_ok = g;
+            }
+        }
+    } else {
+        e.land_ok = 0;  // expected_landing_point_x is not maintained without computer players
     }
-    if (AI_MASK & 1) computer_decide<0>(mask, e, d, in1);
+    if (AI_MASK & 1) computer_decide<0>(mask, e, d, in1, scratch);
     player_move<0>(e.p[0], in1);
-    if (AI_MASK & 2) computer_decide<1>(mask, e, d, in2);
+    if (AI_MASK & 2) computer_decide<1>(mask, e, d, in2, scratch);
     player_move<1>(e.p[1], in2);
 
     bool recalc = ball_player<0>(e, d, in1);
@@ -445,8 +524,12 @@ __device__ __forceinline__ int step_frame(unsigned mask, Env &e, DrawCtx &d, con
     if (AI_MASK != 0) {
         // :331-332 after each new collision; only the value for the final ball state survives.
         if (__any_sync(mask, recalc)) {
-            const int lx = simulate_landing_x<false>(mask, e.b.x, e.b.y, e.b.xv, e.b.yv, recalc);
-            if (recalc) e.b.land = lx;
+            bool g;
+            const int lx = simulate_landing_x<false>(mask, e.b.x, e.b.y, e.b.xv, e.b.yv, recalc, g);
+            if (recalc) {
+                e.b.land = lx;
+                e.land_ok = g;
+            }
         }
     }
 

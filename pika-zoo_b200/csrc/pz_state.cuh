@@ -38,6 +38,8 @@ struct Env {
     int score[2];
     int round_ended, game_ended, p2serve;
     int has32;       // PCG64 buffered-half flag (lives with the env word so it is always resident)
+    int land_ok;     // derived: b.land == landing x of the CURRENT ball and that simulation ended on the
+                     // ground (not at the loop limit), so it stays valid while the ball free-flies
     int ep_frames;   // step() calls since reset (RecordEpisodeStatistics length)
 };
 
@@ -99,7 +101,7 @@ __device__ __forceinline__ void unpack_player(Player &p, uint32_t lo, uint32_t h
 
 // Ball + env, 4 words:
 //   B0  = yv:16 (two's complement) | (xv+32):6 << 16 | pow << 22 | land:9 << 23
-//   B1  = x:9 | y:8 << 9 | px:9 << 17 | has_uint32 << 26
+//   B1  = x:9 | y:8 << 9 | px:9 << 17 | has_uint32 << 26 | land_ok << 27
 //   B2  = ppx:9 | ppy:8 << 9 | py:8 << 17
 //   ENV = score1:10 | score2:10 << 10 | round_ended << 20 | game_ended << 21 | p2serve << 22 | punch:9 << 23
 __device__ __forceinline__ int4 pack_g1(const Env &e) {
@@ -107,7 +109,8 @@ __device__ __forceinline__ int4 pack_g1(const Env &e) {
     int4 w;
     w.x = (int)(((uint32_t)b.yv & 0xFFFFu) | ((uint32_t)(b.xv + 32) << 16) | ((uint32_t)b.pow << 22) |
                 ((uint32_t)b.land << 23));
-    w.y = (int)((uint32_t)b.x | ((uint32_t)b.y << 9) | ((uint32_t)b.px << 17) | ((uint32_t)e.has32 << 26));
+    w.y = (int)((uint32_t)b.x | ((uint32_t)b.y << 9) | ((uint32_t)b.px << 17) | ((uint32_t)e.has32 << 26) |
+                ((uint32_t)e.land_ok << 27));
     w.z = (int)((uint32_t)b.ppx | ((uint32_t)b.ppy << 9) | ((uint32_t)b.py << 17));
     w.w = (int)((uint32_t)e.score[0] | ((uint32_t)e.score[1] << 10) | ((uint32_t)e.round_ended << 20) |
                 ((uint32_t)e.game_ended << 21) | ((uint32_t)e.p2serve << 22) | ((uint32_t)b.punch << 23));
@@ -124,6 +127,7 @@ __device__ __forceinline__ void unpack_g1(Env &e, int4 w) {
     b.y = (b1 >> 9) & 255;
     b.px = (b1 >> 17) & 511;
     e.has32 = (b1 >> 26) & 1;
+    e.land_ok = (b1 >> 27) & 1;
     b.ppx = b2 & 511;
     b.ppy = (b2 >> 9) & 255;
     b.py = (b2 >> 17) & 255;
