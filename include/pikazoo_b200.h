@@ -81,8 +81,12 @@ typedef struct pz_config {
     int32_t autoreset;               /* 1: a call on a terminated env performs reset() (NEXT-STEP) */
     int32_t action_dtype;            /* PZ_ACT_*: element type of actions_dev [n][2] */
     int32_t reward_dtype;            /* PZ_REW_*: element type of reward_dev [n][2] */
-    int32_t reserved;
+    int32_t flags;                   /* PZ_FLAG_* */
 } pz_config;
+
+/* pz_config.flags */
+#define PZ_FLAG_NO_TABLES 1 /* computer players: always run the trajectory simulations iteratively
+                               instead of reading the memoised landing tables (results are identical) */
 
 int pz_version(void);
 int pz_state_words(void);
@@ -116,6 +120,20 @@ int pz_step(int32_t *state_dev, int64_t n, const pz_config *cfg, const void *act
 int pz_rollout(int32_t *state_dev, int64_t n, const pz_config *cfg, int32_t K, int32_t action_source,
                uint64_t action_seed, uint64_t first_env, uint64_t frame0, int32_t *obs_dev,
                int64_t *stats_dev, void *stream);
+
+/* Memoised trajectory simulations for the computer players: two per-device lookup
+ * tables in HBM (pz_tables_bytes() bytes, allocated by the library with cudaMalloc) holding the result
+ * of calculate_expected_landing_point_x_for (physics.py:643-686) and
+ * expected_landing_point_x_when_power_hit (physics.py:820-884) for every ball state with
+ * |y_velocity| <= PZ_TABLE_MAX_YV, built on the device by the same simulation code. They are built
+ * implicitly by the first pz_step / pz_rollout with a computer player and without PZ_FLAG_NO_TABLES
+ * (this synchronises `stream` once); call pz_tables_prepare beforehand when capturing CUDA graphs.
+ * If the allocation fails the kernels silently use the iterative simulations. */
+#define PZ_TABLE_MAX_YV 100
+int pz_tables_prepare(void *stream);
+size_t pz_tables_bytes(void);
+int pz_tables_ready(void); /* 1 if the current device holds built tables */
+void pz_tables_release(void);
 
 /* packed <-> unpacked (int32 [n][53]) conversions, for checkpoints, tests and debugging */
 int pz_export_state(const int32_t *state_dev, int64_t n, int32_t *unpacked_dev, void *stream);

@@ -20,6 +20,7 @@ SERVE_CODES = {"winner": 0, "alternate": 1, "random": 2}
 ACT_I32, ACT_I64, ACT_U8 = 0, 1, 2
 REW_F32, REW_F64 = 0, 1
 ACTIONS_NOOP, ACTIONS_SYNTH = 0, 1
+FLAG_NO_TABLES = 1
 
 STAT_NAMES = (
     "calls", "episodes", "episode_frames", "p1_wins", "p2_wins", "p1_points", "p2_points", "resets",
@@ -43,7 +44,7 @@ class PzConfig(ctypes.Structure):
         ("autoreset", ctypes.c_int32),
         ("action_dtype", ctypes.c_int32),
         ("reward_dtype", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("flags", ctypes.c_int32),
     ]
 
 
@@ -86,6 +87,11 @@ def load() -> ctypes.CDLL:
     for name in ("pz_seed", "pz_seed_array", "pz_reset", "pz_step", "pz_rollout", "pz_export_state",
                  "pz_import_state"):
         getattr(L, name).restype = ctypes.c_int
+    L.pz_tables_prepare.argtypes = [vp]
+    L.pz_tables_prepare.restype = ctypes.c_int
+    L.pz_tables_bytes.restype = ctypes.c_size_t
+    L.pz_tables_ready.restype = ctypes.c_int
+    L.pz_tables_release.restype = None
     # host-buffer path
     L.pz_host_create.argtypes = [ctypes.POINTER(vp), i64, cfgp, u64, u64, i32]
     L.pz_host_create.restype = ctypes.c_int

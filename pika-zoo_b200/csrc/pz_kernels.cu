@@ -9,6 +9,7 @@
 
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 
 #include "../../include/pikazoo_b200.h"
 #include "pz_kernels.cuh"
@@ -405,9 +406,9 @@ __global__ void __launch_bounds__(kThreads) pz_import_kernel(int32_t *state, int
     }
     Ball &b = e.b;
     const int32_t *q = o + 26;
-    b.x = clampi(q[0], 0, 511), b.y = clampi(q[1], 0, 255), b.xv = clampi(q[2], -32, 31);
-    b.yv = clampi(q[3], -32768, 32767), b.px = clampi(q[4], 0, 511), b.py = clampi(q[5], 0, 255);
-    b.ppx = clampi(q[6], 0, 511), b.ppy = clampi(q[7], 0, 255), b.pow = q[8] != 0;
+    b.x = clampi(q[0], 0, 511), b.y = clampi(q[1], -512, 511), b.xv = clampi(q[2], -32, 31);
+    b.yv = clampi(q[3], -32768, 32767), b.px = clampi(q[4], 0, 511), b.py = clampi(q[5], -512, 511);
+    b.ppx = clampi(q[6], 0, 511), b.ppy = clampi(q[7], -512, 511), b.pow = q[8] != 0;
     b.land = clampi(q[9], 0, 511), b.punch = clampi(q[10], 0, 511);
     e.score[0] = clampi(o[37], 0, 1023), e.score[1] = clampi(o[38], 0, 1023);
     e.round_ended = o[39] != 0, e.game_ended = o[40] != 0, e.p2serve = o[41] != 0;
@@ -418,6 +419,81 @@ __global__ void __launch_bounds__(kThreads) pz_import_kernel(int32_t *state, int
     s.g2[i] = make_int4(o[42], o[43], o[44], o[45]);
     s.g3[i] = make_int4(o[46], o[47], o[48], o[49]);
     s.u[i] = (uint32_t)o[51];
+}
+
+// ---- memoised trajectory tables ------------------------------------------------------------------
+// One thread per table entry runs the very simulation the step kernels would run (same code, same
+// warp-collective form; trailing lanes of the last warp recompute the last entry and do not store).
+__global__ void __launch_bounds__(256) pz_build_land_table_kernel(uint16_t *tab) {
+    const int64_t total = kTabLandEntries;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool store = idx < total;
+    if (!store) idx = total - 1;
+    const int x = (int)(idx % kTabNx);
+    int64_t r = idx / kTabNx;
+    const int y = (int)(r % kTabNy);
+    r /= kTabNy;
+    const int xv = (int)(r % kTabNxv) - 20;
+    const int yv = (int)(r / kTabNxv) - kTabYv;
+    bool g;
+    const int lx = simulate_landing_x<false>(kFullMask, x, y, xv, yv, true, g);
+    if (store) tab[idx] = (uint16_t)((unsigned)lx | (g ? 0x8000u : 0u));
+}
+
+__global__ void __launch_bounds__(256) pz_build_power_table_kernel(uint16_t *tab) {
+    const int64_t total = kTabPowerEntries;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool store = idx < total;
+    if (!store) idx = total - 1;
+    const int x = (int)(idx % kTabNx);
+    int64_t r = idx / kTabNx;
+    const int y = (int)(r % kTabNy);
+    r /= kTabNy;
+    const int half_yv0 = (int)(r % kTabNyv) - kTabYv;
+    const int xd = (int)(r / kTabNyv);
+    const int xv0 = (x < kGroundHalfWidth) ? (xd + 1) * 10 : -(xd + 1) * 10;  // physics.py:841-844
+    bool g;
+    const int lx = simulate_landing_x<true>(kFullMask, x, y, xv0, 2 * half_yv0, true, g);
+    if (store) tab[idx] = (uint16_t)((unsigned)lx | (g ? 0x8000u : 0u));
+}
+
+struct DeviceTables {
+    uint16_t *land = nullptr, *power = nullptr;
+    int state = 0;  // 0 = not built, 1 = ready, -1 = allocation failed (iterate instead)
+};
+constexpr int kMaxDevices = 64;
+static DeviceTables g_tables[kMaxDevices];
+static std::mutex g_tables_mu;
+
+// Returns the current device's tables, building them on first use (synchronises `stream` once).
+static const DeviceTables *acquire_tables(cudaStream_t stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    std::lock_guard<std::mutex> lock(g_tables_mu);
+    DeviceTables &t = g_tables[dev];
+    if (t.state == 0) {
+        cudaError_t e1 = cudaMalloc(&t.land, kTabLandEntries * sizeof(uint16_t));
+        cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&t.power, kTabPowerEntries * sizeof(uint16_t)) : e1;
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            if (t.land) cudaFree(t.land);
+            t.land = t.power = nullptr;
+            t.state = -1;
+            cudaGetLastError();  // clear the sticky allocation error: the iterative path needs no table
+        } else {
+            pz_build_land_table_kernel<<<(unsigned)((kTabLandEntries + 255) / 256), 256, 0, stream>>>(t.land);
+            pz_build_power_table_kernel<<<(unsigned)((kTabPowerEntries + 255) / 256), 256, 0, stream>>>(t.power);
+            cudaError_t e3 = cudaStreamSynchronize(stream);
+            if (e3 != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+                cudaFree(t.land);
+                cudaFree(t.power);
+                t.land = t.power = nullptr;
+                t.state = -1;
+            } else {
+                t.state = 1;
+            }
+        }
+    }
+    return t.state == 1 ? &t : nullptr;
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -453,6 +529,16 @@ static void fill_params(KParams &P, int32_t *state, int64_t n, const pz_config *
                 if (c->reward_by_ball_position) r = r + c->additional_reward[agent * 4 + z];
                 P.table[agent * 12 + b * 4 + z] = r;
             }
+}
+
+// Computer players read the memoised trajectory tables unless PZ_FLAG_NO_TABLES is set.
+static void attach_tables(KParams &P, const pz_config *c, cudaStream_t stream) {
+    if ((c->is_player1_computer || c->is_player2_computer) && !(c->flags & PZ_FLAG_NO_TABLES)) {
+        if (const DeviceTables *t = acquire_tables(stream)) {
+            P.cfg.tab_land = t->land;
+            P.cfg.tab_power = t->power;
+        }
+    }
 }
 
 static inline int ai_mask(const pz_config *c) {
@@ -495,6 +581,7 @@ int launch_step(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const
     if (end == begin) return 0;
     KParams P;
     fill_params(P, state_dev, n, cfg);
+    attach_tables(P, cfg, st);
     P.begin = begin;
     P.end = end;
     P.actions = actions_dev;
@@ -580,6 +667,7 @@ int pz_rollout(int32_t *state_dev, int64_t n, const pz_config *cfg, int32_t K, i
     if (n == 0) return 0;
     KParams P;
     fill_params(P, state_dev, n, cfg);
+    attach_tables(P, cfg, (cudaStream_t)stream);
     P.obs = obs_dev;
     P.stats = reinterpret_cast<unsigned long long *>(stats_dev);
     P.K = K;
@@ -595,6 +683,31 @@ int pz_rollout(int32_t *state_dev, int64_t n, const pz_config *cfg, int32_t K, i
         default: pz_rollout_kernel<3><<<grid_for(n), kThreads, 0, st>>>(P); break;
     }
     return launch_status();
+}
+
+int pz_tables_prepare(void *stream) { return acquire_tables((cudaStream_t)stream) ? 0 : (int)cudaErrorMemoryAllocation; }
+
+size_t pz_tables_bytes(void) { return (size_t)(kTabLandEntries + kTabPowerEntries) * sizeof(uint16_t); }
+
+int pz_tables_ready(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+    std::lock_guard<std::mutex> lock(g_tables_mu);
+    return g_tables[dev].state == 1;
+}
+
+void pz_tables_release(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return;
+    std::lock_guard<std::mutex> lock(g_tables_mu);
+    DeviceTables &t = g_tables[dev];
+    if (t.state == 1) {
+        cudaDeviceSynchronize();
+        cudaFree(t.land);
+        cudaFree(t.power);
+    }
+    t.land = t.power = nullptr;
+    t.state = 0;
 }
 
 int pz_export_state(const int32_t *state_dev, int64_t n, int32_t *unpacked_dev, void *stream) {

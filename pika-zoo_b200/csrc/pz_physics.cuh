@@ -15,10 +15,31 @@ constexpr unsigned kFullMask = 0xFFFFFFFFu;
 
 __device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }
 
+// Memoised trajectory simulations (see simulate_landing_x): value = landing x | ended-on-ground << 15.
+//   land [yv + kTabYv][xv + 20][y][x]                        yv in [-kTabYv, kTabYv], xv in [-20, 20]
+//   power[x_direction][yv0 / 2 + kTabYv][y][x]               yv0 = |ball yv| * y_direction * 2
+// with y in [0, 252] and x in [0, 432].
+constexpr int kTabYv = 100;
+constexpr int kTabNx = kGroundWidth + 1, kTabNy = kBallGroundY + 1, kTabNxv = 41, kTabNyv = 2 * kTabYv + 1;
+constexpr int64_t kTabLandEntries = (int64_t)kTabNyv * kTabNxv * kTabNy * kTabNx;
+constexpr int64_t kTabPowerEntries = (int64_t)2 * kTabNyv * kTabNy * kTabNx;
+
+__host__ __device__ __forceinline__ int tab_land_index(int x, int y, int xv, int yv) {
+    return (((yv + kTabYv) * kTabNxv + (xv + 20)) * kTabNy + y) * kTabNx + x;
+}
+__host__ __device__ __forceinline__ int tab_power_index(int x, int y, int xd, int half_yv0) {
+    return ((xd * kTabNyv + (half_yv0 + kTabYv)) * kTabNy + y) * kTabNx + x;
+}
+__device__ __forceinline__ bool tab_pos_ok(int x, int y) {
+    return (unsigned)x < (unsigned)kTabNx && (unsigned)y < (unsigned)kTabNy;
+}
+
 // Per-launch constants (uniform over the grid)
 struct StepCfg {
     int winning_score;
     int serve;  // PZ_SERVE_*
+    const uint16_t *tab_land;   // nullptr: iterate
+    const uint16_t *tab_power;
 };
 
 // Lazily loaded PCG64 stream of the env owned by this thread.
@@ -219,7 +240,8 @@ __device__ __forceinline__ bool ball_world(Ball &b) {
 // everything but (x += xv, y += yv, yv += 1). kSkip iterations are applied in closed form when
 // none of the loop's rules can fire in any of them:
 //   wall    (x_j + xv outside [20,432], j < m)        <=> x_1 and x_m inside [20,432] (x is monotone)
-//   ceiling (y_j + yv_j < 0, i.e. y_{j+1} < 0)        <=  yv >= 0, or y_0 - |yv|(|yv|+1)/2 >= 0
+//   ceiling (y_j + yv_j < 0, i.e. y_{j+1} < 0)        <=  yv >= 0 and y_1 >= 0 (y can be negative after a
+//                                                         net bounce), or yv < 0 and y_0 - |yv|(|yv|+1)/2 >= 0
 //   net     (|x_j - 216| < 25 and y_j > 176, j < m)   <=  y_0, y_{m-1} <= 176 (y is convex in j), or
 //                                                         x_0 and x_{m-1} on one side outside (191,241)
 //   ground  (y_{j+1} > 252)                           <=> y_1 and y_m <= 252 (convex)
@@ -240,7 +262,7 @@ __device__ __forceinline__ int simulate_landing_x(unsigned mask, int x, int y, i
             const int ym1 = y + (m - 1) * yv + (m - 1) * (m - 2) / 2;
             const int ym = y + m * yv + m * (m - 1) / 2;
             const bool wall_ok = min(x1, xm) >= kBallRadius && max(x1, xm) <= kGroundWidth;
-            const bool ceil_ok = yv >= 0 || 2 * y >= yv * (yv - 1);
+            const bool ceil_ok = yv >= 0 ? (y1 >= 0) : (2 * y >= yv * (yv - 1));
             const bool net_ok = max(y, ym1) <= kNetTopTopY ||
                                 max(x, xm1) <= kGroundHalfWidth - kNetHalfWidth ||
                                 min(x, xm1) >= kGroundHalfWidth + kNetHalfWidth;
@@ -281,11 +303,33 @@ __device__ __forceinline__ int simulate_landing_x(unsigned mask, int x, int y, i
     return x;
 }
 
+// expected landing x of the current ball for the lanes with `need`; memoised when possible.
+__device__ __forceinline__ void update_landing(unsigned mask, Env &e, const StepCfg &c, bool need) {
+    const Ball &b = e.b;
+    if (c.tab_land != nullptr) {
+        if (need && iabs(b.yv) <= kTabYv && iabs(b.xv) <= 20 && tab_pos_ok(b.x, b.y)) {
+            const unsigned v = __ldg(c.tab_land + tab_land_index(b.x, b.y, b.xv, b.yv));
+            e.b.land = (int)(v & 0x7FFFu);
+            e.land_ok = (int)(v >> 15);
+            need = false;
+        }
+    }
+    if (__any_sync(mask, need)) {  // outside the memoised domain, or tables off
+        bool g;
+        const int lx = simulate_landing_x<false>(mask, b.x, b.y, b.xv, b.yv, need, g);
+        if (need) {
+            e.b.land = lx;
+            e.land_ok = g;
+        }
+    }
+}
+
 // ---- computer player ---------------------------------------------------------------------------
 // let_computer_decide_user_input (physics.py:689-771) + decide_whether_input_power_hit (:774-817).
 // Warp-collective over `mask`.
 template <int I>
-__device__ __forceinline__ void computer_decide(unsigned mask, Env &e, DrawCtx &d, Input &in, int *scratch) {
+__device__ __forceinline__ void computer_decide(unsigned mask, Env &e, DrawCtx &d, const StepCfg &cfg, Input &in,
+                                                int *scratch) {
     Player &p = e.p[I];
     const Player &o = e.p[1 - I];
     const Ball &b = e.b;
@@ -325,19 +369,36 @@ __device__ __forceinline__ void computer_decide(unsigned mask, Env &e, DrawCtx &
 
     // decide_whether_input_power_hit (:774-817): up to 6 candidate hits (x_direction 1,0 x three
     // y_directions), the first acceptable one in scan order wins. The candidate simulations have no
-    // side effects, so all 6 of every searching lane are run at once, spread over the lanes of the
-    // warp (one (searcher, candidate) pair per lane and pass), and each searcher then scans its six
-    // results in the reference's order. Inputs and results travel through the warp's scratch.
+    // side effects, so all 6 are evaluated and then scanned in the reference's order: from the
+    // memoised table when the ball is inside its domain, otherwise iteratively, spread over the
+    // lanes of the warp (one (searcher, candidate) pair per lane and pass, through the warp's scratch).
+    int y_first = 0;
+    if (search) y_first = (d.integers<2>(e.has32) == 0) ? -1 : 1;  // :795 scan order of y_direction
+    const int ayv = iabs(b.yv);
+    bool found = false;
+    if (cfg.tab_power != nullptr && search && ayv <= kTabYv && tab_pos_ok(b.x, b.y)) {
+        // memoised: six independent loads, scanned in the reference's order
+        int lx[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++)
+            lx[c] = (int)(__ldg(cfg.tab_power + tab_power_index(b.x, b.y, (c < 3) ? 1 : 0,
+                                                                 ayv * y_first * (1 - (c % 3)))) & 0x7FFFu);
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            if (!found && (lx[c] <= left_boundary || lx[c] >= far_boundary) && iabs(lx[c] - o.x) > kPlayerLength) {
+                in.xdir = (c < 3) ? 1 : 0;
+                in.ydir = y_first * (1 - (c % 3));
+                found = true;
+            }
+        }
+        search = false;
+    }
     const unsigned sm = __ballot_sync(mask, search);
-    if (sm) {  // warp-uniform
+    if (sm) {  // warp-uniform: lanes outside the memoised domain, or tables off
         const int lane = threadIdx.x & 31;
         int4 *s_in = reinterpret_cast<int4 *>(scratch);  // [32] {ball x, ball y, |ball yv|, y_first}
         int *s_out = scratch + 128;                       // [32][6] landing x
-        int y_first = 0;
-        if (search) {
-            y_first = (d.integers<2>(e.has32) == 0) ? -1 : 1;  // :795 scan order of y_direction
-            s_in[lane] = make_int4(b.x, b.y, iabs(b.yv), y_first);
-        }
+        if (search) s_in[lane] = make_int4(b.x, b.y, ayv, y_first);
         __syncwarp(mask);
         const int total = 6 * __popc(sm), workers = __popc(mask);
         const int w = __popc(mask & ((1u << lane) - 1u));
@@ -358,7 +419,6 @@ __device__ __forceinline__ void computer_decide(unsigned mask, Env &e, DrawCtx &
         }
         __syncwarp(mask);
         if (search) {
-            bool found = false;
 #pragma unroll
             for (int c = 0; c < 6; c++) {
                 const int lx = s_out[lane * 6 + c];
@@ -368,12 +428,12 @@ __device__ __forceinline__ void computer_decide(unsigned mask, Env &e, DrawCtx &
                     found = true;
                 }
             }
-            if (found) {  // :768-771
-                in.power = 1;
-                if (iabs(o.x - p.x) < 80 && in.ydir != -1) in.ydir = -1;
-            }
         }
         __syncwarp(mask);  // scratch is reused by the other player's search
+    }
+    if (found) {  // :768-771
+        in.power = 1;
+        if (iabs(o.x - p.x) < 80 && in.ydir != -1) in.ydir = -1;
     }
 }
 
@@ -502,35 +562,20 @@ __device__ __forceinline__ int step_frame(unsigned mask, Env &e, DrawCtx &d, con
         // :314-315 is evaluated twice per frame on an unchanged ball; once is enough. And while the
         // ball free-flies along the trajectory that was simulated last frame (land_ok: that
         // simulation ended on the ground), the landing point of the advanced ball is the same.
-        const bool need = !e.land_ok || touching || net192;
-        if (__any_sync(mask, need)) {
-            bool g;
-            const int lx = simulate_landing_x<false>(mask, e.b.x, e.b.y, e.b.xv, e.b.yv, need, g);
-            if (need) {
-                e.b.land = lx;
-                e.land_ok = g;
-            }
-        }
+        update_landing(mask, e, c, !e.land_ok || touching || net192);
     } else {
         e.land_ok = 0;  // expected_landing_point_x is not maintained without computer players
     }
-    if (AI_MASK & 1) computer_decide<0>(mask, e, d, in1, scratch);
+    if (AI_MASK & 1) computer_decide<0>(mask, e, d, c, in1, scratch);
     player_move<0>(e.p[0], in1);
-    if (AI_MASK & 2) computer_decide<1>(mask, e, d, in2, scratch);
+    if (AI_MASK & 2) computer_decide<1>(mask, e, d, c, in2, scratch);
     player_move<1>(e.p[1], in2);
 
     bool recalc = ball_player<0>(e, d, in1);
     recalc |= ball_player<1>(e, d, in2);
     if (AI_MASK != 0) {
         // :331-332 after each new collision; only the value for the final ball state survives.
-        if (__any_sync(mask, recalc)) {
-            bool g;
-            const int lx = simulate_landing_x<false>(mask, e.b.x, e.b.y, e.b.xv, e.b.yv, recalc, g);
-            if (recalc) {
-                e.b.land = lx;
-                e.land_ok = g;
-            }
-        }
+        if (__any_sync(mask, recalc)) update_landing(mask, e, c, recalc);
     }
 
     // scoring, :190-210

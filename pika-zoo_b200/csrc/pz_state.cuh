@@ -101,17 +101,21 @@ __device__ __forceinline__ void unpack_player(Player &p, uint32_t lo, uint32_t h
 
 // Ball + env, 4 words:
 //   B0  = yv:16 (two's complement) | (xv+32):6 << 16 | pow << 22 | land:9 << 23
-//   B1  = x:9 | y:8 << 9 | px:9 << 17 | has_uint32 << 26 | land_ok << 27
-//   B2  = ppx:9 | ppy:8 << 9 | py:8 << 17
+//   B1  = x:9 | px:9 << 9 | ppx:9 << 18 | has_uint32 << 27 | land_ok << 28
+//   B2  = (y+512):10 | (py+512):10 << 10 | (ppy+512):10 << 20
 //   ENV = score1:10 | score2:10 << 10 | round_ended << 20 | game_ended << 21 | p2serve << 22 | punch:9 << 23
+// Ball y is signed: with |yv| > 176 the net-top bounce (physics.py:412-414, applied after the
+// ceiling test :408-409) throws the ball above the ceiling for one frame, y = 177 - |yv| at the
+// lowest; 10 bits cover |yv| <= 689, 16 bits of yv cover every velocity the doubling power hits
+// can build before the ball leaves the court.
 __device__ __forceinline__ int4 pack_g1(const Env &e) {
     const Ball &b = e.b;
     int4 w;
     w.x = (int)(((uint32_t)b.yv & 0xFFFFu) | ((uint32_t)(b.xv + 32) << 16) | ((uint32_t)b.pow << 22) |
                 ((uint32_t)b.land << 23));
-    w.y = (int)((uint32_t)b.x | ((uint32_t)b.y << 9) | ((uint32_t)b.px << 17) | ((uint32_t)e.has32 << 26) |
-                ((uint32_t)e.land_ok << 27));
-    w.z = (int)((uint32_t)b.ppx | ((uint32_t)b.ppy << 9) | ((uint32_t)b.py << 17));
+    w.y = (int)((uint32_t)b.x | ((uint32_t)b.px << 9) | ((uint32_t)b.ppx << 18) | ((uint32_t)e.has32 << 27) |
+                ((uint32_t)e.land_ok << 28));
+    w.z = (int)((uint32_t)(b.y + 512) | ((uint32_t)(b.py + 512) << 10) | ((uint32_t)(b.ppy + 512) << 20));
     w.w = (int)((uint32_t)e.score[0] | ((uint32_t)e.score[1] << 10) | ((uint32_t)e.round_ended << 20) |
                 ((uint32_t)e.game_ended << 21) | ((uint32_t)e.p2serve << 22) | ((uint32_t)b.punch << 23));
     return w;
@@ -124,13 +128,13 @@ __device__ __forceinline__ void unpack_g1(Env &e, int4 w) {
     b.pow = (b0 >> 22) & 1;
     b.land = (b0 >> 23) & 511;
     b.x = b1 & 511;
-    b.y = (b1 >> 9) & 255;
-    b.px = (b1 >> 17) & 511;
-    e.has32 = (b1 >> 26) & 1;
-    e.land_ok = (b1 >> 27) & 1;
-    b.ppx = b2 & 511;
-    b.ppy = (b2 >> 9) & 255;
-    b.py = (b2 >> 17) & 255;
+    b.px = (b1 >> 9) & 511;
+    b.ppx = (b1 >> 18) & 511;
+    e.has32 = (b1 >> 27) & 1;
+    e.land_ok = (b1 >> 28) & 1;
+    b.y = (int)(b2 & 1023) - 512;
+    b.py = (int)((b2 >> 10) & 1023) - 512;
+    b.ppy = (int)((b2 >> 20) & 1023) - 512;
     e.score[0] = ev & 1023;
     e.score[1] = (ev >> 10) & 1023;
     e.round_ended = (ev >> 20) & 1;

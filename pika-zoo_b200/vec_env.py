@@ -41,6 +41,7 @@ def make_config(
     autoreset: bool = True,
     action_dtype: torch.dtype = torch.int32,
     reward_dtype: torch.dtype = torch.float32,
+    landing_tables: bool = True,
 ) -> _lib.PzConfig:
     assert serve in ("winner", "alternate", "random")  # pikazoo_env.py:104
     if not 1 <= int(winning_score) <= 1023:
@@ -62,6 +63,7 @@ def make_config(
     c.autoreset = int(bool(autoreset))
     c.action_dtype = _ACT_DTYPES[action_dtype]
     c.reward_dtype = _REW_DTYPES[reward_dtype]
+    c.flags = 0 if landing_tables else _lib.FLAG_NO_TABLES
     return c
 
 
@@ -88,6 +90,7 @@ class PikaVecEnv:
         reward_dtype: torch.dtype = torch.float32,
         first_env: int = 0,
         track_stats: bool = True,
+        landing_tables: "bool | str" = "auto",
     ):
         self.lib = _lib.load()
         self.device = torch.device(device)
@@ -100,11 +103,17 @@ class PikaVecEnv:
             raise ValueError("num_envs must be >= 1")
         self.seed = int(seed)
         self.first_env = int(first_env)
+        # Computer players can read their trajectory simulations from memoised per-device tables
+        # (1.9 GB of HBM, built once on first use; results identical). "auto": only for batches
+        # large enough for the tables to pay for themselves.
+        if landing_tables == "auto":
+            landing_tables = self.num_envs >= 4096
+        self.landing_tables = bool(landing_tables)
         self._kw = dict(
             winning_score=winning_score, serve=serve, is_player1_computer=is_player1_computer,
             is_player2_computer=is_player2_computer, simplify_action=simplify_action,
             reward_by_ball_position=reward_by_ball_position, autoreset=autoreset,
-            action_dtype=action_dtype, reward_dtype=reward_dtype,
+            action_dtype=action_dtype, reward_dtype=reward_dtype, landing_tables=self.landing_tables,
         )
         self.cfg = make_config(**self._kw)
         self.action_dtype = action_dtype

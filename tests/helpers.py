@@ -129,13 +129,15 @@ class OracleStepper:
 
 
 class CudaStepper:
+    landing_tables = "auto"
+
     def __init__(self, n, base_seed, cfg):
         import torch
         import pikazoo_b200
 
         self.torch = torch
         self.env = pikazoo_b200.PikaVecEnv(n, device="cuda", seed=base_seed, autoreset=True,
-                                           reward_dtype=torch.float64, **cfg)
+                                           reward_dtype=torch.float64, landing_tables=self.landing_tables, **cfg)
 
     def reset(self):
         return self.env.reset().cpu().numpy()
@@ -150,3 +152,15 @@ class CudaStepper:
 
     def final_state(self):
         return self.env.export_state().cpu().numpy()
+
+
+class CudaStepperTables(CudaStepper):
+    """Computer players read the memoised trajectory tables."""
+
+    landing_tables = True
+
+
+class CudaStepperIterative(CudaStepper):
+    """Computer players iterate every trajectory simulation (PZ_FLAG_NO_TABLES)."""
+
+    landing_tables = False

@@ -70,4 +70,4 @@ def test_config_struct_layout_matches_header(cuda_lib):
     c = PzConfig()
     cuda_lib.pz_default_config(ctypes.byref(c))
     assert (c.winning_score, c.serve, c.x_line, c.y_line, c.autoreset) == (15, 0, 216, 176, 1)
-    assert ctypes.sizeof(PzConfig) == 8 * 4 + 8 * 8 + 4 * 4
+    assert ctypes.sizeof(PzConfig) == 8 * 4 + 8 * 8 + 4 * 4 and PzConfig.flags.offset == 108

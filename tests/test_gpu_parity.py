@@ -10,7 +10,7 @@ import torch
 
 from oracle import pyoracle as po
 from oracle.synth import synth_actions_numpy
-from tests.helpers import CudaStepper, replay_group
+from tests.helpers import CudaStepperIterative, CudaStepperTables, replay_group
 
 pytestmark = pytest.mark.gpu
 
@@ -29,9 +29,13 @@ def pz(cuda_lib):
     "ai_vs_ai_ws15_winner", "random_ws15_winner", "simplify_shaped_ws15", "random_ws5_serve_random",
     "ai_p1_vs_random_ws7_alternate", "random_vs_ai_p2_ws7_random", "ai_vs_ai_ws3_random_multi",
 ])
-def test_cuda_replays_reference_golden_games(pz, golden, name):
+@pytest.mark.parametrize("stepper", [CudaStepperIterative, CudaStepperTables], ids=["iterative", "tables"])
+def test_cuda_replays_reference_golden_games(pz, golden, name, stepper):
     group = next(g for g in golden["groups"] if g["name"] == name)
-    bad = replay_group(group, CudaStepper)
+    has_ai = group["config"].get("is_player1_computer") or group["config"].get("is_player2_computer")
+    if stepper is CudaStepperTables and not has_ai:
+        pytest.skip("no computer player: the trajectory tables are not used")
+    bad = replay_group(group, stepper)
     assert not bad, bad[:5]
 
 
@@ -47,9 +51,9 @@ CONFIGS = {
 
 
 def _lockstep(pz, n, steps, cfg, seed, autoreset=True, check_every=1, action_dtype=torch.int32,
-              reward_dtype=torch.float64):
+              reward_dtype=torch.float64, landing_tables="auto"):
     env = pz.PikaVecEnv(n, seed=seed, autoreset=autoreset, action_dtype=action_dtype, reward_dtype=reward_dtype,
-                        **cfg)
+                        landing_tables=landing_tables, **cfg)
     orc = po.OracleVecEnv(n, seed=seed, autoreset=autoreset, **cfg)
     n_actions = 13 if cfg.get("simplify_action") else 18
     assert np.array_equal(env.reset().cpu().numpy(), orc.reset())
@@ -73,6 +77,41 @@ def _lockstep(pz, n, steps, cfg, seed, autoreset=True, check_every=1, action_dty
 def test_cuda_matches_oracle_4096_envs(pz, cfg_name):
     # config 2 of BASELINE.json (4,096 envs) and its variants; every output compared on every step
     _lockstep(pz, 4096, 1500, CONFIGS[cfg_name], seed=20_000)
+
+
+@pytest.mark.parametrize("cfg_name", ["ai_vs_ai", "ai_p1", "ai_p2_random_serve", "ws1"])
+def test_cuda_iterative_simulations_match_oracle(pz, cfg_name):
+    # the same with the memoised tables switched off (PZ_FLAG_NO_TABLES): warp-collective loops only
+    _lockstep(pz, 4096, 1500, CONFIGS[cfg_name], seed=30_000, landing_tables=False)
+
+
+def test_trajectory_tables_equal_iterative_simulation(pz):
+    """The tables are a memo of the iterative simulation: same kernels, flag on/off, must agree
+    on every env of a large batch, and the out-of-domain fallback (|ball yv| > 100) must work."""
+    from pikazoo_b200 import _lib
+
+    n = 200_000
+    kw = dict(seed=5, winning_score=15, serve="random", is_player1_computer=True, is_player2_computer=True)
+    a = pz.PikaVecEnv(n, landing_tables=True, **kw)
+    b = pz.PikaVecEnv(n, landing_tables=False, **kw)
+    a.reset(), b.reset()
+    assert _lib.load().pz_tables_bytes() > 1 << 30
+    for _ in range(6):
+        a.rollout(64), b.rollout(64)
+        assert torch.equal(a.export_state(), b.export_state())
+    assert _lib.load().pz_tables_ready() == 1
+    # force states outside the memoised domain: huge ball y velocities
+    st = a.export_state()
+    st[::3, 29] = 150
+    st[1::3, 29] = -140
+    a.import_state(st), b.import_state(st)
+    orc = po.OracleVecEnv(n, **{k: v for k, v in kw.items() if k != "seed"})
+    orc.state[:] = st.cpu().numpy()
+    for _ in range(3):
+        a.rollout(16), b.rollout(16), orc.rollout(16)
+        sa = a.export_state()
+        assert torch.equal(sa, b.export_state())
+        assert np.array_equal(sa.cpu().numpy(), orc.state)
 
 
 @pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 127, 128, 129, 1000])
@@ -121,13 +160,13 @@ def test_export_import_round_trip_and_seeding(pz):
     other = pz.PikaVecEnv(n, seed=999, **CONFIGS["ai_vs_ai"])
     other.import_state(st)
     assert torch.equal(other.export_state(), st)
-    # the packed form is canonical up to the derived landing-cache bit (B1 bit 27), which import clears
+    # the packed form is canonical up to the derived landing-cache bit (B1 bit 28), which import clears
     n_ = env.num_envs
     a_, b_ = env.state.clone(), other.state.clone()
     a_[5 * n_ - 0:0] = 0  # no-op slice keeps flake8 quiet about unused names
     w1 = slice(4 * n_ + 1, 8 * n_, 4)
-    a_[w1] &= ~(1 << 27)
-    b_[w1] &= ~(1 << 27)
+    a_[w1] &= ~(1 << 28)
+    b_[w1] &= ~(1 << 28)
     assert torch.equal(a_, b_)
     a, b = env.step(None)[0].clone(), other.step(None)[0].clone()
     assert torch.equal(a, b)
@@ -140,10 +179,11 @@ def test_export_import_round_trip_and_seeding(pz):
 
 @pytest.mark.parametrize("cfg_name,actions", [("ai_vs_ai", "noop"), ("random18", "synth"), ("wrappers", "synth"),
                                               ("ai_p2_random_serve", "synth"), ("ws1", "noop")])
-def test_rollout_matches_oracle(pz, cfg_name, actions):
+@pytest.mark.parametrize("tables", [False, True], ids=["iterative", "tables"])
+def test_rollout_matches_oracle(pz, cfg_name, actions, tables):
     cfg = CONFIGS[cfg_name]
     n, K, launches = 2048 + 17, 64, 12
-    env = pz.PikaVecEnv(n, seed=31, first_env=1000, **cfg)
+    env = pz.PikaVecEnv(n, seed=31, first_env=1000, landing_tables=tables, **cfg)
     orc = po.OracleVecEnv(n, seed=31 + 1000, **cfg)
     env.reset(), orc.reset()
     stats = np.zeros(8, dtype=np.int64)
