@@ -347,14 +347,8 @@ static void calculate_expected_landing_point_x_for(pk_ball *b) {
     b->expected_landing_point_x = x;
 }
 
-/* expected_landing_point_x_when_power_hit, physics.py:820-884 */
-static int32_t expected_landing_point_x_when_power_hit(int x_dir, int y_dir, const pk_ball *b) {
-    int32_t x = b->x, y = b->y, xv, yv;
-    if (x < GROUND_HALF_WIDTH)
-        xv = (iabs(x_dir) + 1) * 10;
-    else
-        xv = -(iabs(x_dir) + 1) * 10;
-    yv = iabs(b->y_velocity) * y_dir * 2;
+/* the loop of expected_landing_point_x_when_power_hit, physics.py:847-884 */
+static int32_t power_hit_loop(int32_t x, int32_t y, int32_t xv, int32_t yv) {
     int loop_counter = 0;
     for (;;) {
         loop_counter += 1;
@@ -368,6 +362,31 @@ static int32_t expected_landing_point_x_when_power_hit(int x_dir, int y_dir, con
         if (y > BALL_TOUCHING_GROUND_Y_COORD || loop_counter >= INFINITE_LOOP_LIMIT) return x;
         x = x + xv;
         yv += 1;
+    }
+}
+
+/* expected_landing_point_x_when_power_hit, physics.py:820-884 */
+static int32_t expected_landing_point_x_when_power_hit(int x_dir, int y_dir, const pk_ball *b) {
+    int32_t xv;
+    if (b->x < GROUND_HALF_WIDTH)
+        xv = (iabs(x_dir) + 1) * 10;
+    else
+        xv = -(iabs(x_dir) + 1) * 10;
+    return power_hit_loop(b->x, b->y, xv, iabs(b->y_velocity) * y_dir * 2);
+}
+
+/* test helper: the two trajectory loops on n arbitrary (x, y, x_velocity, y_velocity) starts */
+void pk_simulate_many(int64_t n, const int32_t *xyv, int power, int32_t *out) {
+    for (int64_t i = 0; i < n; i++) {
+        const int32_t *q = xyv + 4 * i;
+        if (power) {
+            out[i] = power_hit_loop(q[0], q[1], q[2], q[3]);
+        } else {
+            pk_ball b;
+            b.x = q[0], b.y = q[1], b.x_velocity = q[2], b.y_velocity = q[3];
+            calculate_expected_landing_point_x_for(&b);
+            out[i] = b.expected_landing_point_x;
+        }
     }
 }
 

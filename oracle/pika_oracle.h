@@ -110,6 +110,11 @@ int64_t pk_vec_rollout(pk_env *envs, int64_t n, const pk_config *c, int K, int a
                        uint64_t action_seed, uint64_t first_env, uint64_t frame0,
                        int64_t *stats);
 
+/* Test helper: calculate_expected_landing_point_x_for (power = 0, physics.py:643-686) or the loop of
+ * expected_landing_point_x_when_power_hit (power = 1, physics.py:847-884) started from
+ * xyv[i] = {x, y, x_velocity, y_velocity}; out[i] = landing x. */
+void pk_simulate_many(int64_t n, const int32_t *xyv, int power, int32_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,8 @@ def lib():
         L.pk_synth_action.restype = i32
         L.pk_vec_rollout.argtypes = [vp, i64, cfgp, ctypes.c_int, ctypes.c_int, u64, u64, u64, vp]
         L.pk_vec_rollout.restype = i64
+        L.pk_simulate_many.argtypes = [i64, vp, ctypes.c_int, vp]
+        L.pk_simulate_many.restype = None
         assert L.pk_env_words() == ENV_WORDS
         _lib = L
     return _lib
@@ -152,3 +154,11 @@ def pcg64_seed(seed: int):
 
 def synth_action(action_seed, global_env, frame, agent, n_actions=18) -> int:
     return int(lib().pk_synth_action(int(action_seed), int(global_env), int(frame), int(agent), int(n_actions)))
+
+
+def simulate_many(xyv: np.ndarray, power: bool) -> np.ndarray:
+    """Landing x of the reference's trajectory loops from starts xyv[n, 4] = (x, y, xv, yv)."""
+    q = np.ascontiguousarray(xyv, dtype=np.int32).reshape(-1, 4)
+    out = np.zeros(len(q), dtype=np.int32)
+    lib().pk_simulate_many(len(q), _p(q), int(bool(power)), _p(out))
+    return out

@@ -365,56 +365,20 @@ __global__ void __launch_bounds__(kThreads) pz_export_kernel(const int32_t *stat
     Env e;
     load_env(e, s, i);
     int32_t *o = out + i * PZ_UNPACKED_WORDS;
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const Player &p = e.p[k];
-        int32_t *q = o + 13 * k;
-        q[0] = p.x, q[1] = p.y, q[2] = p.yv, q[3] = p.state, q[4] = p.frame, q[5] = p.delay, q[6] = p.arm;
-        q[7] = p.dive, q[8] = p.lying, q[9] = p.coll, q[10] = p.bold, q[11] = p.standby, q[12] = p.keyprev;
-    }
-    const Ball &b = e.b;
-    int32_t *q = o + 26;
-    q[0] = b.x, q[1] = b.y, q[2] = b.xv, q[3] = b.yv, q[4] = b.px, q[5] = b.py, q[6] = b.ppx, q[7] = b.ppy;
-    q[8] = b.pow, q[9] = b.land, q[10] = b.punch;
-    o[37] = e.score[0], o[38] = e.score[1], o[39] = e.round_ended, o[40] = e.game_ended, o[41] = e.p2serve;
+    env_to_unpacked(e, o);
     const int4 st = s.g2[i], ic = s.g3[i];
     o[42] = st.x, o[43] = st.y, o[44] = st.z, o[45] = st.w;
     o[46] = ic.x, o[47] = ic.y, o[48] = ic.z, o[49] = ic.w;
-    o[50] = e.has32;
     o[51] = (int32_t)s.u[i];
-    o[52] = e.ep_frames;
 }
 
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
-
-// Values outside the packed field ranges are clamped (they cannot occur in a state produced
-// by the simulator itself).
 __global__ void __launch_bounds__(kThreads) pz_import_kernel(int32_t *state, int64_t n, const int32_t *in) {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     StatePtrs s = state_ptrs(state, n);
     const int32_t *o = in + i * PZ_UNPACKED_WORDS;
     Env e;
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        Player &p = e.p[k];
-        const int32_t *q = o + 13 * k;
-        p.x = clampi(q[0], 0, 511), p.y = clampi(q[1], 0, 255), p.yv = clampi(q[2], -32, 31);
-        p.state = clampi(q[3], 0, 7), p.frame = clampi(q[4], 0, 7), p.delay = clampi(q[5], 0, 7);
-        p.arm = q[6] > 0 ? 1 : -1, p.dive = clampi(q[7], -1, 1), p.lying = clampi(q[8], -4, 3);
-        p.coll = q[9] != 0, p.bold = clampi(q[10], 0, 7), p.standby = q[11] != 0, p.keyprev = q[12] != 0;
-    }
-    Ball &b = e.b;
-    const int32_t *q = o + 26;
-    b.x = clampi(q[0], 0, 511), b.y = clampi(q[1], -512, 511), b.xv = clampi(q[2], -32, 31);
-    b.yv = clampi(q[3], -32768, 32767), b.px = clampi(q[4], 0, 511), b.py = clampi(q[5], -512, 511);
-    b.ppx = clampi(q[6], 0, 511), b.ppy = clampi(q[7], -512, 511), b.pow = q[8] != 0;
-    b.land = clampi(q[9], 0, 511), b.punch = clampi(q[10], 0, 511);
-    e.score[0] = clampi(o[37], 0, 1023), e.score[1] = clampi(o[38], 0, 1023);
-    e.round_ended = o[39] != 0, e.game_ended = o[40] != 0, e.p2serve = o[41] != 0;
-    e.has32 = o[50] != 0;
-    e.land_ok = 0;
-    e.ep_frames = o[52];
+    env_from_unpacked(e, o);
     store_env(e, s, i);
     s.g2[i] = make_int4(o[42], o[43], o[44], o[45]);
     s.g3[i] = make_int4(o[46], o[47], o[48], o[49]);

@@ -160,16 +160,24 @@ __device__ __forceinline__ void unpack_g0(Env &e, int4 w) {
 
 // Streaming 128-bit accesses: state and outputs are touched once per launch, keep them out of L1.
 __device__ __forceinline__ int4 ld_stream(const int4 *p) {
+#ifdef PZ_HOST_EMULATION  // tests/emul: the device code compiled for the host, one lane per warp
+    return *p;
+#else
     int4 r;
     asm volatile("ld.global.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
+#endif
 }
 __device__ __forceinline__ void st_stream(int4 *p, int4 v) {
+#ifdef PZ_HOST_EMULATION
+    *p = v;
+#else
     asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
                  "r"(v.w)
                  : "memory");
+#endif
 }
 
 __device__ __forceinline__ void load_env(Env &e, const StatePtrs &s, int64_t i) {
@@ -201,6 +209,52 @@ __device__ __forceinline__ void rng_store(const Rng &r, const StatePtrs &s, int6
     st.w = (int)(uint32_t)(r.s_hi >> 32);
     st_stream(s.g2 + i, st);
     s.u[i] = r.uinteger;
+}
+
+// ---- unpacked parity form (int32[53], oracle/pika_oracle.h pk_env; words 42..51 are the PCG64
+// stream and are handled by the callers) -------------------------------------------------------
+__device__ __forceinline__ void env_to_unpacked(const Env &e, int32_t *o) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const Player &p = e.p[k];
+        int32_t *q = o + 13 * k;
+        q[0] = p.x, q[1] = p.y, q[2] = p.yv, q[3] = p.state, q[4] = p.frame, q[5] = p.delay, q[6] = p.arm;
+        q[7] = p.dive, q[8] = p.lying, q[9] = p.coll, q[10] = p.bold, q[11] = p.standby, q[12] = p.keyprev;
+    }
+    const Ball &b = e.b;
+    int32_t *q = o + 26;
+    q[0] = b.x, q[1] = b.y, q[2] = b.xv, q[3] = b.yv, q[4] = b.px, q[5] = b.py, q[6] = b.ppx, q[7] = b.ppy;
+    q[8] = b.pow, q[9] = b.land, q[10] = b.punch;
+    o[37] = e.score[0], o[38] = e.score[1], o[39] = e.round_ended, o[40] = e.game_ended, o[41] = e.p2serve;
+    o[50] = e.has32;
+    o[52] = e.ep_frames;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// Values outside the packed field ranges are clamped (they cannot occur in a state produced by
+// the simulator itself). The derived landing-cache bit is cleared.
+__device__ __forceinline__ void env_from_unpacked(Env &e, const int32_t *o) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        Player &p = e.p[k];
+        const int32_t *q = o + 13 * k;
+        p.x = clampi(q[0], 0, 511), p.y = clampi(q[1], 0, 255), p.yv = clampi(q[2], -32, 31);
+        p.state = clampi(q[3], 0, 7), p.frame = clampi(q[4], 0, 7), p.delay = clampi(q[5], 0, 7);
+        p.arm = q[6] > 0 ? 1 : -1, p.dive = clampi(q[7], -1, 1), p.lying = clampi(q[8], -4, 3);
+        p.coll = q[9] != 0, p.bold = clampi(q[10], 0, 7), p.standby = q[11] != 0, p.keyprev = q[12] != 0;
+    }
+    Ball &b = e.b;
+    const int32_t *q = o + 26;
+    b.x = clampi(q[0], 0, 511), b.y = clampi(q[1], -512, 511), b.xv = clampi(q[2], -32, 31);
+    b.yv = clampi(q[3], -32768, 32767), b.px = clampi(q[4], 0, 511), b.py = clampi(q[5], -512, 511);
+    b.ppx = clampi(q[6], 0, 511), b.ppy = clampi(q[7], -512, 511), b.pow = q[8] != 0;
+    b.land = clampi(q[9], 0, 511), b.punch = clampi(q[10], 0, 511);
+    e.score[0] = clampi(o[37], 0, 1023), e.score[1] = clampi(o[38], 0, 1023);
+    e.round_ended = o[39] != 0, e.game_ended = o[40] != 0, e.p2serve = o[41] != 0;
+    e.has32 = o[50] != 0;
+    e.land_ok = 0;
+    e.ep_frames = o[52];
 }
 
 }  // namespace pz

@@ -1,0 +1,184 @@
+// TEST INFRASTRUCTURE — the DEVICE code of pika-zoo_b200/csrc (pz_state.cuh, pz_rng.cuh,
+// pz_physics.cuh) compiled for the host with g++, one lane per "warp", so that the packing,
+// the PCG64 restatement, the fast-forwarded trajectory simulations and the computer player can be
+// fuzzed against the oracle in the `-m "not gpu"` suite (tests/test_device_code_on_host.py).
+// It is never linked into the product: libpikazoo_b200.so is built by nvcc from the .cu files only,
+// and nothing under pika-zoo_b200/ can load this. The kernel glue (launch geometry, bulk-copy
+// observation output, statistics atomics) is NOT covered here; the -m gpu tests cover it.
+#define PZ_HOST_EMULATION 1
+#include <cuda_runtime.h>  // vector types only; no CUDA call is made
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+// ---- one-lane warp shims -------------------------------------------------------------------------
+struct Dim3Shim { unsigned x = 0, y = 0, z = 0; };
+static Dim3Shim threadIdx_shim;
+#define threadIdx threadIdx_shim
+using std::max;
+using std::min;
+static inline bool __any_sync(unsigned, bool p) { return p; }
+static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __fns(unsigned mask, unsigned base, int offset) {
+    int seen = 0;
+    for (unsigned b = base; b < 32; b++)
+        if (mask & (1u << b))
+            if (++seen == offset) return (int)b;
+    return -1;
+}
+static inline uint64_t __umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
+template <typename T>
+static inline T __ldg(const T *p) { return *p; }
+
+#include "../../pika-zoo_b200/csrc/pz_physics.cuh"
+
+using namespace pz;
+
+namespace {
+
+struct Batch {
+    int64_t n;
+    std::vector<int32_t> state;  // the packed SoA buffer, exactly as on the device
+};
+
+template <int AI_MASK>
+int step_one(Env &e, DrawCtx &d, const StepCfg &c, uint32_t k1, uint32_t k2, int *scratch) {
+    return step_frame<AI_MASK>(1u, e, d, c, k1, k2, scratch);
+}
+
+}  // namespace
+
+extern "C" {
+
+int emul_state_words() { return 17; }
+
+// unpacked int32[n][53] -> packed SoA (same conversion as pz_import_state)
+void emul_import(int32_t *packed, int64_t n, const int32_t *unpacked) {
+    StatePtrs s = state_ptrs(packed, n);
+    for (int64_t i = 0; i < n; i++) {
+        const int32_t *o = unpacked + i * 53;
+        Env e;
+        env_from_unpacked(e, o);
+        store_env(e, s, i);
+        s.g2[i] = make_int4(o[42], o[43], o[44], o[45]);
+        s.g3[i] = make_int4(o[46], o[47], o[48], o[49]);
+        s.u[i] = (uint32_t)o[51];
+    }
+}
+
+void emul_export(const int32_t *packed, int64_t n, int32_t *unpacked) {
+    StatePtrs s = state_ptrs(const_cast<int32_t *>(packed), n);
+    for (int64_t i = 0; i < n; i++) {
+        int32_t *o = unpacked + i * 53;
+        Env e;
+        load_env(e, s, i);
+        env_to_unpacked(e, o);
+        const int4 st = s.g2[i], ic = s.g3[i];
+        o[42] = st.x, o[43] = st.y, o[44] = st.z, o[45] = st.w;
+        o[46] = ic.x, o[47] = ic.y, o[48] = ic.z, o[49] = ic.w;
+        o[51] = (int32_t)s.u[i];
+    }
+}
+
+void emul_seed(int32_t *packed, int64_t n, uint64_t base_seed) {
+    StatePtrs s = state_ptrs(packed, n);
+    for (int64_t i = 0; i < n; i++) {
+        Env e;
+        fresh_env(e);
+        Rng r;
+        pcg64_seed(base_seed + (uint64_t)i, r);
+        store_env(e, s, i);
+        rng_store(r, s, i);
+        s.g3[i] = make_int4((int)(uint32_t)r.inc_lo, (int)(uint32_t)(r.inc_lo >> 32), (int)(uint32_t)r.inc_hi,
+                            (int)(uint32_t)(r.inc_hi >> 32));
+    }
+}
+
+// One batched call with the product's NEXT-STEP auto-reset semantics (mirrors pz_step_kernel's body):
+// base reward of player_1 in {-1,0,1} per env, obs int32[n][2][35], done u8[n]. Every env goes
+// through a load_env/store_env round trip, so the packed layout is exercised on every frame.
+void emul_step(int32_t *packed, int64_t n, int winning_score, int serve, int ai_mask, int simplify, int autoreset,
+               const int32_t *actions, int32_t *obs, int32_t *base_reward, uint8_t *done, int do_reset_all) {
+    StatePtrs s = state_ptrs(packed, n);
+    StepCfg c;
+    c.winning_score = winning_score;
+    c.serve = serve;
+    c.tab_land = nullptr;
+    c.tab_power = nullptr;
+    static int scratch[32 * 70];
+    for (int64_t i = 0; i < n; i++) {
+        DrawCtx d;
+        d.s = s;
+        d.idx = i;
+        d.r.loaded = false;
+        d.r.dirty = false;
+        Env e;
+        load_env(e, s, i);
+        int base = 0;
+        bool stepped = false;
+        if (do_reset_all) {
+            reset_env(e, d, c);
+        } else if (!e.game_ended) {
+            const int a1 = actions ? actions[2 * i] : 0, a2 = actions ? actions[2 * i + 1] : 0;
+            bool b1, b2;
+            uint32_t k1, k2;
+            if (simplify) {
+                k1 = decode_keys<0, true>(a1, b1);
+                k2 = decode_keys<1, true>(a2, b2);
+            } else {
+                k1 = decode_keys<0, false>(a1, b1);
+                k2 = decode_keys<1, false>(a2, b2);
+            }
+            if (ai_mask != 0) rng_load(d.r, s, i);
+            switch (ai_mask) {
+                case 0: base = step_one<0>(e, d, c, k1, k2, scratch); break;
+                case 1: base = step_one<1>(e, d, c, k1, k2, scratch); break;
+                case 2: base = step_one<2>(e, d, c, k1, k2, scratch); break;
+                default: base = step_one<3>(e, d, c, k1, k2, scratch); break;
+            }
+            stepped = true;
+        } else if (autoreset) {
+            reset_env(e, d, c);
+        }
+        if (do_reset_all || stepped || autoreset) {
+            store_env(e, s, i);
+            if (d.r.dirty) rng_store(d.r, s, i);
+        }
+        if (obs) {
+            int u[35];
+            obs_values(e, u);
+            for (int k = 0; k < 70; k++) obs[i * 70 + k] = u[obs_src(k)];
+        }
+        if (base_reward) base_reward[i] = base;
+        if (done) done[i] = (uint8_t)((stepped && e.game_ended) || (!stepped && !do_reset_all && !autoreset));
+    }
+}
+
+// The two trajectory simulations alone (fast-forwarded device form), for exhaustive comparison
+// with the reference's plain loops. Returns landing x; *by_ground = ended on the ground.
+int emul_simulate(int x, int y, int xv, int yv, int power, int *by_ground) {
+    bool g;
+    const int lx = power ? simulate_landing_x<true>(1u, x, y, xv, yv, true, g)
+                         : simulate_landing_x<false>(1u, x, y, xv, yv, true, g);
+    if (by_ground) *by_ground = g ? 1 : 0;
+    return lx;
+}
+
+void emul_simulate_many(int64_t n, const int32_t *xyv, int power, int32_t *out) {
+    for (int64_t i = 0; i < n; i++) {
+        bool g;
+        const int32_t *q = xyv + 4 * i;
+        out[i] = power ? simulate_landing_x<true>(1u, q[0], q[1], q[2], q[3], true, g)
+                       : simulate_landing_x<false>(1u, q[0], q[1], q[2], q[3], true, g);
+    }
+}
+
+int emul_synth_action(uint64_t seed, uint64_t env, uint64_t frame, int agent, uint32_t n_actions) {
+    return synth_action(seed, env, frame, agent, n_actions);
+}
+
+}  // extern "C"

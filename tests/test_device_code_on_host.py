@@ -1,0 +1,215 @@
+"""The DEVICE headers (pz_state.cuh / pz_rng.cuh / pz_physics.cuh) compiled for the host with one
+lane per warp (tests/emul/pz_emul.cpp) against the oracle, without a GPU: packing round trips,
+PCG64 seeding and draws, the fast-forwarded trajectory simulations over a domain much wider than
+play reaches, and lock-step games for every AI mask. The kernels proper (launch geometry, bulk-copy
+output, warp-collective scheduling, statistics) are covered by the -m gpu tests."""
+
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from oracle.synth import synth_actions_numpy
+from tests.emul.build import build
+
+LIB = build()
+pytestmark = pytest.mark.skipif(LIB is None, reason="CUDA headers not found")
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def emul():
+    L = ctypes.CDLL(LIB)
+    L.emul_simulate.restype = ctypes.c_int
+    L.emul_synth_action.restype = ctypes.c_int
+    L.emul_synth_action.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32]
+    L.emul_seed.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64]
+    L.emul_import.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    L.emul_export.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    L.emul_simulate_many.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    L.emul_step.argtypes = [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_int] * 5 + [ctypes.c_void_p] * 4 + [ctypes.c_int]
+    return L
+
+
+class EmulVecEnv:
+    def __init__(self, L, n, seed, winning_score=15, serve="winner", is_player1_computer=False,
+                 is_player2_computer=False, simplify_action=False, autoreset=True):
+        self.L, self.n = L, n
+        self.packed = np.zeros(17 * n, dtype=np.int32)
+        self.args = (winning_score, po.SERVE_CODES[serve], int(is_player1_computer) | 2 * int(is_player2_computer),
+                     int(simplify_action), int(autoreset))
+        self.obs = np.zeros((n, 2, 35), dtype=np.int32)
+        self.base = np.zeros(n, dtype=np.int32)
+        self.done = np.zeros(n, dtype=np.uint8)
+        L.emul_seed(_p(self.packed), n, seed)
+
+    def _call(self, actions, reset):
+        a = None if actions is None else np.ascontiguousarray(actions, dtype=np.int32)
+        self.L.emul_step(_p(self.packed), self.n, *self.args, None if a is None else _p(a), _p(self.obs),
+                         _p(self.base), _p(self.done), int(reset))
+
+    def reset(self):
+        self._call(None, True)
+        return self.obs
+
+    def step(self, actions):
+        self._call(actions, False)
+        return self.obs, self.base, self.done
+
+    def export(self):
+        out = np.zeros((self.n, 53), dtype=np.int32)
+        self.L.emul_export(_p(self.packed), self.n, _p(out))
+        return out
+
+    def load(self, unpacked):
+        self.L.emul_import(_p(self.packed), self.n, _p(np.ascontiguousarray(unpacked, dtype=np.int32)))
+
+
+def test_seeding_matches_oracle(emul):
+    n = 257
+    for base in (0, 1, 12345, 2**32 - 3, 2**63 + 11, 2**64 - n):
+        e = EmulVecEnv(emul, n, base)
+        o = po.OracleVecEnv(n, seed=base)
+        assert np.array_equal(e.export(), o.state)
+
+
+@pytest.mark.parametrize("power", [False, True])
+def test_fast_forwarded_simulation_equals_plain_loop(emul, power):
+    """simulate_landing_x (closed-form skips of free flight) == the reference loops, on the whole
+    reachable domain and far beyond it (negative y after net bounces, |yv| up to 700, loop limit)."""
+    rng = np.random.default_rng(7 + power)
+    n = 400_000
+    q = np.empty((n, 4), dtype=np.int32)
+    q[:, 0] = rng.integers(0, 433, n)
+    q[:, 1] = rng.integers(-512, 253, n)
+    q[:, 2] = rng.integers(-20, 21, n)
+    q[:, 3] = rng.integers(-700, 701, n)
+    # a third of the cases inside the domain play actually reaches, dense around the net and walls
+    m = n // 3
+    q[:m, 1] = rng.integers(0, 253, m)
+    q[:m, 3] = rng.integers(-60, 61, m)
+    q[m:2 * m, 0] = rng.integers(180, 253, m)
+    q[m:2 * m, 1] = rng.integers(150, 253, m)
+    if power:
+        q[:, 2] = rng.choice(np.array([-20, -10, 10, 20], dtype=np.int32), n)
+    out = np.zeros(n, dtype=np.int32)
+    emul.emul_simulate_many(n, _p(q), int(power), _p(out))
+    ref = po.simulate_many(q, power)
+    bad = np.nonzero(out != ref)[0]
+    assert len(bad) == 0, (q[bad[:5]].tolist(), out[bad[:5]].tolist(), ref[bad[:5]].tolist())
+
+
+def test_simulation_exhaustive_slice(emul):
+    """every (x, y) for a band of velocities, both loops"""
+    xs, ys = np.meshgrid(np.arange(0, 433, dtype=np.int32), np.arange(0, 253, dtype=np.int32), indexing="ij")
+    for xv, yv in [(0, 0), (20, -31), (-20, 40), (7, 1), (-13, -90), (10, 262), (-20, -262), (3, 101)]:
+        q = np.stack([xs.ravel(), ys.ravel(), np.full(xs.size, xv, np.int32), np.full(xs.size, yv, np.int32)], 1)
+        q = np.ascontiguousarray(q, dtype=np.int32)
+        for power in (0, 1):
+            out = np.zeros(len(q), dtype=np.int32)
+            emul.emul_simulate_many(len(q), _p(q), power, _p(out))
+            assert np.array_equal(out, po.simulate_many(q, bool(power))), (xv, yv, power)
+
+
+CONFIGS = {
+    "random18": dict(),
+    "ai_vs_ai": dict(is_player1_computer=True, is_player2_computer=True),
+    "ai_p1_alternate": dict(is_player1_computer=True, serve="alternate", winning_score=7),
+    "ai_p2_random_serve": dict(is_player2_computer=True, serve="random", winning_score=5),
+    "simplify_ws3": dict(simplify_action=True, winning_score=3, serve="random"),
+}
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_lockstep_with_oracle(emul, name):
+    cfg = CONFIGS[name]
+    n, steps, seed = 192, 2500, 30_000  # seed 30000 / env 3214 was the fast-forward ceiling bug's witness
+    e = EmulVecEnv(emul, n, seed, **cfg)
+    o = po.OracleVecEnv(n, seed=seed, **cfg)
+    assert np.array_equal(e.reset(), o.reset())
+    n_actions = 13 if cfg.get("simplify_action") else 18
+    for t in range(steps):
+        a = synth_actions_numpy(seed + 77, 0, n, t, n_actions)
+        obs, base, done = e.step(a)
+        o_obs, o_rew, o_done = o.step(a)
+        assert np.array_equal(obs, o_obs), f"obs differ at step {t}"
+        assert np.array_equal(base, o_rew[:, 0].astype(np.int32)) and np.array_equal(done, o_done), t
+        if t % 50 == 0 or t == steps - 1:
+            assert np.array_equal(e.export(), o.state), f"state differs at step {t}"
+
+
+def test_known_witness_of_the_ceiling_bug(emul):
+    """State (from a 4,096-env GPU run) whose power-hit candidate flies above the ceiling (y = -10):
+    the computer must find the (x_direction 1, y_direction 1) hit and move right."""
+    prev = [178, 111, 3, 2, 2, 0, 1, 1, -2, 0, 2, 0, 0, 248, 228, 16, 2, 0, 2, 1, 1, -2, 0, 1, 0, 0, 213, 243, 10,
+            131, 203, 113, 223, 179, 1, 213, 203, 0, 0, 0, 0, 0, 2047048881, -470378562, -633581333, 1788586230,
+            -1227392537, 1011126410, 2026769623, -172115264, 0, 264967842, 249]
+    cfg = dict(winning_score=5, serve="random", is_player2_computer=True)
+    e = EmulVecEnv(emul, 1, 0, **cfg)
+    e.load(np.array([prev], dtype=np.int32))
+    o = po.OracleVecEnv(1, seed=0, **cfg)
+    o.state[:] = np.array([prev], dtype=np.int32)
+    a = np.array([[15, 3]], dtype=np.int32)
+    e.step(a), o.step(a)
+    assert o.state[0, 13] == 254  # checked against the unmodified reference (x 248 -> 254)
+    assert np.array_equal(e.export(), o.state)
+
+
+def test_random_states_one_step(emul):
+    """Fuzz: random (clamped-to-range) states, far outside what play reaches, stepped once by both."""
+    rng = np.random.default_rng(99)
+    n = 60_000
+    base = po.OracleVecEnv(n, seed=5)
+    base.reset()
+    st = base.state.copy()
+    for k in (0, 13):
+        lo, hi = (32, 184) if k == 0 else (248, 400)
+        st[:, k + 0] = rng.integers(lo, hi + 1, n)
+        st[:, k + 1] = rng.integers(108, 245, n)
+        st[:, k + 2] = rng.integers(-16, 17, n)
+        st[:, k + 3] = rng.integers(0, 5, n)
+        st[:, k + 4] = rng.integers(0, 5, n)
+        st[:, k + 5] = rng.integers(0, 6, n)
+        st[:, k + 6] = rng.choice([-1, 1], n)
+        st[:, k + 7] = rng.integers(-1, 2, n)
+        st[:, k + 8] = rng.integers(-2, 4, n)
+        st[:, k + 9] = rng.integers(0, 2, n)
+        st[:, k + 10] = rng.integers(0, 5, n)
+        st[:, k + 11] = rng.integers(0, 2, n)
+        st[:, k + 12] = rng.integers(0, 2, n)
+    st[:, 26] = rng.integers(20, 433, n)
+    st[:, 27] = rng.integers(-200, 253, n)
+    st[:, 28] = rng.integers(-20, 21, n)
+    st[:, 29] = rng.integers(-300, 301, n)
+    st[:, 30:34] = rng.integers(0, 253, (n, 4))
+    st[:, 34] = rng.integers(0, 2, n)
+    st[:, 35] = rng.integers(0, 433, n)
+    st[:, 36] = rng.integers(0, 433, n)
+    st[:, 37:39] = rng.integers(0, 4, (n, 2))
+    st[:, 39] = rng.integers(0, 2, n) * (rng.integers(0, 4, n) == 0)
+    st[:, 41] = rng.integers(0, 2, n)
+    for name in ("ai_vs_ai", "ai_p2_random_serve", "random18"):
+        cfg = CONFIGS[name]
+        e = EmulVecEnv(emul, n, 0, **cfg)
+        o = po.OracleVecEnv(n, seed=0, **cfg)
+        e.load(st)
+        o.state[:] = st
+        assert np.array_equal(e.export(), st)  # pack/unpack round trip of every field
+        for t in range(3):
+            a = synth_actions_numpy(4, 0, n, t, 18)
+            obs, base_r, done = e.step(a)
+            o_obs, o_rew, o_done = o.step(a)
+            bad = np.nonzero((obs != o_obs).any(axis=(1, 2)))[0]
+            assert len(bad) == 0, (name, t, st[bad[0]].tolist())
+            assert np.array_equal(e.export(), o.state)
+
+
+def test_synth_actions_match(emul):
+    for env, frame, agent in [(0, 0, 0), (5, 77, 1), (2**40 + 3, 2**33, 0)]:
+        for n_actions in (13, 18):
+            assert emul.emul_synth_action(91, env, frame, agent, n_actions) == po.synth_action(91, env, frame, agent,
+                                                                                               n_actions)
