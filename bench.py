@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-rollout", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
     return ap.parse_args()
 
 
@@ -281,15 +282,14 @@ def run_b200_arm(args):
     stats_dict = {name: int(stats[i]) for i, name in enumerate(_lib.STAT_NAMES)}
 
     # ---- e2e: host buffers through the C ABI (pz_host_step): H2D actions + D2H obs/reward/done ----
-    e2e = None
-    if not args.no_e2e:
+    def host_e2e(obs_dtype, act_dtype, label):
         L = _lib.load()
-        cfg = pikazoo_b200.make_config(**ENV_KW)
+        cfg = pikazoo_b200.make_config(obs_dtype=obs_dtype, action_dtype=act_dtype, **ENV_KW)
         ctx = ctypes.c_void_p()
         first, _ = pikazoo_b200.shard_range(total, world, rank)
         _lib.check(L.pz_host_create(ctypes.byref(ctx), n, ctypes.byref(cfg), 2026, first, 8), "pz_host_create")
-        h_act = [torch.randint(0, 18, (n, 2), dtype=torch.int32).pin_memory() for _ in range(2)]
-        h_obs = torch.empty((n, 2, 35), dtype=torch.int32).pin_memory()
+        h_act = [torch.randint(0, 18, (n, 2), dtype=act_dtype).pin_memory() for _ in range(2)]
+        h_obs = torch.empty((n, 2, 35), dtype=obs_dtype).pin_memory()
         h_rew = torch.empty((n, 2), dtype=torch.float32).pin_memory()
         h_done = torch.empty((n,), dtype=torch.uint8).pin_memory()
         _lib.check(L.pz_host_reset(ctx, h_obs.data_ptr()), "pz_host_reset")
@@ -307,13 +307,64 @@ def run_b200_arm(args):
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         L.pz_host_destroy(ctx)
-        e2e = {
+        return {
             "value": total * E / float(te.item()), "unit": "env-steps/s",
-            "h2d_bytes_per_step": n * 2 * 4, "d2h_bytes_per_step": n * (280 + 8 + 1),
-            "steps": E, "api": "pz_host_step (C ABI, pinned host buffers, 8 chunks on 8 streams; "
-                               "host-blocking call timed with perf_counter, max over ranks)",
+            "h2d_bytes_per_step": n * 2 * h_act[0].element_size(),
+            "d2h_bytes_per_step": n * (70 * h_obs.element_size() + 8 + 1),
+            "steps": E, "dtypes": label,
+            "api": "pz_host_step (C ABI, pinned host buffers, 8 chunks on 8 streams; host-blocking call timed "
+                   "with perf_counter, max over ranks)",
         }
-        del h_obs, h_rew, h_done, h_act
+
+    e2e = e2e_compact = None
+    if not args.no_e2e:
+        e2e = host_e2e(torch.int32, torch.int32, "obs int32 (the reference's declared dtype), actions int32")
+        # same call with the lossless compact API dtypes: half the PCIe bytes per env-step
+        e2e_compact = host_e2e(torch.int16, torch.uint8, "obs int16, actions uint8 (lossless)")
+
+    # ---- secondary per-step variants (same launch geometry; each its own env batch) ----
+    def time_steps(env, actions_ring, steps=300, warm=20):
+        for k in range(warm):
+            env.step(actions_ring[k % len(actions_ring)] if actions_ring else None)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for k in range(steps):
+            env.step(actions_ring[k % len(actions_ring)] if actions_ring else None)
+        b.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item()) / steps
+        return {"us_per_launch": ms * 1e3, "env_steps_per_sec": env.num_envs * world / (ms * 1e-3)}
+
+    variants = None
+    if not args.no_variants:
+        variants = {}
+        first, _ = pikazoo_b200.shard_range(total, world, rank)
+        v = pikazoo_b200.PikaVecEnv(n, device=dev, seed=11, first_env=first, obs_dtype=torch.float16,
+                                    normalize_observation=True, action_dtype=torch.uint8, **ENV_KW)
+        v.reset()
+        ring_u8 = [r.to(torch.uint8) for r in ring[:4]]
+        variants["f16_normalised_obs_u8_actions"] = dict(time_steps(v, ring_u8), bytes_per_env_step=2 + 140 + 8 + 1 + 64)
+        del v
+        v = pikazoo_b200.PikaVecEnv(n, device=dev, seed=12, first_env=first, is_player1_computer=True,
+                                    is_player2_computer=True, **ENV_KW)
+        v.reset()
+        variants["computer_vs_computer_per_step"] = time_steps(v, None)
+        del v
+        v = pikazoo_b200.PikaVecEnv(n, device=dev, seed=2026, first_env=first, l2_hints=False, **ENV_KW)
+        v.reset()
+        variants["main_workload_without_l2_policy_hints"] = time_steps(v, ring)
+        del v
+        shaped = ((0.1, 0.2, 0.3, 0.4, -0.1, -0.2, -0.3, -0.4), 216, 176)
+        v = pikazoo_b200.PikaVecEnv(65536, device=dev, seed=13, first_env=rank * 65536, simplify_action=True,
+                                    reward_by_ball_position=shaped, **ENV_KW)
+        v.reset()
+        ring13 = [torch.randint(0, 13, (65536, 2), generator=gen, device=dev, dtype=torch.int32) for _ in range(4)]
+        variants["configs[2]_65536_envs_fused_wrappers"] = time_steps(v, ring13, steps=1000, warm=50)
+        del v, ring13
 
     # ---- config 4: K = 64 register-resident rollout, computer vs computer (not HBM-bound) ----
     rollout = None
@@ -355,8 +406,12 @@ def run_b200_arm(args):
                          "launch_ms_p50": per_launch_ms[len(per_launch_ms) // 2], "peak_source": peak_src},
             "e2e": e2e, "gpu_launches": K, "clocks": clocks.summary(), "episode_stats": stats_dict,
         }
+        if e2e_compact:
+            line["e2e_compact"] = e2e_compact
         if rollout:
             line["rollout"] = rollout
+        if variants:
+            line["variants"] = variants
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_port_throughput(args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",

@@ -13,6 +13,10 @@
  *                             + SimplifyAction.step               pikazoo/wrappers/simplify_action.py:16-25
  *                             + RewardByBallPosition.step         pikazoo/wrappers/reward_by_ball_position.py:20-31
  *                             + raw_env._get_obs                  pikazoo/env/pikazoo_env.py:576-624
+ *                             + NormalizeObservation.step/reset   pikazoo/wrappers/normalize_observation.py:18-32
+ *                             + RewardInNormalState.step          pikazoo/wrappers/reward_in_normal_state.py:10-15
+ *   pz_step_ex                pz_step + RecordEpisodeStatistics   pikazoo/wrappers/record_episode_statistics.py:17-40
+ *                             (per-env running return / length) and optional truncation
  *   pz_rollout                K x raw_env.step with the state held in registers
  *   pz_step_host              raw_env.step for callers holding HOST buffers (numpy users)
  *   pz_export_state / pz_import_state   the Python object graph <-> packed device state
@@ -33,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PZ_VERSION 1
+#define PZ_VERSION 2
 
 /* packed device state: int32 words per env (structure-of-arrays) */
 #define PZ_STATE_WORDS 17
@@ -45,6 +49,16 @@ extern "C" {
 enum { PZ_SERVE_WINNER = 0, PZ_SERVE_ALTERNATE = 1, PZ_SERVE_RANDOM = 2 }; /* pikazoo_env.py:104 */
 enum { PZ_ACT_I32 = 0, PZ_ACT_I64 = 1, PZ_ACT_U8 = 2 };
 enum { PZ_REW_F32 = 0, PZ_REW_F64 = 1 };
+/* element type of the observation rows [n][2][35]. I32 is the reference's declared dtype
+ * (pikazoo_env.py:564); I16 is the same integers in half the bytes (every value fits: |v| <= 32767
+ * is enforced by saturation, play stays within +-700); the float types hold (float)value, or the
+ * NormalizeObservation output when pz_config.normalize_observation is set. F64 is what the reference
+ * wrapper itself produces (numpy true division of int64 arrays); F32 = float32(F64 value) exactly;
+ * F16 / BF16 = round-to-nearest-even of the F32 value. */
+enum { PZ_OBS_I32 = 0, PZ_OBS_I16 = 1, PZ_OBS_F32 = 2, PZ_OBS_F16 = 3, PZ_OBS_BF16 = 4, PZ_OBS_F64 = 5 };
+/* RewardInNormalState composition order relative to RewardByBallPosition */
+enum { PZ_RINS_OFF = 0, PZ_RINS_OUTER = 1 /* RewardInNormalState(RewardByBallPosition(env)) */,
+       PZ_RINS_INNER = 2 /* RewardByBallPosition(RewardInNormalState(env)) */ };
 enum { PZ_ACTIONS_NOOP = 0, PZ_ACTIONS_SYNTH = 1 }; /* pz_rollout action source */
 
 enum {
@@ -66,7 +80,8 @@ enum {
     PZ_STAT_P2_POINTS = 6,
     PZ_STAT_RESETS = 7,      /* raw_env.reset calls executed by auto-reset */
     PZ_STAT_BAD_ACTIONS = 8, /* actions outside the action space (treated as action 0) */
-    PZ_STAT_FROZEN = 9       /* calls on terminated envs with autoreset off (no-ops) */
+    PZ_STAT_FROZEN = 9,      /* calls on terminated envs with autoreset off (no-ops) */
+    PZ_STAT_TRUNCATED = 10   /* episodes cut by max_episode_frames */
 };
 
 typedef struct pz_config {
@@ -82,11 +97,22 @@ typedef struct pz_config {
     int32_t action_dtype;            /* PZ_ACT_*: element type of actions_dev [n][2] */
     int32_t reward_dtype;            /* PZ_REW_*: element type of reward_dev [n][2] */
     int32_t flags;                   /* PZ_FLAG_* */
+    int32_t obs_dtype;               /* PZ_OBS_*: element type of obs_dev */
+    int32_t normalize_observation;   /* fuse NormalizeObservation: (obs - low) / (high - low) with the bounds of
+                                        pikazoo_env.py:485-562; float obs dtypes only */
+    int32_t reward_in_normal_state;  /* PZ_RINS_*: fuse RewardInNormalState (reward_in_normal_state.py:10-15) */
+    int32_t max_episode_frames;      /* 0: never truncate (the reference never does). > 0: an env whose episode
+                                        reaches this many step() calls without terminating is truncated: it
+                                        reports truncated = 1 on that call and is reset (or frozen) by the next */
+    double normal_state_reward;      /* RewardInNormalState(env, reward) */
 } pz_config;
 
 /* pz_config.flags */
 #define PZ_FLAG_NO_TABLES 1 /* computer players: always run the trajectory simulations iteratively
                                instead of reading the memoised landing tables (results are identical) */
+
+#define PZ_FLAG_NO_L2_HINTS 2 /* do not ask L2 to keep the env state resident across launches / to evict the
+                                 outputs first; for A/B measurements */
 
 int pz_version(void);
 int pz_state_words(void);
@@ -101,16 +127,36 @@ int pz_seed(int32_t *state_dev, int64_t n, uint64_t base_seed, uint64_t first_en
 /* Same with explicit per-env seeds (device array of n uint64). */
 int pz_seed_array(int32_t *state_dev, int64_t n, const uint64_t *seeds_dev, void *stream);
 
-/* reset() on every env. obs_dev: int32 [n][2][35] or NULL. */
-int pz_reset(int32_t *state_dev, int64_t n, const pz_config *cfg, int32_t *obs_dev, void *stream);
+/* reset() on every env. obs_dev: [n][2][35] of cfg->obs_dtype, or NULL. */
+int pz_reset(int32_t *state_dev, int64_t n, const pz_config *cfg, void *obs_dev, void *stream);
 
 /* One frame of every env.
- *   actions_dev [n][2] (cfg->action_dtype), obs_dev int32 [n][2][35] (may be NULL),
+ *   actions_dev [n][2] (cfg->action_dtype), obs_dev [n][2][35] of cfg->obs_dtype (may be NULL),
  *   reward_dev [n][2] (cfg->reward_dtype, may be NULL), done_dev uint8 [n] (may be NULL),
  *   stats_dev int64 [PZ_NUM_STATS] (may be NULL).
  * Env terminated before the call: autoreset ? reset() (reward 0, done 0) : frozen (done 1). */
 int pz_step(int32_t *state_dev, int64_t n, const pz_config *cfg, const void *actions_dev,
-            int32_t *obs_dev, void *reward_dev, uint8_t *done_dev, int64_t *stats_dev, void *stream);
+            void *obs_dev, void *reward_dev, uint8_t *done_dev, int64_t *stats_dev, void *stream);
+
+/* pz_step plus per-env episode bookkeeping (RecordEpisodeStatistics, record_episode_statistics.py:17-40)
+ * and truncation. Every member may be NULL.
+ *   episode_return_dev  double [n][2], in/out, caller-owned like the state: the running sum of each
+ *                       agent's (wrapped) rewards since the last reset, in step order as Python adds them
+ *                       (record_episode_statistics.py:32); zeroed by a reset, so on the call that ends an
+ *                       episode it holds infos[agent]["episode"]["r"].
+ *   episode_length_dev  int32 [n], out: step() calls since the last reset (["episode"]["l"] when done).
+ *   truncated_dev       uint8 [n], out: 1 on the call where the episode reached cfg->max_episode_frames
+ *                       without terminating (and on every later call while frozen). */
+typedef struct pz_episode_io {
+    double *episode_return_dev;
+    int32_t *episode_length_dev;
+    uint8_t *truncated_dev;
+} pz_episode_io;
+int pz_reset_ex(int32_t *state_dev, int64_t n, const pz_config *cfg, void *obs_dev, const pz_episode_io *episode,
+                void *stream); /* pz_reset that also zeroes episode_return_dev / episode_length_dev */
+int pz_step_ex(int32_t *state_dev, int64_t n, const pz_config *cfg, const void *actions_dev, void *obs_dev,
+               void *reward_dev, uint8_t *done_dev, int64_t *stats_dev, const pz_episode_io *episode,
+               void *stream);
 
 /* K frames of every env in one launch, state register-resident, auto-reset always on.
  * action_source PZ_ACTIONS_NOOP: both actions 0 (computer players decide for themselves);
@@ -118,7 +164,7 @@ int pz_step(int32_t *state_dev, int64_t n, const pz_config *cfg, const void *act
  *   synth(action_seed, first_env + i, frame0 + k, agent)   (DESIGN.md "synthetic actions").
  * obs_dev (optional): observation after the last frame. stats_dev (optional) as above. */
 int pz_rollout(int32_t *state_dev, int64_t n, const pz_config *cfg, int32_t K, int32_t action_source,
-               uint64_t action_seed, uint64_t first_env, uint64_t frame0, int32_t *obs_dev,
+               uint64_t action_seed, uint64_t first_env, uint64_t frame0, void *obs_dev,
                int64_t *stats_dev, void *stream);
 
 /* Memoised trajectory simulations for the computer players: two per-device lookup
@@ -147,9 +193,10 @@ int pz_import_state(int32_t *state_dev, int64_t n, const int32_t *unpacked_dev, 
 typedef struct pz_host_ctx pz_host_ctx;
 int pz_host_create(pz_host_ctx **out, int64_t n, const pz_config *cfg, uint64_t base_seed,
                    uint64_t first_env, int32_t chunks);
-int pz_host_reset(pz_host_ctx *ctx, int32_t *obs_host);
-int pz_host_step(pz_host_ctx *ctx, const void *actions_host, int32_t *obs_host, void *reward_host,
+int pz_host_reset(pz_host_ctx *ctx, void *obs_host);
+int pz_host_step(pz_host_ctx *ctx, const void *actions_host, void *obs_host, void *reward_host,
                  uint8_t *done_host);
+size_t pz_obs_elem_bytes(int32_t obs_dtype); /* 0 for an unknown code */
 int pz_host_stats(pz_host_ctx *ctx, int64_t stats_host[PZ_NUM_STATS]);
 int32_t *pz_host_state_dev(pz_host_ctx *ctx);
 void pz_host_destroy(pz_host_ctx *ctx);

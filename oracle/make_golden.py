@@ -61,6 +61,22 @@ GROUPS_FULL = [
                                        serve="random"), "noop", 6000, 10, 4, 30000),
 ]
 
+# The other wrappers of the reference, stacked: tests/golden/wrappers.json
+W1 = dict(winning_score=5, serve="random", simplify_action=True, reward_by_ball_position=SHAPED,
+          reward_in_normal_state=-0.01, normalize_observation=True, record_episode_statistics=True)
+W2 = dict(winning_score=5, serve="winner", reward_by_ball_position=((0.5, 0, -0.5, 0.25, 0, 0.125, 0, -1), 200, 150),
+          reward_in_normal_state=0.002, normal_state_first=True, record_episode_statistics=True)
+W3 = dict(winning_score=3, serve="alternate", is_player2_computer=True, normalize_observation=True,
+          record_episode_statistics=True)
+W4 = dict(winning_score=2, serve="winner", is_player1_computer=True, is_player2_computer=True,
+          reward_in_normal_state=1, normalize_observation=True, record_episode_statistics=True)
+GROUPS_WRAPPERS = [
+    ("normalize_rins_outer_shaped_simplify_ws5", W1, "synth", 7000, 60, 3, 30000),
+    ("rins_inner_shaped_record_ws5", W2, "synth", 8000, 60, 2, 30000),
+    ("normalize_record_ai_p2_ws3", W3, "synth", 9000, 40, 2, 30000),
+    ("normalize_rins_int_ai_vs_ai_ws2", W4, "noop", 9500, 16, 2, 30000),
+]
+
 GROUPS_QUICK = [
     ("ai_vs_ai_ws15_winner", GROUPS_FULL[0][1], "noop", 0, 2, 1, 30000),
     ("random_ws15_winner", GROUPS_FULL[1][1], "synth", 1000, 4, 1, 30000),
@@ -71,46 +87,42 @@ GROUPS_QUICK = [
 ACTION_SEED = 0x5EED
 
 
-def _hash_obs(h, obs):
-    h.update(np.asarray(obs["player_1"]).astype("<i4").tobytes())
-    h.update(np.asarray(obs["player_2"]).astype("<i4").tobytes())
+def _hash_obs(h, obs, normalized=False):
+    dt = "<f8" if normalized else "<i4"
+    h.update(np.asarray(obs["player_1"]).astype(dt).tobytes())
+    h.update(np.asarray(obs["player_2"]).astype(dt).tobytes())
 
 
 def run_session(args):
-    """One reference env, checked frame by frame against the C oracle."""
+    """One reference env (with the reference's own wrappers), checked call by call against the C
+    oracle driven through its batched entry point with n = 1 (pk_vec_step_ex, auto-reset on)."""
     cfg, action_mode, seed, env_index, episodes, max_calls = args
     env = rh.make_env(seed, **cfg)
     raw = env.raw
     n_actions = 13 if cfg.get("simplify_action") else 18
+    normalized = bool(cfg.get("normalize_observation"))
+    record = bool(cfg.get("record_episode_statistics"))
 
-    ocfg = po.make_config(**cfg)
-    ostate = np.zeros(po.ENV_WORDS, dtype=np.int32)
-    oobs = np.zeros(70, dtype=np.int32)
-    orew = np.zeros(2, dtype=np.float64)
-    oterm = np.zeros(1, dtype=np.uint8)
-    L = po.lib()
-    L.pk_init(po._p(ostate), seed)
+    orc = po.OracleVecEnv(1, seed=seed, autoreset=True, **cfg)
 
     def check(obs, rew, term, where):
-        ref_obs = np.concatenate([obs["player_1"], obs["player_2"]]).astype(np.int32)
-        if not np.array_equal(ref_obs, oobs):
-            raise AssertionError(f"obs mismatch {where}: {np.nonzero(ref_obs != oobs)[0]}")
+        ref_obs = np.concatenate([obs["player_1"], obs["player_2"]])
+        mine = orc.normalized_obs().reshape(70) if normalized else orc.obs.reshape(70)
+        if ref_obs.dtype != (np.float64 if normalized else np.int64) or not np.array_equal(ref_obs, mine):
+            raise AssertionError(f"obs mismatch {where}: {np.nonzero(ref_obs != mine)[0]}")
         ref_state = rh.unpacked_state(raw)
-        if not np.array_equal(ref_state, ostate[:52]):
-            raise AssertionError(f"state mismatch {where}: words {np.nonzero(ref_state != ostate[:52])[0]}")
+        if not np.array_equal(ref_state, orc.state[0, :52]):
+            raise AssertionError(f"state mismatch {where}: words {np.nonzero(ref_state != orc.state[0, :52])[0]}")
         if rew is not None:
             r = np.array([rew["player_1"], rew["player_2"]], dtype=np.float64)
-            if not np.array_equal(r, orew) or bool(term) != bool(oterm[0]):
-                raise AssertionError(f"reward/term mismatch {where}: {r} {orew} {term} {oterm}")
+            if not np.array_equal(r, orc.reward[0]) or bool(term) != bool(orc.done[0]):
+                raise AssertionError(f"reward/term mismatch {where}: {r} {orc.reward[0]} {term} {orc.done[0]}")
 
     h = hashlib.sha256()
-    import ctypes
-
-    cref = ctypes.byref(ocfg)
     obs, _ = env.reset()
-    L.pk_reset(po._p(ostate), cref, po._p(oobs))
+    orc.reset()
     check(obs, None, None, (seed, "reset0"))
-    _hash_obs(h, obs)
+    _hash_obs(h, obs, normalized)
 
     results = []
     calls = 0
@@ -122,53 +134,69 @@ def run_session(args):
         else:
             a1 = synth_action(ACTION_SEED, env_index, frame, 0, n_actions)
             a2 = synth_action(ACTION_SEED, env_index, frame, 1, n_actions)
-        obs, rew, terms, _, _ = env.step({"player_1": a1, "player_2": a2})
-        rc = L.pk_step(po._p(ostate), cref, a1, a2, po._p(oobs), po._p(orew), po._p(oterm))
-        assert rc == 0
+        obs, rew, terms, _, infos = env.step({"player_1": a1, "player_2": a2})
+        orc.step(np.array([[a1, a2]], dtype=np.int32))
         calls += 1
         frame += 1
         ep_frames += 1
         term = bool(terms["player_1"])
         check(obs, rew, term, (seed, len(results), ep_frames))
-        _hash_obs(h, obs)
+        _hash_obs(h, obs, normalized)
         h.update(np.array([rew["player_1"], rew["player_2"]], dtype="<f8").tobytes())
         h.update(bytes([int(term)]))
         if term:
-            results.append({"frames": ep_frames, "scores": [int(raw.scores[0]), int(raw.scores[1])]})
+            ep = {"frames": ep_frames, "scores": [int(raw.scores[0]), int(raw.scores[1])]}
+            if record:  # RecordEpisodeStatistics, record_episode_statistics.py:34-39
+                r = [infos[a]["episode"]["r"] for a in ("player_1", "player_2")]
+                ln = [infos[a]["episode"]["l"] for a in ("player_1", "player_2")]
+                assert ln[0] == ln[1] == ep_frames == int(orc.episode_length[0])
+                if not np.array_equal(np.array(r, dtype=np.float64), orc.episode_return[0]):
+                    raise AssertionError(f"episode return mismatch {seed}: {r} {orc.episode_return[0]}")
+                h.update(np.array(r, dtype="<f8").tobytes())
+                h.update(np.array([ln[0]], dtype="<i4").tobytes())
+                ep["returns"] = [float(r[0]), float(r[1])]
+            results.append(ep)
             ep_frames = 0
             if len(results) < episodes and calls < max_calls:
                 obs, _ = env.reset()  # the product's auto-reset call
-                L.pk_reset(po._p(ostate), cref, po._p(oobs))
+                orc.step(np.array([[a1, a2]], dtype=np.int32))  # a call on a terminated env = reset()
                 calls += 1
                 frame += 1
                 check(obs, None, None, (seed, len(results), "reset"))
-                _hash_obs(h, obs)
+                if record:
+                    assert orc.episode_return[0].tolist() == [0.0, 0.0] and orc.episode_length[0] == 0
+                _hash_obs(h, obs, normalized)
     return {
         "seed": seed,
         "episodes": results,
         "calls": calls,
         "unfinished_frames": ep_frames,
         "sha256": h.hexdigest(),
-        "final_state": [int(v) for v in ostate[:52]],
+        "final_state": [int(v) for v in orc.state[0, :52]],
     }
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--out", default=os.path.join(_ROOT, "tests", "golden", "sessions.json"))
+    ap.add_argument("--wrappers", action="store_true", help="the wrapper-stack groups -> tests/golden/wrappers.json")
+    ap.add_argument("--out", default=None)
     ap.add_argument("--procs", type=int, default=len(os.sched_getaffinity(0)))
     a = ap.parse_args()
     if not rh.reference_available():
         raise SystemExit("reference not present; golden fixtures can only be generated in the build container")
     po.build()
-    groups = GROUPS_QUICK if a.quick else GROUPS_FULL
+    groups = GROUPS_WRAPPERS if a.wrappers else (GROUPS_QUICK if a.quick else GROUPS_FULL)
+    if a.out is None:
+        a.out = os.path.join(_ROOT, "tests", "golden", "wrappers.json" if a.wrappers else "sessions.json")
     out = {
         "generator": "oracle/make_golden.py",
         "reference": "helpingstar/pika-zoo @ /root/reference (unmodified), numpy " + np.__version__,
         "seeding": "S0: env.np_random.bit_generator.state = np.random.PCG64(seed).state; reset()",
         "action_seed": ACTION_SEED,
-        "hash": "sha256(reset obs | per step: obs1, obs2 int32 LE, rewards 2xfloat64 LE, terminated byte | reset obs after a terminated step)",
+        "hash": "sha256(reset obs | per step: obs1, obs2 int32 LE (float64 LE when normalize_observation), rewards "
+                "2xfloat64 LE, terminated byte, [on termination with record_episode_statistics: episode returns "
+                "2xfloat64 LE, episode length int32 LE] | reset obs after a terminated step)",
         "groups": [],
     }
     total_games = 0

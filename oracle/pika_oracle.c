@@ -674,12 +674,19 @@ int pk_step(pk_env *e, const pk_config *c, int32_t a1, int32_t a2, int32_t obs[7
     if (reward) {
         reward[0] = (double)player1_reward;
         reward[1] = (double)(-player1_reward);
-        if (c->reward_by_ball_position) {
+        /* wrappers, innermost first. RewardInNormalState.step, reward_in_normal_state.py:10-15 */
+        if (c->reward_in_normal_state == 2)
+            for (int i = 0; i < 2; i++)
+                if (reward[i] == 0) reward[i] = c->normal_state_reward;
+        if (c->reward_by_ball_position) { /* RewardByBallPosition.step, reward_by_ball_position.py:20-31 */
             int x_sign = e->b.x >= c->x_line; /* obs["player_1"][26], [27] */
             int y_sign = e->b.y > c->y_line;
             int ball_pos = 1 * y_sign + 2 * x_sign;
             for (int i = 0; i < 2; i++) reward[i] += c->additional_reward[i * 4 + ball_pos];
         }
+        if (c->reward_in_normal_state == 1)
+            for (int i = 0; i < 2; i++)
+                if (reward[i] == 0) reward[i] = c->normal_state_reward;
     }
     if (terminated) *terminated = (uint8_t)e->game_ended; /* :233 */
     return 0;
@@ -696,33 +703,81 @@ void pk_vec_reset(pk_env *envs, int64_t n, const pk_config *c, int32_t *obs) {
     for (int64_t i = 0; i < n; i++) pk_reset(&envs[i], c, obs ? obs + 70 * i : NULL);
 }
 
-int pk_vec_step(pk_env *envs, int64_t n, const pk_config *c, const int32_t *actions, int32_t *obs,
-                double *reward, uint8_t *done, int autoreset) {
+/* raw_env._get_obs of every env (pikazoo_env.py:576-624) without stepping */
+void pk_vec_obs(const pk_env *envs, int64_t n, int32_t *obs) {
+    for (int64_t i = 0; i < n; i++) get_obs(&envs[i], obs + 70 * i);
+}
+
+static int is_truncated(const pk_env *e, const pk_config *c) {
+    return c->max_episode_frames > 0 && !e->game_ended && e->episode_frames >= c->max_episode_frames;
+}
+
+void pk_vec_reset_ex(pk_env *envs, int64_t n, const pk_config *c, int32_t *obs, double *ep_return,
+                     int32_t *ep_length) {
+    pk_vec_reset(envs, n, c, obs);
+    for (int64_t i = 0; i < n; i++) { /* record_episode_statistics.py:20-26 */
+        if (ep_return) ep_return[2 * i] = ep_return[2 * i + 1] = 0.0;
+        if (ep_length) ep_length[i] = 0;
+    }
+}
+
+int pk_vec_step_ex(pk_env *envs, int64_t n, const pk_config *c, const int32_t *actions, int32_t *obs,
+                   double *reward, uint8_t *done, int autoreset, double *ep_return,
+                   int32_t *ep_length, uint8_t *truncated) {
     int rc = 0;
     for (int64_t i = 0; i < n; i++) {
         pk_env *e = &envs[i];
         int32_t *o = obs ? obs + 70 * i : NULL;
-        if (e->game_ended) {
+        if (e->game_ended || is_truncated(e, c)) {
             if (autoreset) {
                 pk_reset(e, c, o);
-                if (done) done[i] = 0;
+                if (ep_return) ep_return[2 * i] = ep_return[2 * i + 1] = 0.0; /* :24-25 */
             } else {
                 if (o) get_obs(e, o);
-                if (done) done[i] = 1;
             }
             if (reward) reward[2 * i] = reward[2 * i + 1] = 0.0;
-            continue;
+        } else {
+            uint8_t t = 0;
+            double r[2];
+            if (pk_step(e, c, actions ? actions[2 * i] : 0, actions ? actions[2 * i + 1] : 0, o, r, &t) != 0) rc = -1;
+            if (reward) {
+                reward[2 * i] = r[0];
+                reward[2 * i + 1] = r[1];
+            }
+            if (ep_return) { /* :32 */
+                ep_return[2 * i] += r[0];
+                ep_return[2 * i + 1] += r[1];
+            }
         }
-        uint8_t t = 0;
-        double r[2];
-        if (pk_step(e, c, actions[2 * i], actions[2 * i + 1], o, r, &t) != 0) rc = -1;
-        if (reward) {
-            reward[2 * i] = r[0];
-            reward[2 * i + 1] = r[1];
-        }
-        if (done) done[i] = t;
+        if (done) done[i] = (uint8_t)e->game_ended;
+        if (ep_length) ep_length[i] = e->episode_frames; /* :33 */
+        if (truncated) truncated[i] = (uint8_t)is_truncated(e, c);
     }
     return rc;
+}
+
+int pk_vec_step(pk_env *envs, int64_t n, const pk_config *c, const int32_t *actions, int32_t *obs,
+                double *reward, uint8_t *done, int autoreset) {
+    return pk_vec_step_ex(envs, n, c, actions, obs, reward, done, autoreset, NULL, NULL, NULL);
+}
+
+/* raw_env.observation_space bounds, pikazoo_env.py:485-562 */
+static const int32_t OBS_LOW[35] = {32, 108, -15, -1, -2, 0, 0, 0, 0, 0, 0, 0, 0,
+                                    32, 108, -15, -1, -2, 0, 0, 0, 0, 0, 0, 0, 0,
+                                    20, 0, 0, 0, 0, 0, -20, -124, 0};
+static const int32_t OBS_HIGH[35] = {400, 244, 16, 1, 3, 4, 4, 1, 1, 1, 1, 1, 1,
+                                     400, 244, 16, 1, 3, 4, 4, 1, 1, 1, 1, 1, 1,
+                                     432, 252, 432, 252, 432, 252, 20, 124, 1};
+
+/* NormalizeObservation.step / reset, normalize_observation.py:18-32: numpy true division of two
+ * int64 arrays = one IEEE double division per element */
+void pk_normalize_obs(int64_t n, const int32_t *obs, double *out) {
+    for (int64_t i = 0; i < n; i++)
+        for (int a = 0; a < 2; a++)
+            for (int k = 0; k < 35; k++) {
+                int64_t j = i * 70 + a * 35 + k;
+                out[j] = (double)(obs[j] - OBS_LOW[k]) / (double)(OBS_HIGH[k] - OBS_LOW[k]);
+            }
 }
 
 /* splitmix64-style finaliser over (seed, env, frame, agent); product-defined, DESIGN.md */
@@ -738,12 +793,12 @@ int32_t pk_synth_action(uint64_t action_seed, uint64_t global_env, uint64_t fram
 
 int64_t pk_vec_rollout(pk_env *envs, int64_t n, const pk_config *c, int K, int action_mode,
                        uint64_t action_seed, uint64_t first_env, uint64_t frame0, int64_t *stats) {
-    int64_t local[8] = {0};
+    int64_t local[9] = {0};
     uint32_t n_actions = c->simplify_action ? 13u : 18u;
     for (int64_t i = 0; i < n; i++) {
         pk_env *e = &envs[i];
         for (int k = 0; k < K; k++) {
-            if (e->game_ended) {
+            if (e->game_ended || is_truncated(e, c)) {
                 pk_reset(e, c, NULL);
                 local[7] += 1;
                 continue;
@@ -769,10 +824,12 @@ int64_t pk_vec_rollout(pk_env *envs, int64_t n, const pk_config *c, int K, int a
                     local[3] += 1;
                 else
                     local[4] += 1;
+            } else if (is_truncated(e, c)) {
+                local[8] += 1;
             }
         }
     }
     if (stats)
-        for (int k = 0; k < 8; k++) stats[k] += local[k];
+        for (int k = 0; k < 9; k++) stats[k] += local[k];
     return (int64_t)n * K;
 }

@@ -15,6 +15,9 @@
  *          pikazoo/env/pikazoo_env.py:119-141,149-248,576-624,
  *          pikazoo/wrappers/simplify_action.py:16-25,
  *          pikazoo/wrappers/reward_by_ball_position.py:20-31,
+ *          pikazoo/wrappers/normalize_observation.py:18-32,
+ *          pikazoo/wrappers/reward_in_normal_state.py:10-15,
+ *          pikazoo/wrappers/record_episode_statistics.py:17-40,
  *          numpy 2.3.5 (unpinned in the reference: pyproject.toml:25 "numpy>=1.21.0"):
  *          SeedSequence, PCG64 (XSL-RR 128/64), Generator.integers scalar path
  *          (buffered 32-bit Lemire), as restated in SURVEY.md §8(c).
@@ -66,6 +69,12 @@ typedef struct {
     int32_t reward_by_ball_position; /* RewardByBallPosition wrapper on */
     int32_t x_line, y_line;       /* reward_by_ball_position.py:11-12 */
     double additional_reward[8];  /* reward_by_ball_position.py:10 */
+    /* RewardInNormalState(env, reward): 0 off, 1 = outermost (applied after RewardByBallPosition),
+     * 2 = innermost (applied before it); reward_in_normal_state.py:10-15 */
+    int32_t reward_in_normal_state;
+    /* product-defined truncation (the reference never truncates): 0 off */
+    int32_t max_episode_frames;
+    double normal_state_reward;
 } pk_config;
 
 int pk_env_words(void); /* sizeof(pk_env)/4 == 53 */
@@ -94,6 +103,23 @@ int pk_step(pk_env *e, const pk_config *c, int32_t a1, int32_t a2, int32_t obs[7
  * actions int32 [n][2]; obs int32 [n][2][35]; reward double [n][2]; done uint8 [n]. */
 int pk_vec_step(pk_env *envs, int64_t n, const pk_config *c, const int32_t *actions,
                 int32_t *obs, double *reward, uint8_t *done, int autoreset);
+
+void pk_vec_obs(const pk_env *envs, int64_t n, int32_t *obs); /* _get_obs of every env, no step */
+
+/* pk_vec_step plus RecordEpisodeStatistics (record_episode_statistics.py:17-40) and the product's
+ * truncation. ep_return double [n][2] in/out: running sum of each agent's wrapped rewards, zeroed by
+ * a reset (:24-25), += on every step (:32); ep_length int32 [n]: step() calls since reset (:33);
+ * truncated uint8 [n]: the episode reached c->max_episode_frames without terminating. A truncated
+ * env is treated like a terminated one by the next call (reset, or frozen). Any pointer may be NULL. */
+int pk_vec_step_ex(pk_env *envs, int64_t n, const pk_config *c, const int32_t *actions, int32_t *obs,
+                   double *reward, uint8_t *done, int autoreset, double *ep_return,
+                   int32_t *ep_length, uint8_t *truncated);
+void pk_vec_reset_ex(pk_env *envs, int64_t n, const pk_config *c, int32_t *obs, double *ep_return,
+                     int32_t *ep_length);
+
+/* NormalizeObservation (normalize_observation.py:18-32): (obs - low) / (high - low) in double with the
+ * bounds of raw_env.observation_space (pikazoo_env.py:485-562); obs int32 [n][70] -> out double [n][70]. */
+void pk_normalize_obs(int64_t n, const int32_t *obs, double *out);
 void pk_vec_init(pk_env *envs, int64_t n, uint64_t base_seed);
 void pk_vec_reset(pk_env *envs, int64_t n, const pk_config *c, int32_t *obs);
 
@@ -104,8 +130,8 @@ int32_t pk_synth_action(uint64_t action_seed, uint64_t global_env, uint64_t fram
 
 /* K frames of every env with auto-reset; action_mode 0 = all actions 0 (NOOP; computer
  * players ignore them), 1 = pk_synth_action(action_seed, first_env + i, frame0 + k, agent).
- * stats[8] += {env_steps, episodes, sum_episode_frames, p1_wins, p2_wins,
- *              p1_points, p2_points, resets}. Returns total env-steps executed. */
+ * stats[9] += {env_steps, episodes, sum_episode_frames, p1_wins, p2_wins,
+ *              p1_points, p2_points, resets, truncated}. Returns total env-steps executed. */
 int64_t pk_vec_rollout(pk_env *envs, int64_t n, const pk_config *c, int K, int action_mode,
                        uint64_t action_seed, uint64_t first_env, uint64_t frame0,
                        int64_t *stats);

@@ -30,6 +30,9 @@ class PkConfig(ctypes.Structure):
         ("x_line", ctypes.c_int32),
         ("y_line", ctypes.c_int32),
         ("additional_reward", ctypes.c_double * 8),
+        ("reward_in_normal_state", ctypes.c_int32),
+        ("max_episode_frames", ctypes.c_int32),
+        ("normal_state_reward", ctypes.c_double),
     ]
 
 
@@ -66,6 +69,11 @@ def lib():
         L.pk_step.restype = ctypes.c_int
         L.pk_vec_step.argtypes = [vp, i64, cfgp, vp, vp, vp, vp, ctypes.c_int]
         L.pk_vec_step.restype = ctypes.c_int
+        L.pk_vec_step_ex.argtypes = [vp, i64, cfgp, vp, vp, vp, vp, ctypes.c_int, vp, vp, vp]
+        L.pk_vec_step_ex.restype = ctypes.c_int
+        L.pk_vec_reset_ex.argtypes = [vp, i64, cfgp, vp, vp, vp]
+        L.pk_normalize_obs.argtypes = [i64, vp, vp]
+        L.pk_vec_obs.argtypes = [vp, i64, vp]
         L.pk_vec_init.argtypes = [vp, i64, u64]
         L.pk_vec_reset.argtypes = [vp, i64, cfgp, vp]
         L.pk_synth_action.argtypes = [u64, u64, u64, ctypes.c_int, u32]
@@ -86,6 +94,11 @@ def make_config(
     is_player2_computer=False,
     simplify_action=False,
     reward_by_ball_position=None,
+    reward_in_normal_state=None,
+    normal_state_first=False,
+    max_episode_frames=0,
+    normalize_observation=False,        # handled by OracleVecEnv.normalized_obs / convert_obs
+    record_episode_statistics=False,    # OracleVecEnv always keeps episode_return / episode_length
 ) -> PkConfig:
     c = PkConfig()
     c.winning_score = int(winning_score)
@@ -101,6 +114,10 @@ def make_config(
         c.x_line, c.y_line = int(x_line), int(y_line)
         for k in range(8):
             c.additional_reward[k] = float(add[k])
+    if reward_in_normal_state is not None:
+        c.reward_in_normal_state = 2 if normal_state_first else 1
+        c.normal_state_reward = float(reward_in_normal_state)
+    c.max_episode_frames = int(max_episode_frames)
     return c
 
 
@@ -119,25 +136,41 @@ class OracleVecEnv:
         self.obs = np.zeros((self.n, 2, 35), dtype=np.int32)
         self.reward = np.zeros((self.n, 2), dtype=np.float64)
         self.done = np.zeros((self.n,), dtype=np.uint8)
+        self.truncated = np.zeros((self.n,), dtype=np.uint8)
+        self.episode_return = np.zeros((self.n, 2), dtype=np.float64)
+        self.episode_length = np.zeros((self.n,), dtype=np.int32)
         lib().pk_vec_init(_p(self.state), self.n, int(seed))
 
     def reset(self):
-        lib().pk_vec_reset(_p(self.state), self.n, ctypes.byref(self.cfg), _p(self.obs))
+        lib().pk_vec_reset_ex(_p(self.state), self.n, ctypes.byref(self.cfg), _p(self.obs), _p(self.episode_return),
+                              _p(self.episode_length))
         return self.obs
 
     def step(self, actions):
-        a = np.ascontiguousarray(actions, dtype=np.int32).reshape(self.n, 2)
-        rc = lib().pk_vec_step(
-            _p(self.state), self.n, ctypes.byref(self.cfg), _p(a), _p(self.obs), _p(self.reward), _p(self.done),
-            int(self.autoreset),
+        a = None if actions is None else np.ascontiguousarray(actions, dtype=np.int32).reshape(self.n, 2)
+        rc = lib().pk_vec_step_ex(
+            _p(self.state), self.n, ctypes.byref(self.cfg), None if a is None else _p(a), _p(self.obs),
+            _p(self.reward), _p(self.done), int(self.autoreset), _p(self.episode_return), _p(self.episode_length),
+            _p(self.truncated),
         )
         if rc != 0:
             raise IndexError("action out of range")
         return self.obs, self.reward, self.done
 
+    def current_obs(self):
+        """_get_obs of every env from the current state (e.g. after a rollout)."""
+        lib().pk_vec_obs(_p(self.state), self.n, _p(self.obs))
+        return self.obs
+
+    def normalized_obs(self, dtype=np.float64):
+        """NormalizeObservation output for the current obs: float64 as the reference wrapper produces
+        it; float32 = astype(float32) of that; float16 = astype(float16) of the float32; "bfloat16" =
+        the float32 rounded to nearest-even on its upper 16 bits, returned as uint16 bit patterns."""
+        return convert_obs(self.obs, dtype, normalize=True)
+
     def rollout(self, K, action_mode=0, action_seed=0, first_env=0, frame0=0, stats=None):
         if stats is None:
-            stats = np.zeros(8, dtype=np.int64)
+            stats = np.zeros(9, dtype=np.int64)
         lib().pk_vec_rollout(
             _p(self.state), self.n, ctypes.byref(self.cfg), int(K), int(action_mode), int(action_seed),
             int(first_env), int(frame0), _p(stats),
@@ -162,3 +195,35 @@ def simulate_many(xyv: np.ndarray, power: bool) -> np.ndarray:
     out = np.zeros(len(q), dtype=np.int32)
     lib().pk_simulate_many(len(q), _p(q), int(bool(power)), _p(out))
     return out
+
+
+def normalize_obs(obs: np.ndarray) -> np.ndarray:
+    o = np.ascontiguousarray(obs, dtype=np.int32).reshape(-1, 70)
+    out = np.zeros(o.shape, dtype=np.float64)
+    lib().pk_normalize_obs(len(o), _p(o), _p(out))
+    return out.reshape(np.shape(obs))
+
+
+def float32_to_bfloat16_bits(f: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even of float32 to bfloat16, as uint16 bit patterns (no NaNs occur here)."""
+    u = np.ascontiguousarray(f, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = u + 0x7FFF + ((u >> 16) & 1)
+    return (u >> 16).astype(np.uint16)
+
+
+def convert_obs(obs: np.ndarray, dtype, normalize: bool):
+    """The product's observation dtypes restated with numpy (include/pikazoo_b200.h PZ_OBS_*)."""
+    if dtype in (np.int32, np.int16):
+        assert not normalize
+        return np.asarray(obs).astype(dtype)
+    f64 = normalize_obs(obs) if normalize else np.asarray(obs).astype(np.float64)
+    if dtype == np.float64:
+        return f64
+    f32 = f64.astype(np.float32)
+    if dtype == np.float32:
+        return f32
+    if dtype == np.float16:
+        return f32.astype(np.float16)
+    if dtype == "bfloat16":
+        return float32_to_bfloat16_bits(f32)
+    raise ValueError(dtype)

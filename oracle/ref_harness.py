@@ -157,10 +157,15 @@ def load_reference():
     return pikazoo_v0, wrappers
 
 
-def make_env(seed, *, simplify_action=False, reward_by_ball_position=None, **kwargs):
+def make_env(seed, *, simplify_action=False, reward_by_ball_position=None, reward_in_normal_state=None,
+             normal_state_first=False, normalize_observation=False, record_episode_statistics=False, **kwargs):
     """Construct a reference env (optionally wrapped) seeded by protocol S0.
 
     reward_by_ball_position: None or (additional_reward[8], x_line, y_line).
+    reward_in_normal_state: None or the reward; normal_state_first puts that wrapper INSIDE
+    RewardByBallPosition instead of outside it. Wrapper order, innermost first:
+    SimplifyAction, [RewardInNormalState], RewardByBallPosition, [RewardInNormalState],
+    NormalizeObservation, RecordEpisodeStatistics — all the reference's own classes.
     Returns the outermost env; ``.unwrapped`` / ``raw`` attribute gives the raw_env.
     """
     pikazoo_v0, wrappers = load_reference()
@@ -169,9 +174,17 @@ def make_env(seed, *, simplify_action=False, reward_by_ball_position=None, **kwa
     env = raw
     if simplify_action:
         env = wrappers.SimplifyAction(env)
+    if reward_in_normal_state is not None and normal_state_first:
+        env = wrappers.RewardInNormalState(env, reward_in_normal_state)
     if reward_by_ball_position is not None:
         add, x_line, y_line = reward_by_ball_position
         env = wrappers.RewardByBallPosition(env, tuple(add), x_line, y_line)
+    if reward_in_normal_state is not None and not normal_state_first:
+        env = wrappers.RewardInNormalState(env, reward_in_normal_state)
+    if normalize_observation:
+        env = wrappers.NormalizeObservation(env)
+    if record_episode_statistics:
+        env = wrappers.RecordEpisodeStatistics(env)
     env.raw = raw
     return env
 

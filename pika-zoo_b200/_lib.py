@@ -19,12 +19,16 @@ NUM_STATS = 16
 SERVE_CODES = {"winner": 0, "alternate": 1, "random": 2}
 ACT_I32, ACT_I64, ACT_U8 = 0, 1, 2
 REW_F32, REW_F64 = 0, 1
+OBS_I32, OBS_I16, OBS_F32, OBS_F16, OBS_BF16, OBS_F64 = 0, 1, 2, 3, 4, 5
+RINS_OFF, RINS_OUTER, RINS_INNER = 0, 1, 2
 ACTIONS_NOOP, ACTIONS_SYNTH = 0, 1
 FLAG_NO_TABLES = 1
+FLAG_NO_L2_HINTS = 2
+VERSION = 2
 
 STAT_NAMES = (
     "calls", "episodes", "episode_frames", "p1_wins", "p2_wins", "p1_points", "p2_points", "resets",
-    "bad_actions", "frozen",
+    "bad_actions", "frozen", "truncated",
 )
 
 
@@ -45,6 +49,21 @@ class PzConfig(ctypes.Structure):
         ("action_dtype", ctypes.c_int32),
         ("reward_dtype", ctypes.c_int32),
         ("flags", ctypes.c_int32),
+        ("obs_dtype", ctypes.c_int32),
+        ("normalize_observation", ctypes.c_int32),
+        ("reward_in_normal_state", ctypes.c_int32),
+        ("max_episode_frames", ctypes.c_int32),
+        ("normal_state_reward", ctypes.c_double),
+    ]
+
+
+class PzEpisodeIo(ctypes.Structure):
+    """struct pz_episode_io (include/pikazoo_b200.h)."""
+
+    _fields_ = [
+        ("episode_return_dev", ctypes.c_void_p),
+        ("episode_length_dev", ctypes.c_void_p),
+        ("truncated_dev", ctypes.c_void_p),
     ]
 
 
@@ -81,11 +100,16 @@ def load() -> ctypes.CDLL:
     L.pz_seed_array.argtypes = [vp, i64, vp, vp]
     L.pz_reset.argtypes = [vp, i64, cfgp, vp, vp]
     L.pz_step.argtypes = [vp, i64, cfgp, vp, vp, vp, vp, vp, vp]
+    epp = ctypes.POINTER(PzEpisodeIo)
+    L.pz_reset_ex.argtypes = [vp, i64, cfgp, vp, epp, vp]
+    L.pz_step_ex.argtypes = [vp, i64, cfgp, vp, vp, vp, vp, vp, epp, vp]
+    L.pz_obs_elem_bytes.argtypes = [i32]
+    L.pz_obs_elem_bytes.restype = ctypes.c_size_t
     L.pz_rollout.argtypes = [vp, i64, cfgp, i32, i32, u64, u64, u64, vp, vp, vp]
     L.pz_export_state.argtypes = [vp, i64, vp, vp]
     L.pz_import_state.argtypes = [vp, i64, vp, vp]
-    for name in ("pz_seed", "pz_seed_array", "pz_reset", "pz_step", "pz_rollout", "pz_export_state",
-                 "pz_import_state"):
+    for name in ("pz_seed", "pz_seed_array", "pz_reset", "pz_reset_ex", "pz_step", "pz_step_ex", "pz_rollout",
+                 "pz_export_state", "pz_import_state"):
         getattr(L, name).restype = ctypes.c_int
     L.pz_tables_prepare.argtypes = [vp]
     L.pz_tables_prepare.restype = ctypes.c_int
@@ -105,7 +129,7 @@ def load() -> ctypes.CDLL:
     L.pz_host_state_dev.restype = vp
     L.pz_host_destroy.argtypes = [vp]
     L.pz_host_destroy.restype = None
-    if L.pz_state_words() != STATE_WORDS or L.pz_unpacked_words() != UNPACKED_WORDS:
+    if L.pz_version() != VERSION or L.pz_state_words() != STATE_WORDS or L.pz_unpacked_words() != UNPACKED_WORDS:
         raise PikaLibraryError("libpikazoo_b200.so does not match this Python package (rebuild it)")
     _lib = L
     return L

@@ -11,13 +11,14 @@ import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_PATH = os.path.join(CSRC, "libpikazoo_b200.so")
-SOURCES = ["pz_kernels.cu", "pz_host.cu"]
-HEADERS = ["pz_state.cuh", "pz_rng.cuh", "pz_physics.cuh", "pz_kernels.cuh"]
+SOURCES = ["pz_kernels.cu", "pz_host.cu", "pz_step_ai0.cu", "pz_step_ai1.cu", "pz_step_ai2.cu", "pz_step_ai3.cu"]
+HEADERS = ["pz_state.cuh", "pz_rng.cuh", "pz_physics.cuh", "pz_kernels.cuh", "pz_device.cuh", "pz_step_inst.inc"]
 
 
 def _nvcc() -> str:
@@ -38,19 +39,29 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [
-        _nvcc(),
-        "-gencode", "arch=compute_100a,code=sm_100a",
-        "-lineinfo", "-O3", "-std=c++17",
-        "-Xcompiler", "-fPIC", "-shared",
-        "-I", INCLUDE,
-        "-o", LIB_PATH,
-    ] + [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    nvcc = _nvcc()
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+             "-I", INCLUDE]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd), flush=True)
-    subprocess.run(cmd, check=True)
+        flags += ["-Xptxas", "-v"]
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + flags + ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, r
+
+    # the translation units are independent (no relocatable device code): compile them in parallel
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    for src, obj, r in results:
+        if verbose or r.returncode != 0:
+            sys.stderr.write(f"---- {src}\n{r.stdout}{r.stderr}")
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}")
+    subprocess.run([nvcc, "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB_PATH] + [obj for _, obj, _ in results], check=True)
     return LIB_PATH
 
 

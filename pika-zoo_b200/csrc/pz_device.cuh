@@ -1,0 +1,332 @@
+// Device-side pieces shared by the kernel translation units: launch parameters, observation output
+// (shared-memory staging + one bulk async copy per warp), statistics, rewards, and the per-step
+// kernel template. The step kernel is instantiated per (AI_MASK, observation dtype) in
+// pz_step_ai{0,1,2,3}.cu so that every combination keeps its own register budget (the int32 /
+// no-computer instantiation stays at 80 registers) and the translation units compile in parallel.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/pikazoo_b200.h"
+#include "pz_physics.cuh"
+
+namespace pz {
+
+constexpr int kThreads = 128;  // 4 warps; 4 x 8960 B of observation staging per CTA
+constexpr int kWarps = kThreads / 32;
+constexpr int kObsRow = 70;                      // int32 per env: [obs_p1 | obs_p2]
+constexpr int kWarpObsBytes = 32 * kObsRow * 4;  // 8960, multiple of 16
+
+struct KParams {
+    int32_t *state;
+    int64_t n;           // envs in the state buffer (SoA stride)
+    int64_t begin, end;  // env range processed by this launch (begin % 32 == 0)
+    const void *actions;
+    void *obs;
+    void *reward;
+    uint8_t *done;
+    unsigned long long *stats;
+    double2 *ep_return;   // RecordEpisodeStatistics running returns (in/out), may be null
+    int32_t *ep_length;   // may be null
+    uint8_t *truncated;   // may be null
+    StepCfg cfg;
+    int autoreset, simplify, shaped, act_dtype, rew_dtype, obs_dtype, normalize;
+    int max_frames;       // 0: never truncate
+    uint64_t state_policy, out_policy;  // L2 cache policies (pz_state.cuh), kL2EvictNormal when hints are off
+    int x_line, y_line;
+    // rollout only
+    int K, action_source;
+    uint64_t action_seed, first_env, frame0;
+    // RewardByBallPosition fused: table[agent][own base reward + 1][zone], evaluated on the host in
+    // double exactly as Python evaluates `int + float` (reward_by_ball_position.py:28-29)
+    double table[24];
+};
+
+// ---- observation output ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Whole warps write their 32 observation rows ([obs_p1 | obs_p2], 70 elements) as ONE contiguous bulk
+// copy shared -> global issued by lane 0 (cp.async.bulk; no per-thread strided stores): 8,960 B for
+// 4-byte elements, 4,480 B for 2-byte ones. Rows are staged with 64-bit (resp. 32-bit) shared stores;
+// the row stride of 70 (resp. 35) words makes them conflict-free per half-warp (resp. warp).
+template <int DT>
+struct ObsType;
+template <>
+struct ObsType<PZ_OBS_I32> { static constexpr int bytes = 4; };
+template <>
+struct ObsType<PZ_OBS_I16> { static constexpr int bytes = 2; };
+template <>
+struct ObsType<PZ_OBS_F32> { static constexpr int bytes = 4; };
+template <>
+struct ObsType<PZ_OBS_F16> { static constexpr int bytes = 2; };
+template <>
+struct ObsType<PZ_OBS_BF16> { static constexpr int bytes = 2; };
+template <>
+struct ObsType<PZ_OBS_F64> { static constexpr int bytes = 8; };
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// The 70 elements of one env's row, written with the widest naturally aligned stores
+// (row addresses are multiples of 70 * element size, so 8 / 4 / 16-byte aligned).
+template <int DT>
+__device__ __forceinline__ void write_obs_row(const Env &e, bool normalize, void *row) {
+    int u[35];
+    obs_values(e, u);
+    if (DT == PZ_OBS_I32) {
+        int2 *r2 = reinterpret_cast<int2 *>(row);
+#pragma unroll
+        for (int j = 0; j < 35; j++) r2[j] = make_int2(u[obs_src(2 * j)], u[obs_src(2 * j + 1)]);
+    } else if (DT == PZ_OBS_I16) {
+        uint32_t *r = reinterpret_cast<uint32_t *>(row);
+#pragma unroll
+        for (int j = 0; j < 35; j++)
+            r[j] = ((uint32_t)u[obs_src(2 * j)] & 0xFFFFu) | ((uint32_t)u[obs_src(2 * j + 1)] << 16);
+    } else if (DT == PZ_OBS_F64) {
+        double f[35];
+        obs_floats(u, f, normalize);
+        double2 *r = reinterpret_cast<double2 *>(row);
+#pragma unroll
+        for (int j = 0; j < 35; j++) r[j] = make_double2(f[obs_src(2 * j)], f[obs_src(2 * j + 1)]);
+    } else {
+        float f[35];
+        obs_floats(u, f, normalize);
+        if (DT == PZ_OBS_F32) {
+            float2 *r = reinterpret_cast<float2 *>(row);
+#pragma unroll
+            for (int j = 0; j < 35; j++) r[j] = make_float2(f[obs_src(2 * j)], f[obs_src(2 * j + 1)]);
+        } else {
+            uint32_t *r = reinterpret_cast<uint32_t *>(row);
+#pragma unroll
+            for (int j = 0; j < 35; j++)
+                r[j] = DT == PZ_OBS_F16 ? pack_half2(f[obs_src(2 * j)], f[obs_src(2 * j + 1)])
+                                        : pack_bf162(f[obs_src(2 * j)], f[obs_src(2 * j + 1)]);
+        }
+    }
+}
+
+__device__ __forceinline__ void bulk_store_issue(void *gdst, const void *ssrc, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+                 "r"(smem_addr(ssrc)), "r"(bytes), "l"(policy)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// Returns true if this lane issued a bulk copy it must wait for before the CTA's smem dies.
+template <int DT>
+__device__ __forceinline__ bool emit_obs_as(const Env &e, bool valid, bool normalize, void *obs, int64_t env_idx,
+                                            int64_t end, int *warp_stage, int lane, uint64_t policy) {
+    constexpr int row_bytes = kObsRow * ObsType<DT>::bytes;
+    const int64_t warp_first = env_idx - lane;
+    char *g = reinterpret_cast<char *>(obs);
+    if (DT != PZ_OBS_F64 && warp_first + 32 <= end) {  // warp-uniform: full warp
+        write_obs_row<DT>(e, normalize, reinterpret_cast<char *>(warp_stage) + lane * row_bytes);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            bulk_store_issue(g + warp_first * row_bytes, warp_stage, 32 * row_bytes, policy);
+            return true;
+        }
+    } else if (valid) {  // ragged tail (and float64 rows, 17,920 B per warp): plain vector stores
+        write_obs_row<DT>(e, normalize, g + env_idx * row_bytes);
+    }
+    return false;
+}
+
+__device__ __forceinline__ bool emit_obs(const Env &e, bool valid, int obs_dtype, bool normalize, void *obs,
+                                         int64_t env_idx, int64_t end, int *warp_stage, int lane, uint64_t policy) {
+    switch (obs_dtype) {  // launch-uniform
+        case PZ_OBS_I32: return emit_obs_as<PZ_OBS_I32>(e, valid, normalize, obs, env_idx, end, warp_stage, lane, policy);
+        case PZ_OBS_I16: return emit_obs_as<PZ_OBS_I16>(e, valid, normalize, obs, env_idx, end, warp_stage, lane, policy);
+        case PZ_OBS_F32: return emit_obs_as<PZ_OBS_F32>(e, valid, normalize, obs, env_idx, end, warp_stage, lane, policy);
+        case PZ_OBS_F16: return emit_obs_as<PZ_OBS_F16>(e, valid, normalize, obs, env_idx, end, warp_stage, lane, policy);
+        case PZ_OBS_BF16: return emit_obs_as<PZ_OBS_BF16>(e, valid, normalize, obs, env_idx, end, warp_stage, lane, policy);
+        default: return emit_obs_as<PZ_OBS_F64>(e, valid, normalize, obs, env_idx, end, warp_stage, lane, policy);
+    }
+}
+
+// ---- statistics ------------------------------------------------------------------------------------
+__device__ __forceinline__ void stat_add(unsigned long long *stats, int slot, unsigned v) {
+    if (v) atomicAdd(stats + slot, (unsigned long long)v);
+}
+
+// Episode-granular events only (rare), aggregated per warp before touching L2 atomics.
+__device__ __forceinline__ void accumulate_stats(unsigned long long *stats, const Env &e, bool terminated,
+                                                 bool was_reset, bool bad, bool frozen, bool truncated, int lane) {
+    const unsigned tm = __ballot_sync(kFullMask, terminated);
+    const unsigned rm = __ballot_sync(kFullMask, was_reset);
+    const unsigned bm = __ballot_sync(kFullMask, bad);
+    const unsigned fm = __ballot_sync(kFullMask, frozen);
+    const unsigned xm = __ballot_sync(kFullMask, truncated);
+    if ((tm | rm | bm | fm | xm) == 0) return;
+    unsigned frames = 0, s1 = 0, s2 = 0, w1 = 0;
+    if (tm) {
+        frames = __reduce_add_sync(kFullMask, terminated ? (unsigned)e.ep_frames : 0u);
+        s1 = __reduce_add_sync(kFullMask, terminated ? (unsigned)e.score[0] : 0u);
+        s2 = __reduce_add_sync(kFullMask, terminated ? (unsigned)e.score[1] : 0u);
+        w1 = __popc(__ballot_sync(kFullMask, terminated && e.score[0] > e.score[1]));
+    }
+    if (lane == 0) {
+        stat_add(stats, PZ_STAT_EPISODES, __popc(tm));
+        stat_add(stats, PZ_STAT_EPISODE_FRAMES, frames);
+        stat_add(stats, PZ_STAT_P1_WINS, w1);
+        stat_add(stats, PZ_STAT_P2_WINS, __popc(tm) - w1);
+        stat_add(stats, PZ_STAT_P1_POINTS, s1);
+        stat_add(stats, PZ_STAT_P2_POINTS, s2);
+        stat_add(stats, PZ_STAT_RESETS, __popc(rm));
+        stat_add(stats, PZ_STAT_BAD_ACTIONS, __popc(bm));
+        stat_add(stats, PZ_STAT_FROZEN, __popc(fm));
+        stat_add(stats, PZ_STAT_TRUNCATED, __popc(xm));
+    }
+}
+
+__device__ __forceinline__ void load_actions(const KParams &P, int64_t i, int &a1, int &a2) {
+    if (P.act_dtype == PZ_ACT_I32) {
+        int2 a = reinterpret_cast<const int2 *>(P.actions)[i];
+        a1 = a.x;
+        a2 = a.y;
+    } else if (P.act_dtype == PZ_ACT_I64) {
+        longlong2 a = reinterpret_cast<const longlong2 *>(P.actions)[i];
+        a1 = (a.x < -1 || a.x > 1000) ? -1 : (int)a.x;
+        a2 = (a.y < -1 || a.y > 1000) ? -1 : (int)a.y;
+    } else {
+        uchar2 a = reinterpret_cast<const uchar2 *>(P.actions)[i];
+        a1 = a.x;
+        a2 = a.y;
+    }
+}
+
+// RewardByBallPosition zone (reward_by_ball_position.py:22-26) from the post-step ball
+__device__ __forceinline__ int ball_zone(const Env &e, const KParams &P) {
+    return (e.b.y > P.y_line ? 1 : 0) + 2 * (e.b.x >= P.x_line ? 1 : 0);
+}
+
+// The (wrapped) rewards of one executed step: RewardByBallPosition / RewardInNormalState come from
+// the host-built table [agent][own base reward + 1][zone].
+__device__ __forceinline__ void step_rewards(const KParams &P, const Env &e, int base, double &r1, double &r2) {
+    if (P.shaped) {
+        const int z = ball_zone(e, P);
+        r1 = P.table[(base + 1) * 4 + z];
+        r2 = P.table[12 + (1 - base) * 4 + z];
+    } else {
+        r1 = (double)base;
+        r2 = (double)(-base);
+    }
+}
+
+__device__ __forceinline__ void store_reward(const KParams &P, int64_t i, double r1, double r2) {
+    if (P.rew_dtype == PZ_REW_F32) {
+        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(
+                         reinterpret_cast<float2 *>(P.reward) + i),
+                     "f"((float)r1), "f"((float)r2), "l"(P.out_policy)
+                     : "memory");
+    } else {
+        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(
+                         reinterpret_cast<double2 *>(P.reward) + i),
+                     "d"(r1), "d"(r2), "l"(P.out_policy)
+                     : "memory");
+    }
+}
+
+// An episode is over when the game ended or (optionally) when it reached max_frames step() calls.
+__device__ __forceinline__ bool episode_truncated(const KParams &P, const Env &e) {
+    return P.max_frames > 0 && !e.game_ended && e.ep_frames >= P.max_frames;
+}
+
+// ---- per-step kernel ---------------------------------------------------------------------------
+template <int AI_MASK, int OBS_DT>
+__global__ void __launch_bounds__(kThreads) pz_step_kernel(const __grid_constant__ KParams P) {
+    __shared__ __align__(128) int stage[kWarps][32 * kObsRow];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = P.begin + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool valid = i < P.end;
+
+    DrawCtx d;
+    d.s = state_ptrs(P.state, P.n, P.state_policy);
+    d.idx = i;
+    d.r.loaded = false;
+    d.r.dirty = false;
+    Env e;
+    int a1 = 0, a2 = 0;
+    if (valid) {
+        load_env(e, d.s, i);
+        if (P.actions) load_actions(P, i, a1, a2);
+        if (AI_MASK != 0) rng_load(d.r, d.s, i);  // computer players draw on most frames
+    } else {
+        fresh_env(e);
+        e.game_ended = 1;
+    }
+
+    const bool over = e.game_ended || episode_truncated(P, e);
+    const bool run = valid && !over;
+    const bool do_reset = valid && over && P.autoreset;
+    const bool frozen = valid && over && !P.autoreset;
+    const unsigned mask = __ballot_sync(kFullMask, run);
+    int base = 0;
+    bool bad = false;
+    if (run) {
+        bool bad1, bad2;
+        uint32_t k1, k2;
+        if (P.simplify) {
+            k1 = decode_keys<0, true>(a1, bad1);
+            k2 = decode_keys<1, true>(a2, bad2);
+        } else {
+            k1 = decode_keys<0, false>(a1, bad1);
+            k2 = decode_keys<1, false>(a2, bad2);
+        }
+        bad = bad1 || bad2;
+        base = step_frame<AI_MASK>(mask, e, d, P.cfg, k1, k2, stage[warp]);
+    } else if (do_reset) {
+        reset_env(e, d, P.cfg);
+    }
+
+    __syncwarp();  // the staging buffer doubled as the computer players' scratch
+    bool pending = false;
+    if (P.obs) pending = emit_obs_as<OBS_DT>(e, valid, P.normalize, P.obs, i, P.end, stage[warp], lane, P.out_policy);
+    const bool truncated = valid && episode_truncated(P, e);  // this call's step reached the cap, or frozen there
+    if (valid) {
+        if (run || do_reset) {
+            store_env(e, d.s, i);
+            if (d.r.dirty) rng_store(d.r, d.s, i);
+        }
+        double r1 = 0.0, r2 = 0.0;
+        if (run) step_rewards(P, e, base, r1, r2);
+        if (P.reward) store_reward(P, i, r1, r2);
+        if (P.ep_return) {  // record_episode_statistics.py:24-25 (reset zeroes), :32 (step adds)
+            if (do_reset) {
+                P.ep_return[i] = make_double2(0.0, 0.0);
+            } else if (run) {
+                double2 acc = P.ep_return[i];
+                acc.x += r1;
+                acc.y += r2;
+                P.ep_return[i] = acc;
+            }
+        }
+        if (P.ep_length) P.ep_length[i] = e.ep_frames;
+        if (P.done) P.done[i] = (uint8_t)(e.game_ended ? 1 : 0);  // a reset cleared it; frozen envs keep it
+        if (P.truncated) P.truncated[i] = (uint8_t)(truncated ? 1 : 0);
+    }
+    if (P.stats) {
+        accumulate_stats(P.stats, e, run && e.game_ended, do_reset, bad, frozen, run && truncated, lane);
+        if (i == P.begin) atomicAdd(P.stats + PZ_STAT_CALLS, (unsigned long long)(P.end - P.begin));
+    }
+    if (pending) bulk_store_wait_read();
+}
+
+// Launches pz_step_kernel<AI_MASK, P.obs_dtype>; defined (explicitly instantiated) in pz_step_ai*.cu.
+template <int AI_MASK>
+void launch_step_kernel(unsigned grid, cudaStream_t st, const KParams &P);
+
+}  // namespace pz

@@ -17,13 +17,13 @@ struct pz_host_ctx {
     int device = 0;
     int32_t *state = nullptr;
     void *actions = nullptr;
-    int32_t *obs = nullptr;
+    char *obs = nullptr;
     void *reward = nullptr;
     uint8_t *done = nullptr;
     int64_t *stats = nullptr;
     std::vector<cudaStream_t> streams;
     std::vector<int64_t> bounds;  // chunk c = [bounds[c], bounds[c+1])
-    size_t act_elem = 4, rew_elem = 4;
+    size_t act_elem = 4, rew_elem = 4, obs_row = 2 * PZ_OBS_WORDS * 4;  // obs_row: bytes per env
 };
 
 namespace {
@@ -53,6 +53,11 @@ int pz_host_create(pz_host_ctx **out, int64_t n, const pz_config *cfg, uint64_t 
     c->cfg = *cfg;
     c->act_elem = cfg->action_dtype == PZ_ACT_I64 ? 8 : (cfg->action_dtype == PZ_ACT_U8 ? 1 : 4);
     c->rew_elem = cfg->reward_dtype == PZ_REW_F64 ? 8 : 4;
+    if (pz_obs_elem_bytes(cfg->obs_dtype) == 0) {
+        delete c;
+        return PZ_E_BADCONFIG;
+    }
+    c->obs_row = 2 * PZ_OBS_WORDS * pz_obs_elem_bytes(cfg->obs_dtype);
     if (chunks < 1) chunks = 1;
     // chunk boundaries on multiples of 128 envs (whole CTAs, 16-byte aligned slices of every array)
     int64_t blocks = (n + 127) / 128;
@@ -68,7 +73,7 @@ int pz_host_create(pz_host_ctx **out, int64_t n, const pz_config *cfg, uint64_t 
         if ((rc = (int)cudaGetDevice(&c->device))) break;
         if ((rc = (int)cudaMalloc(&c->state, pz_state_bytes(n)))) break;
         if ((rc = (int)cudaMalloc(&c->actions, (size_t)n * 2 * c->act_elem))) break;
-        if ((rc = (int)cudaMalloc(&c->obs, (size_t)n * 2 * PZ_OBS_WORDS * sizeof(int32_t)))) break;
+        if ((rc = (int)cudaMalloc(&c->obs, (size_t)n * c->obs_row))) break;
         if ((rc = (int)cudaMalloc(&c->reward, (size_t)n * 2 * c->rew_elem))) break;
         if ((rc = (int)cudaMalloc(&c->done, (size_t)n))) break;
         if ((rc = (int)cudaMalloc(&c->stats, PZ_NUM_STATS * sizeof(int64_t)))) break;
@@ -88,23 +93,22 @@ int pz_host_create(pz_host_ctx **out, int64_t n, const pz_config *cfg, uint64_t 
     return 0;
 }
 
-int pz_host_reset(pz_host_ctx *c, int32_t *obs_host) {
+int pz_host_reset(pz_host_ctx *c, void *obs_host) {
     if (!c) return PZ_E_BADARG;
     const int chunks = (int)c->streams.size();
     for (int k = 0; k < chunks; k++) {
         const int64_t b = c->bounds[k], e = c->bounds[k + 1];
         if (e <= b) continue;
-        int rc = pz::launch_reset(c->state, c->n, b, e, &c->cfg, obs_host ? c->obs : nullptr, c->streams[k]);
+        int rc = pz::launch_reset(c->state, c->n, b, e, &c->cfg, obs_host ? c->obs : nullptr, nullptr, c->streams[k]);
         if (rc) return rc;
         if (obs_host)
-            PZ_CUDA(cudaMemcpyAsync(obs_host + b * 2 * PZ_OBS_WORDS, c->obs + b * 2 * PZ_OBS_WORDS,
-                                    (size_t)(e - b) * 2 * PZ_OBS_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                                    c->streams[k]));
+            PZ_CUDA(cudaMemcpyAsync((char *)obs_host + (size_t)b * c->obs_row, c->obs + (size_t)b * c->obs_row,
+                                    (size_t)(e - b) * c->obs_row, cudaMemcpyDeviceToHost, c->streams[k]));
     }
     return sync_all(c);
 }
 
-int pz_host_step(pz_host_ctx *c, const void *actions_host, int32_t *obs_host, void *reward_host,
+int pz_host_step(pz_host_ctx *c, const void *actions_host, void *obs_host, void *reward_host,
                  uint8_t *done_host) {
     if (!c) return PZ_E_BADARG;
     const bool both_ai = c->cfg.is_player1_computer && c->cfg.is_player2_computer;
@@ -121,11 +125,11 @@ int pz_host_step(pz_host_ctx *c, const void *actions_host, int32_t *obs_host, vo
                                     cudaMemcpyHostToDevice, s));
         int rc = pz::launch_step(c->state, c->n, b, e, &c->cfg, actions_host ? c->actions : nullptr,
                                  obs_host ? c->obs : nullptr, reward_host ? c->reward : nullptr,
-                                 done_host ? c->done : nullptr, c->stats, s);
+                                 done_host ? c->done : nullptr, c->stats, nullptr, s);
         if (rc) return rc;
         if (obs_host)
-            PZ_CUDA(cudaMemcpyAsync(obs_host + b * 2 * PZ_OBS_WORDS, c->obs + b * 2 * PZ_OBS_WORDS,
-                                    cnt * 2 * PZ_OBS_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            PZ_CUDA(cudaMemcpyAsync((char *)obs_host + (size_t)b * c->obs_row, c->obs + (size_t)b * c->obs_row,
+                                    cnt * c->obs_row, cudaMemcpyDeviceToHost, s));
         if (reward_host)
             PZ_CUDA(cudaMemcpyAsync((char *)reward_host + (size_t)b * 2 * c->rew_elem,
                                     (const char *)c->reward + (size_t)b * 2 * c->rew_elem, cnt * 2 * c->rew_elem,

@@ -12,216 +12,26 @@
 #include <mutex>
 
 #include "../../include/pikazoo_b200.h"
+#include "pz_device.cuh"
 #include "pz_kernels.cuh"
-#include "pz_physics.cuh"
 
 namespace pz {
 
-constexpr int kThreads = 128;  // 4 warps; 4 x 8960 B of observation staging per CTA
-constexpr int kWarps = kThreads / 32;
-constexpr int kObsRow = 70;                      // int32 per env: [obs_p1 | obs_p2]
-constexpr int kWarpObsBytes = 32 * kObsRow * 4;  // 8960, multiple of 16
-
-struct KParams {
-    int32_t *state;
-    int64_t n;           // envs in the state buffer (SoA stride)
-    int64_t begin, end;  // env range processed by this launch (begin % 32 == 0)
-    const void *actions;
-    int32_t *obs;
-    void *reward;
-    uint8_t *done;
-    unsigned long long *stats;
-    StepCfg cfg;
-    int autoreset, simplify, shaped, act_dtype, rew_dtype;
-    int x_line, y_line;
-    // rollout only
-    int K, action_source;
-    uint64_t action_seed, first_env, frame0;
-    // RewardByBallPosition fused: table[agent][own base reward + 1][zone], evaluated on the host in
-    // double exactly as Python evaluates `int + float` (reward_by_ball_position.py:28-29)
-    double table[24];
-};
-
-// ---- observation output ------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// Whole warps write their 32 x 280 B of observations as ONE contiguous 8960-byte bulk copy
-// shared -> global issued by lane 0 (cp.async.bulk; no per-thread strided stores). Rows are staged
-// with 64-bit shared stores (row stride 280 B => conflict-free per half-warp).
-__device__ __forceinline__ void stage_obs_row(const Env &e, int *row) {
-    int u[35];
-    obs_values(e, u);
-    int2 *r2 = reinterpret_cast<int2 *>(row);
-#pragma unroll
-    for (int j = 0; j < 35; j++) r2[j] = make_int2(u[obs_src(2 * j)], u[obs_src(2 * j + 1)]);
-}
-
-__device__ __forceinline__ void bulk_store_issue(void *gdst, const void *ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(ssrc)),
-                 "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_store_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
-// Returns true if this lane issued a bulk copy it must wait for before the CTA's smem dies.
-__device__ __forceinline__ bool emit_obs(const Env &e, bool valid, int32_t *obs, int64_t env_idx, int64_t end,
-                                         int *warp_stage, int lane) {
-    const int64_t warp_first = env_idx - lane;
-    if (warp_first + 32 <= end) {  // warp-uniform: full warp
-        stage_obs_row(e, warp_stage + lane * kObsRow);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-            bulk_store_issue(obs + warp_first * kObsRow, warp_stage, kWarpObsBytes);
-            return true;
-        }
-    } else if (valid) {  // ragged tail: plain 64-bit stores (rows are 8-byte aligned)
-        int u[35];
-        obs_values(e, u);
-        int2 *g = reinterpret_cast<int2 *>(obs + env_idx * kObsRow);
-#pragma unroll
-        for (int j = 0; j < 35; j++) g[j] = make_int2(u[obs_src(2 * j)], u[obs_src(2 * j + 1)]);
-    }
-    return false;
-}
-
-// ---- statistics ------------------------------------------------------------------------------------
-__device__ __forceinline__ void stat_add(unsigned long long *stats, int slot, unsigned v) {
-    if (v) atomicAdd(stats + slot, (unsigned long long)v);
-}
-
-// Episode-granular events only (rare), aggregated per warp before touching L2 atomics.
-__device__ __forceinline__ void accumulate_stats(unsigned long long *stats, const Env &e, bool terminated,
-                                                 bool was_reset, bool bad, bool frozen, int lane) {
-    const unsigned tm = __ballot_sync(kFullMask, terminated);
-    const unsigned rm = __ballot_sync(kFullMask, was_reset);
-    const unsigned bm = __ballot_sync(kFullMask, bad);
-    const unsigned fm = __ballot_sync(kFullMask, frozen);
-    if ((tm | rm | bm | fm) == 0) return;
-    unsigned frames = 0, s1 = 0, s2 = 0, w1 = 0;
-    if (tm) {
-        frames = __reduce_add_sync(kFullMask, terminated ? (unsigned)e.ep_frames : 0u);
-        s1 = __reduce_add_sync(kFullMask, terminated ? (unsigned)e.score[0] : 0u);
-        s2 = __reduce_add_sync(kFullMask, terminated ? (unsigned)e.score[1] : 0u);
-        w1 = __popc(__ballot_sync(kFullMask, terminated && e.score[0] > e.score[1]));
-    }
-    if (lane == 0) {
-        stat_add(stats, PZ_STAT_EPISODES, __popc(tm));
-        stat_add(stats, PZ_STAT_EPISODE_FRAMES, frames);
-        stat_add(stats, PZ_STAT_P1_WINS, w1);
-        stat_add(stats, PZ_STAT_P2_WINS, __popc(tm) - w1);
-        stat_add(stats, PZ_STAT_P1_POINTS, s1);
-        stat_add(stats, PZ_STAT_P2_POINTS, s2);
-        stat_add(stats, PZ_STAT_RESETS, __popc(rm));
-        stat_add(stats, PZ_STAT_BAD_ACTIONS, __popc(bm));
-        stat_add(stats, PZ_STAT_FROZEN, __popc(fm));
-    }
-}
-
-__device__ __forceinline__ void load_actions(const KParams &P, int64_t i, int &a1, int &a2) {
-    if (P.act_dtype == PZ_ACT_I32) {
-        int2 a = reinterpret_cast<const int2 *>(P.actions)[i];
-        a1 = a.x;
-        a2 = a.y;
-    } else if (P.act_dtype == PZ_ACT_I64) {
-        longlong2 a = reinterpret_cast<const longlong2 *>(P.actions)[i];
-        a1 = (a.x < -1 || a.x > 1000) ? -1 : (int)a.x;
-        a2 = (a.y < -1 || a.y > 1000) ? -1 : (int)a.y;
-    } else {
-        uchar2 a = reinterpret_cast<const uchar2 *>(P.actions)[i];
-        a1 = a.x;
-        a2 = a.y;
-    }
-}
-
-// RewardByBallPosition zone (reward_by_ball_position.py:22-26) from the post-step ball
-__device__ __forceinline__ int ball_zone(const Env &e, const KParams &P) {
-    return (e.b.y > P.y_line ? 1 : 0) + 2 * (e.b.x >= P.x_line ? 1 : 0);
-}
-
-__device__ __forceinline__ void store_reward(const KParams &P, int64_t i, const Env &e, int base, bool stepped) {
-    double r1 = 0.0, r2 = 0.0;
-    if (stepped) {
-        if (P.shaped) {
-            const int z = ball_zone(e, P);
-            r1 = P.table[(base + 1) * 4 + z];
-            r2 = P.table[12 + (1 - base) * 4 + z];
-        } else {
-            r1 = (double)base;
-            r2 = (double)(-base);
-        }
-    }
-    if (P.rew_dtype == PZ_REW_F32)
-        reinterpret_cast<float2 *>(P.reward)[i] = make_float2((float)r1, (float)r2);
-    else
-        reinterpret_cast<double2 *>(P.reward)[i] = make_double2(r1, r2);
-}
-
-// ---- per-step kernel ---------------------------------------------------------------------------
-template <int AI_MASK>
-__global__ void __launch_bounds__(kThreads) pz_step_kernel(const __grid_constant__ KParams P) {
-    __shared__ __align__(128) int stage[kWarps][32 * kObsRow];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t i = P.begin + (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    const bool valid = i < P.end;
-
-    DrawCtx d;
-    d.s = state_ptrs(P.state, P.n);
-    d.idx = i;
-    d.r.loaded = false;
-    d.r.dirty = false;
+// Observation rows from non-inlined code, for the kernels that emit them once per launch (reset,
+// rollout): keeps the six dtype variants out of their register allocation. The env is re-read from
+// the state the calling thread has just stored (same thread, program order), so nothing but a few
+// scalars crosses the call.
+__device__ __noinline__ bool emit_obs_cold(int32_t *state, int64_t n, int64_t env_idx, int64_t end, int obs_dtype,
+                                           bool normalize, void *obs, int *warp_stage, uint64_t state_policy,
+                                           uint64_t out_policy) {
+    const int lane = threadIdx.x & 31;
+    const bool valid = env_idx < end;
     Env e;
-    int a1 = 0, a2 = 0;
-    if (valid) {
-        load_env(e, d.s, i);
-        if (P.actions) load_actions(P, i, a1, a2);
-        if (AI_MASK != 0) rng_load(d.r, d.s, i);  // computer players draw on most frames
-    } else {
+    if (valid)
+        load_env(e, state_ptrs(state, n, state_policy), env_idx);
+    else
         fresh_env(e);
-        e.game_ended = 1;
-    }
-
-    const bool run = valid && !e.game_ended;
-    const bool do_reset = valid && e.game_ended && P.autoreset;
-    const bool frozen = valid && e.game_ended && !P.autoreset;
-    const unsigned mask = __ballot_sync(kFullMask, run);
-    int base = 0;
-    bool bad = false;
-    if (run) {
-        bool bad1, bad2;
-        uint32_t k1, k2;
-        if (P.simplify) {
-            k1 = decode_keys<0, true>(a1, bad1);
-            k2 = decode_keys<1, true>(a2, bad2);
-        } else {
-            k1 = decode_keys<0, false>(a1, bad1);
-            k2 = decode_keys<1, false>(a2, bad2);
-        }
-        bad = bad1 || bad2;
-        base = step_frame<AI_MASK>(mask, e, d, P.cfg, k1, k2, stage[warp]);
-    } else if (do_reset) {
-        reset_env(e, d, P.cfg);
-    }
-
-    __syncwarp();  // the staging buffer doubled as the computer players' scratch
-    bool pending = false;
-    if (P.obs) pending = emit_obs(e, valid, P.obs, i, P.end, stage[warp], lane);
-    if (valid) {
-        if (run || do_reset) {
-            store_env(e, d.s, i);
-            if (d.r.dirty) rng_store(d.r, d.s, i);
-        }
-        if (P.reward) store_reward(P, i, e, base, run);
-        if (P.done) P.done[i] = (uint8_t)((run && e.game_ended) || frozen);
-    }
-    if (P.stats) {
-        accumulate_stats(P.stats, e, run && e.game_ended, do_reset, bad, frozen, lane);
-        if (i == P.begin) atomicAdd(P.stats + PZ_STAT_CALLS, (unsigned long long)(P.end - P.begin));
-    }
-    if (pending) bulk_store_wait_read();
+    return emit_obs(e, valid, obs_dtype, normalize, obs, env_idx, end, warp_stage, lane, out_policy);
 }
 
 // ---- K-frame register-resident rollout -------------------------------------------------------
@@ -233,7 +43,7 @@ __global__ void __launch_bounds__(kThreads) pz_rollout_kernel(const __grid_const
     const bool valid = i < P.end;
 
     DrawCtx d;
-    d.s = state_ptrs(P.state, P.n);
+    d.s = state_ptrs(P.state, P.n, P.state_policy);
     d.idx = i;
     d.r.loaded = false;
     d.r.dirty = false;
@@ -248,11 +58,11 @@ __global__ void __launch_bounds__(kThreads) pz_rollout_kernel(const __grid_const
     const uint64_t genv = P.first_env + (uint64_t)i;
 
     // episode-granular statistics accumulated per thread, reduced once at the end
-    unsigned st_ep = 0, st_frames = 0, st_w1 = 0, st_s1 = 0, st_s2 = 0, st_resets = 0;
+    unsigned st_ep = 0, st_frames = 0, st_w1 = 0, st_s1 = 0, st_s2 = 0, st_resets = 0, st_trunc = 0;
 
 #pragma unroll 1
     for (int k = 0; k < P.K; k++) {
-        const bool run = valid && !e.game_ended;
+        const bool run = valid && !e.game_ended && !episode_truncated(P, e);
         const unsigned mask = __ballot_sync(kFullMask, run);
         if (run) {
             uint32_t k1 = 0, k2 = 0;
@@ -275,6 +85,8 @@ __global__ void __launch_bounds__(kThreads) pz_rollout_kernel(const __grid_const
                 st_w1 += (e.score[0] > e.score[1]) ? 1u : 0u;
                 st_s1 += (unsigned)e.score[0];
                 st_s2 += (unsigned)e.score[1];
+            } else if (episode_truncated(P, e)) {
+                st_trunc += 1;
             }
         } else if (valid) {
             reset_env(e, d, P.cfg);
@@ -283,15 +95,18 @@ __global__ void __launch_bounds__(kThreads) pz_rollout_kernel(const __grid_const
     }
 
     __syncwarp();
-    bool pending = false;
-    if (P.obs) pending = emit_obs(e, valid, P.obs, i, P.end, stage[warp], lane);
     if (valid) {
         store_env(e, d.s, i);
         if (d.r.dirty) rng_store(d.r, d.s, i);
     }
+    bool pending = false;
+    if (P.obs) pending = emit_obs_cold(P.state, P.n, i, P.end, P.obs_dtype, P.normalize, P.obs, stage[warp], P.state_policy,
+                                       P.out_policy);
     if (P.stats) {
         const unsigned ep = __reduce_add_sync(kFullMask, st_ep);
         const unsigned rs = __reduce_add_sync(kFullMask, st_resets);
+        const unsigned tr = __reduce_add_sync(kFullMask, st_trunc);
+        if (lane == 0) stat_add(P.stats, PZ_STAT_TRUNCATED, tr);
         if (ep | rs) {
             const unsigned fr = __reduce_add_sync(kFullMask, st_frames);
             const unsigned w1 = __reduce_add_sync(kFullMask, st_w1);
@@ -320,7 +135,7 @@ __global__ void __launch_bounds__(kThreads) pz_reset_kernel(const __grid_constan
     const int64_t i = P.begin + (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const bool valid = i < P.end;
     DrawCtx d;
-    d.s = state_ptrs(P.state, P.n);
+    d.s = state_ptrs(P.state, P.n, P.state_policy);
     d.idx = i;
     d.r.loaded = false;
     d.r.dirty = false;
@@ -334,7 +149,10 @@ __global__ void __launch_bounds__(kThreads) pz_reset_kernel(const __grid_constan
         fresh_env(e);
     }
     bool pending = false;
-    if (P.obs) pending = emit_obs(e, valid, P.obs, i, P.end, stage[warp], lane);
+    if (P.obs) pending = emit_obs_cold(P.state, P.n, i, P.end, P.obs_dtype, P.normalize, P.obs, stage[warp], P.state_policy,
+                                       P.out_policy);
+    if (valid && P.ep_return) P.ep_return[i] = make_double2(0.0, 0.0);
+    if (valid && P.ep_length) P.ep_length[i] = 0;
     if (pending) bulk_store_wait_read();
 }
 
@@ -467,6 +285,10 @@ static int check_config(const pz_config *c) {
     if (c->serve < 0 || c->serve > 2) return PZ_E_BADCONFIG;
     if (c->action_dtype < 0 || c->action_dtype > 2) return PZ_E_BADCONFIG;
     if (c->reward_dtype < 0 || c->reward_dtype > 1) return PZ_E_BADCONFIG;
+    if (c->obs_dtype < PZ_OBS_I32 || c->obs_dtype > PZ_OBS_F64) return PZ_E_BADCONFIG;
+    if (c->normalize_observation && (c->obs_dtype == PZ_OBS_I32 || c->obs_dtype == PZ_OBS_I16)) return PZ_E_BADCONFIG;
+    if (c->reward_in_normal_state < PZ_RINS_OFF || c->reward_in_normal_state > PZ_RINS_INNER) return PZ_E_BADCONFIG;
+    if (c->max_episode_frames < 0) return PZ_E_BADCONFIG;
     return 0;
 }
 
@@ -480,17 +302,27 @@ static void fill_params(KParams &P, int32_t *state, int64_t n, const pz_config *
     P.cfg.serve = c->serve;
     P.autoreset = c->autoreset != 0;
     P.simplify = c->simplify_action != 0;
-    P.shaped = c->reward_by_ball_position != 0;
+    P.shaped = c->reward_by_ball_position != 0 || c->reward_in_normal_state != PZ_RINS_OFF;
     P.act_dtype = c->action_dtype;
     P.rew_dtype = c->reward_dtype;
+    P.obs_dtype = c->obs_dtype;
+    P.normalize = c->normalize_observation != 0;
+    P.max_frames = c->max_episode_frames;
+    const bool hints = !(c->flags & PZ_FLAG_NO_L2_HINTS);
+    P.state_policy = hints ? kL2EvictLast : kL2EvictNormal;
+    P.out_policy = hints ? kL2EvictFirst : kL2EvictNormal;
     P.x_line = c->x_line;
     P.y_line = c->y_line;
     for (int agent = 0; agent < 2; agent++)
         for (int b = 0; b < 3; b++)
             for (int z = 0; z < 4; z++) {
-                // Python: rews[agent] (int) += additional_reward[agent*4 + zone]
+                // the wrapper stack evaluated in double, as Python does on `int` / `float` rewards, innermost
+                // wrapper first: reward_in_normal_state.py:13-14 `if rews[agent] == 0: rews[agent] = reward`,
+                // reward_by_ball_position.py:28-29 `rews[agent] += additional_reward[agent*4 + zone]`
                 double r = (double)(b - 1);
+                if (c->reward_in_normal_state == PZ_RINS_INNER && r == 0.0) r = c->normal_state_reward;
                 if (c->reward_by_ball_position) r = r + c->additional_reward[agent * 4 + z];
+                if (c->reward_in_normal_state == PZ_RINS_OUTER && r == 0.0) r = c->normal_state_reward;
                 P.table[agent * 12 + b * 4 + z] = r;
             }
 }
@@ -518,8 +350,8 @@ static int launch_status() {
     return err == cudaSuccess ? 0 : (int)err;
 }
 
-int launch_reset(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const pz_config *cfg, int32_t *obs_dev,
-                 cudaStream_t stream) {
+int launch_reset(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const pz_config *cfg, void *obs_dev,
+                 const pz_episode_io *ep, cudaStream_t stream) {
     if (!state_dev || n < 0 || begin < 0 || end > n || begin > end || (begin & 31)) return PZ_E_BADARG;
     if (int rc = check_config(cfg)) return rc;
     if (!aligned16(state_dev) || !aligned16(obs_dev)) return PZ_E_ALIGN;
@@ -529,13 +361,18 @@ int launch_reset(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, cons
     P.begin = begin;
     P.end = end;
     P.obs = obs_dev;
+    if (ep) {
+        if (!aligned16(ep->episode_return_dev)) return PZ_E_ALIGN;
+        P.ep_return = reinterpret_cast<double2 *>(ep->episode_return_dev);
+        P.ep_length = ep->episode_length_dev;
+    }
     pz_reset_kernel<<<grid_for(end - begin), kThreads, 0, stream>>>(P);
     return launch_status();
 }
 
 int launch_step(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const pz_config *cfg,
-                const void *actions_dev, int32_t *obs_dev, void *reward_dev, uint8_t *done_dev, int64_t *stats_dev,
-                cudaStream_t st) {
+                const void *actions_dev, void *obs_dev, void *reward_dev, uint8_t *done_dev, int64_t *stats_dev,
+                const pz_episode_io *ep, cudaStream_t st) {
     if (!state_dev || n < 0 || begin < 0 || end > n || begin > end || (begin & 31)) return PZ_E_BADARG;
     if (int rc = check_config(cfg)) return rc;
     const int am = ai_mask(cfg);
@@ -553,12 +390,18 @@ int launch_step(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const
     P.reward = reward_dev;
     P.done = done_dev;
     P.stats = reinterpret_cast<unsigned long long *>(stats_dev);
+    if (ep) {
+        if (!aligned16(ep->episode_return_dev)) return PZ_E_ALIGN;
+        P.ep_return = reinterpret_cast<double2 *>(ep->episode_return_dev);
+        P.ep_length = ep->episode_length_dev;
+        P.truncated = ep->truncated_dev;
+    }
     const unsigned grid = grid_for(end - begin);
     switch (am) {
-        case 0: pz_step_kernel<0><<<grid, kThreads, 0, st>>>(P); break;
-        case 1: pz_step_kernel<1><<<grid, kThreads, 0, st>>>(P); break;
-        case 2: pz_step_kernel<2><<<grid, kThreads, 0, st>>>(P); break;
-        default: pz_step_kernel<3><<<grid, kThreads, 0, st>>>(P); break;
+        case 0: launch_step_kernel<0>(grid, st, P); break;
+        case 1: launch_step_kernel<1>(grid, st, P); break;
+        case 2: launch_step_kernel<2>(grid, st, P); break;
+        default: launch_step_kernel<3>(grid, st, P); break;
     }
     return launch_status();
 }
@@ -611,18 +454,41 @@ int pz_seed_array(int32_t *state_dev, int64_t n, const uint64_t *seeds_dev, void
     return launch_status();
 }
 
-int pz_reset(int32_t *state_dev, int64_t n, const pz_config *cfg, int32_t *obs_dev, void *stream) {
-    return pz::launch_reset(state_dev, n, 0, n, cfg, obs_dev, (cudaStream_t)stream);
+size_t pz_obs_elem_bytes(int32_t obs_dtype) {
+    switch (obs_dtype) {
+        case PZ_OBS_I32:
+        case PZ_OBS_F32: return 4;
+        case PZ_OBS_I16:
+        case PZ_OBS_F16:
+        case PZ_OBS_BF16: return 2;
+        case PZ_OBS_F64: return 8;
+        default: return 0;
+    }
 }
 
-int pz_step(int32_t *state_dev, int64_t n, const pz_config *cfg, const void *actions_dev, int32_t *obs_dev,
+int pz_reset(int32_t *state_dev, int64_t n, const pz_config *cfg, void *obs_dev, void *stream) {
+    return pz::launch_reset(state_dev, n, 0, n, cfg, obs_dev, nullptr, (cudaStream_t)stream);
+}
+
+int pz_reset_ex(int32_t *state_dev, int64_t n, const pz_config *cfg, void *obs_dev, const pz_episode_io *episode,
+                void *stream) {
+    return pz::launch_reset(state_dev, n, 0, n, cfg, obs_dev, episode, (cudaStream_t)stream);
+}
+
+int pz_step(int32_t *state_dev, int64_t n, const pz_config *cfg, const void *actions_dev, void *obs_dev,
             void *reward_dev, uint8_t *done_dev, int64_t *stats_dev, void *stream) {
-    return pz::launch_step(state_dev, n, 0, n, cfg, actions_dev, obs_dev, reward_dev, done_dev, stats_dev,
+    return pz::launch_step(state_dev, n, 0, n, cfg, actions_dev, obs_dev, reward_dev, done_dev, stats_dev, nullptr,
+                           (cudaStream_t)stream);
+}
+
+int pz_step_ex(int32_t *state_dev, int64_t n, const pz_config *cfg, const void *actions_dev, void *obs_dev,
+               void *reward_dev, uint8_t *done_dev, int64_t *stats_dev, const pz_episode_io *episode, void *stream) {
+    return pz::launch_step(state_dev, n, 0, n, cfg, actions_dev, obs_dev, reward_dev, done_dev, stats_dev, episode,
                            (cudaStream_t)stream);
 }
 
 int pz_rollout(int32_t *state_dev, int64_t n, const pz_config *cfg, int32_t K, int32_t action_source,
-               uint64_t action_seed, uint64_t first_env, uint64_t frame0, int32_t *obs_dev, int64_t *stats_dev,
+               uint64_t action_seed, uint64_t first_env, uint64_t frame0, void *obs_dev, int64_t *stats_dev,
                void *stream) {
     if (!state_dev || n < 0 || K < 1) return PZ_E_BADARG;
     if (action_source != PZ_ACTIONS_NOOP && action_source != PZ_ACTIONS_SYNTH) return PZ_E_BADARG;

@@ -11,9 +11,9 @@ namespace pz {
 // Step / reset the env range [begin, end) of a state buffer holding n envs (begin % 32 == 0).
 // actions/obs/reward/done are the base pointers of the full [n]-sized arrays.
 int launch_step(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const pz_config *cfg,
-                const void *actions_dev, int32_t *obs_dev, void *reward_dev, uint8_t *done_dev, int64_t *stats_dev,
-                cudaStream_t stream);
-int launch_reset(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const pz_config *cfg, int32_t *obs_dev,
-                 cudaStream_t stream);
+                const void *actions_dev, void *obs_dev, void *reward_dev, uint8_t *done_dev, int64_t *stats_dev,
+                const pz_episode_io *episode, cudaStream_t stream);
+int launch_reset(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const pz_config *cfg, void *obs_dev,
+                 const pz_episode_io *episode, cudaStream_t stream);
 
 }  // namespace pz

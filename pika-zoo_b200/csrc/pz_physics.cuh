@@ -7,6 +7,8 @@
 // this frame (warp votes keep the warp converged; a lane that has finished idles predicated
 // instead of forcing a reconvergence stack).
 #pragma once
+#include <utility>
+
 #include "pz_rng.cuh"
 
 namespace pz {
@@ -623,6 +625,56 @@ __device__ __forceinline__ void obs_values(const Env &e, int (&u)[35]) {
     u[32] = b.xv;
     u[33] = b.yv;
     u[34] = b.pow;
+}
+
+// NormalizeObservation (pikazoo/wrappers/normalize_observation.py:18-32): (obs - low) / (high - low)
+// with the bounds of raw_env.observation_space (pikazoo_env.py:485-562), per distinct value u[k].
+// The reference divides int64 arrays with numpy true division, i.e. one correctly rounded double
+// division per element; the float32 form is float32(that double), which equals the correctly rounded
+// float32 division of the same two integers (double rounding is innocuous for p = 24 into P = 53 >= 2p + 2).
+__host__ __device__ constexpr int obs_low(int k) {
+    return k < 26 ? ((k % 13) == 0 ? kPlayerHalfLength : (k % 13) == 1 ? 108 : (k % 13) == 2 ? -15
+                     : (k % 13) == 3 ? -1 : (k % 13) == 4 ? -2 : 0)
+                  : (k == 26 ? kBallRadius : k == 32 ? -20 : k == 33 ? -124 : 0);
+}
+__host__ __device__ constexpr int obs_high(int k) {
+    return k < 26 ? ((k % 13) == 0 ? kGroundWidth - kPlayerHalfLength : (k % 13) == 1 ? kPlayerGroundY
+                     : (k % 13) == 2 ? 16 : (k % 13) == 3 ? 1 : (k % 13) == 4 ? 3 : ((k % 13) < 7 ? 4 : 1))
+                  : ((k == 26 || k == 28 || k == 30) ? kGroundWidth
+                     : (k == 27 || k == 29 || k == 31) ? kBallGroundY : k == 32 ? 20 : k == 33 ? 124 : 1);
+}
+
+// float32(n / D) for a compile-time divisor without a division: q = n * RN(1/D), one FMA for the exact
+// residual n - q*D, one FMA to apply it (Markstein's correction; correctly rounded for every numerator
+// the packed state can hold — checked exhaustively on the host by tests/test_device_code_on_host.py).
+// Powers of two multiply exactly.
+template <int D>
+__device__ __forceinline__ float div_const_f32(int n) {
+    const float a = (float)n;  // exact: |n| < 2^24
+    if ((D & (D - 1)) == 0) return a * (1.0f / (float)D);
+    constexpr float r = 1.0f / (float)D;
+    const float q = a * r;
+    const float rem = fmaf(-q, (float)D, a);
+    return fmaf(rem, r, q);
+}
+
+// element K of the distinct values, as floating point
+template <typename F, int K>
+__device__ __forceinline__ F obs_float(const int (&u)[35], bool normalize) {
+    if (!normalize) return (F)u[K];
+    if (sizeof(F) == 4) return (F)div_const_f32<obs_high(K) - obs_low(K)>(u[K] - obs_low(K));
+    return (F)(u[K] - obs_low(K)) / (F)(obs_high(K) - obs_low(K));
+}
+
+template <typename F, int... K>
+__device__ __forceinline__ void obs_floats_impl(const int (&u)[35], F (&f)[35], bool normalize,
+                                                std::integer_sequence<int, K...>) {
+    ((f[K] = obs_float<F, K>(u, normalize)), ...);
+}
+// all 35 distinct values (the two agents' rows are permutations of them)
+template <typename F>
+__device__ __forceinline__ void obs_floats(const int (&u)[35], F (&f)[35], bool normalize) {
+    obs_floats_impl(u, f, normalize, std::make_integer_sequence<int, 35>{});
 }
 
 // index into u[] of element k (0..69) of the [obs_p1 | obs_p2] row

@@ -56,13 +56,24 @@ struct Rng {
 //   G0 = {P1 bits 0..31, P2 bits 0..31, P1 bits 32..43 | P2 bits 32..43 << 12, ep_frames}
 //   G1 = {B0, B1, B2, ENV}
 //   G2 = PCG64 state (little-endian 32-bit words), G3 = PCG64 inc, U = uinteger
+// L2 eviction policies (the 64-bit operand of `.L2::cache_hint`; values of createpolicy.fractional
+// with fraction 1.0). The env state is re-read by the next launch and is small next to the 126 MB L2
+// (32 MB per million envs without computer players, 71 MB with), while observations / rewards / dones
+// are written once and never read back by the simulator: state accesses ask to be evicted last, output
+// stores first, so the state lives in L2 across launches and never travels to HBM and back.
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ULL;
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ULL;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ULL;
+
 struct StatePtrs {
     int4 *g0, *g1, *g2, *g3;
     uint32_t *u;
+    uint64_t policy;  // L2 cache policy of every state access
 };
 
-__host__ __device__ inline StatePtrs state_ptrs(int32_t *base, int64_t n) {
+__host__ __device__ inline StatePtrs state_ptrs(int32_t *base, int64_t n, uint64_t policy = kL2EvictLast) {
     StatePtrs s;
+    s.policy = policy;
     s.g0 = reinterpret_cast<int4 *>(base);
     s.g1 = s.g0 + n;
     s.g2 = s.g1 + n;
@@ -158,47 +169,67 @@ __device__ __forceinline__ void unpack_g0(Env &e, int4 w) {
     e.ep_frames = w.w;
 }
 
-// Streaming 128-bit accesses: state and outputs are touched once per launch, keep them out of L1.
-__device__ __forceinline__ int4 ld_stream(const int4 *p) {
+// 128-bit state accesses: touched once per launch (keep them out of L1), L2 policy from the caller.
+__device__ __forceinline__ int4 ld_stream(const int4 *p, uint64_t policy) {
 #ifdef PZ_HOST_EMULATION  // tests/emul: the device code compiled for the host, one lane per warp
+    (void)policy;
     return *p;
 #else
     int4 r;
-    asm volatile("ld.global.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
+                 : "l"(p), "l"(policy));
     return r;
 #endif
 }
-__device__ __forceinline__ void st_stream(int4 *p, int4 v) {
+__device__ __forceinline__ void st_stream(int4 *p, int4 v, uint64_t policy) {
 #ifdef PZ_HOST_EMULATION
+    (void)policy;
     *p = v;
 #else
-    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
-                 "r"(v.w)
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.s32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy)
                  : "memory");
+#endif
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p, uint64_t policy) {
+#ifdef PZ_HOST_EMULATION
+    (void)policy;
+    return *p;
+#else
+    uint32_t r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(policy));
+    return r;
+#endif
+}
+__device__ __forceinline__ void st_stream_u32(uint32_t *p, uint32_t v, uint64_t policy) {
+#ifdef PZ_HOST_EMULATION
+    (void)policy;
+    *p = v;
+#else
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(policy) : "memory");
 #endif
 }
 
 __device__ __forceinline__ void load_env(Env &e, const StatePtrs &s, int64_t i) {
-    int4 a = ld_stream(s.g0 + i);
-    int4 b = ld_stream(s.g1 + i);
+    int4 a = ld_stream(s.g0 + i, s.policy);
+    int4 b = ld_stream(s.g1 + i, s.policy);
     unpack_g0(e, a);
     unpack_g1(e, b);
 }
 __device__ __forceinline__ void store_env(const Env &e, const StatePtrs &s, int64_t i) {
-    st_stream(s.g0 + i, pack_g0(e));
-    st_stream(s.g1 + i, pack_g1(e));
+    st_stream(s.g0 + i, pack_g0(e), s.policy);
+    st_stream(s.g1 + i, pack_g1(e), s.policy);
 }
 
 __device__ __forceinline__ void rng_load(Rng &r, const StatePtrs &s, int64_t i) {
-    int4 st = ld_stream(s.g2 + i);
-    int4 ic = ld_stream(s.g3 + i);
+    int4 st = ld_stream(s.g2 + i, s.policy);
+    int4 ic = ld_stream(s.g3 + i, s.policy);
     r.s_lo = (uint64_t)(uint32_t)st.x | ((uint64_t)(uint32_t)st.y << 32);
     r.s_hi = (uint64_t)(uint32_t)st.z | ((uint64_t)(uint32_t)st.w << 32);
     r.inc_lo = (uint64_t)(uint32_t)ic.x | ((uint64_t)(uint32_t)ic.y << 32);
     r.inc_hi = (uint64_t)(uint32_t)ic.z | ((uint64_t)(uint32_t)ic.w << 32);
-    r.uinteger = s.u[i];
+    r.uinteger = ld_stream_u32(s.u + i, s.policy);
     r.loaded = true;
 }
 __device__ __forceinline__ void rng_store(const Rng &r, const StatePtrs &s, int64_t i) {
@@ -207,8 +238,8 @@ __device__ __forceinline__ void rng_store(const Rng &r, const StatePtrs &s, int6
     st.y = (int)(uint32_t)(r.s_lo >> 32);
     st.z = (int)(uint32_t)r.s_hi;
     st.w = (int)(uint32_t)(r.s_hi >> 32);
-    st_stream(s.g2 + i, st);
-    s.u[i] = r.uinteger;
+    st_stream(s.g2 + i, st, s.policy);
+    st_stream_u32(s.u + i, r.uinteger, s.policy);
 }
 
 // ---- unpacked parity form (int32[53], oracle/pika_oracle.h pk_env; words 42..51 are the PCG64

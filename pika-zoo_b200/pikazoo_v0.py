@@ -69,6 +69,10 @@ class raw_env:
         # fused wrapper options, set by pikazoo.wrappers.* before the first reset
         self._simplify_action = False
         self._reward_by_ball_position = None
+        self._reward_in_normal_state = None
+        self._normal_state_first = False
+        self._normalize_observation = False
+        self._record_episode_statistics = False
         self._seed_value = int(np.random.SeedSequence().entropy % (2**63)) if seed is None else int(seed)
         self._vec: Optional[PikaVecEnv] = None
         self.scores: List[int] = [0, 0]
@@ -79,6 +83,10 @@ class raw_env:
         self._vec = PikaVecEnv(
             1, device=self._device, seed=self._seed_value, autoreset=False, reward_dtype=torch.float64,
             simplify_action=self._simplify_action, reward_by_ball_position=self._reward_by_ball_position,
+            reward_in_normal_state=self._reward_in_normal_state, normal_state_first=self._normal_state_first,
+            normalize_observation=self._normalize_observation,
+            obs_dtype=torch.float64 if self._normalize_observation else torch.int32,
+            record_episode_statistics=self._record_episode_statistics,
             **self._kwargs,
         )
         self._actions = torch.zeros((1, 2), dtype=torch.int32, device=self._vec.device)
@@ -93,7 +101,10 @@ class raw_env:
             self._vec.load_state_dict(state)
 
     def _obs_dict(self, obs: torch.Tensor) -> Dict[str, np.ndarray]:
-        o = obs[0].cpu().numpy().astype(np.int64)  # the reference returns np.array of Python ints
+        # the reference returns np.array of Python ints (int64); NormalizeObservation makes them float64
+        o = obs[0].cpu().numpy()
+        if not self._normalize_observation:
+            o = o.astype(np.int64)
         return {self.possible_agents[0]: o[0], self.possible_agents[1]: o[1]}
 
     def _get_infos(self):
@@ -128,15 +139,29 @@ class raw_env:
         s = self._vec.scores()[0].cpu().tolist()
         self.scores[0], self.scores[1] = int(s[0]), int(s[1])
         observations = self._obs_dict(obs)
-        if self._reward_by_ball_position is None:
+        if self._reward_by_ball_position is None and not isinstance(self._reward_in_normal_state, float):
             r = [int(r[0]), int(r[1])]  # the reference's base rewards are Python ints
         rewards = {self.agents[0]: r[0], self.agents[1]: r[1]}
         terminations = {agent: terminated for agent in self.agents}
         truncations = {agent: False for agent in self.agents}
         infos = self._get_infos()
+        if terminated and self._record_episode_statistics:  # record_episode_statistics.py:34-39
+            ret, length = self._episode_rewards(), self._episode_lengths()
+            for agent in self.agents:
+                infos[agent] = dict(infos[agent], episode={"r": ret[agent], "l": length[agent]})
         if terminated:
             self.agents = []
         return observations, rewards, terminations, truncations, infos
+
+    def _episode_rewards(self):
+        r = self._vec.episode_return[0].cpu().tolist()
+        if self._reward_by_ball_position is None and not isinstance(self._reward_in_normal_state, float):
+            r = [int(r[0]), int(r[1])]
+        return dict(zip(self.possible_agents, r))
+
+    def _episode_lengths(self):
+        n = int(self._vec.episode_length[0].item())
+        return {agent: n for agent in self.possible_agents}
 
     @functools.lru_cache(maxsize=None)
     def observation_space(self, agent=None):

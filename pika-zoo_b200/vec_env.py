@@ -27,6 +27,8 @@ from . import _lib
 
 _ACT_DTYPES = {torch.int32: _lib.ACT_I32, torch.int64: _lib.ACT_I64, torch.uint8: _lib.ACT_U8}
 _REW_DTYPES = {torch.float32: _lib.REW_F32, torch.float64: _lib.REW_F64}
+_OBS_DTYPES = {torch.int32: _lib.OBS_I32, torch.int16: _lib.OBS_I16, torch.float32: _lib.OBS_F32,
+               torch.float16: _lib.OBS_F16, torch.bfloat16: _lib.OBS_BF16, torch.float64: _lib.OBS_F64}
 
 AGENTS = ("player_1", "player_2")
 
@@ -42,6 +44,12 @@ def make_config(
     action_dtype: torch.dtype = torch.int32,
     reward_dtype: torch.dtype = torch.float32,
     landing_tables: bool = True,
+    obs_dtype: torch.dtype = torch.int32,
+    normalize_observation: bool = False,
+    reward_in_normal_state: Optional[float] = None,
+    normal_state_first: bool = False,
+    max_episode_frames: int = 0,
+    l2_hints: bool = True,
 ) -> _lib.PzConfig:
     assert serve in ("winner", "alternate", "random")  # pikazoo_env.py:104
     if not 1 <= int(winning_score) <= 1023:
@@ -63,7 +71,20 @@ def make_config(
     c.autoreset = int(bool(autoreset))
     c.action_dtype = _ACT_DTYPES[action_dtype]
     c.reward_dtype = _REW_DTYPES[reward_dtype]
-    c.flags = 0 if landing_tables else _lib.FLAG_NO_TABLES
+    c.flags = (0 if landing_tables else _lib.FLAG_NO_TABLES) | (0 if l2_hints else _lib.FLAG_NO_L2_HINTS)
+    if obs_dtype not in _OBS_DTYPES:
+        raise TypeError(f"obs_dtype must be one of {sorted(str(k) for k in _OBS_DTYPES)}")
+    c.obs_dtype = _OBS_DTYPES[obs_dtype]
+    if normalize_observation and not obs_dtype.is_floating_point:
+        raise TypeError("normalize_observation needs a floating-point obs_dtype "
+                        "(the reference wrapper yields float64; its declared space is float32)")
+    c.normalize_observation = int(bool(normalize_observation))
+    if reward_in_normal_state is not None:  # reward_in_normal_state.py:7-9
+        c.reward_in_normal_state = _lib.RINS_INNER if normal_state_first else _lib.RINS_OUTER
+        c.normal_state_reward = float(reward_in_normal_state)
+    if int(max_episode_frames) < 0:
+        raise ValueError("max_episode_frames must be >= 0 (0 = never truncate)")
+    c.max_episode_frames = int(max_episode_frames)
     return c
 
 
@@ -91,7 +112,28 @@ class PikaVecEnv:
         first_env: int = 0,
         track_stats: bool = True,
         landing_tables: "bool | str" = "auto",
+        obs_dtype: torch.dtype = torch.int32,
+        normalize_observation: bool = False,
+        reward_in_normal_state: Optional[float] = None,
+        normal_state_first: bool = False,
+        max_episode_frames: int = 0,
+        record_episode_statistics: bool = False,
+        l2_hints: bool = True,
     ):
+        """Beyond the reference's constructor arguments:
+
+        obs_dtype: torch.int32 (the reference's declared dtype), int16 (same integers, half the bytes),
+          or float32 / float16 / bfloat16 / float64 — `(float)value`, or with normalize_observation=True
+          the NormalizeObservation wrapper's output (normalize_observation.py:18-32) computed in the
+          kernel; float64 is bit-identical to the reference wrapper, float32 is float32() of it.
+        reward_in_normal_state: fuses RewardInNormalState(env, reward) (reward_in_normal_state.py:10-15),
+          applied outside RewardByBallPosition, or inside it with normal_state_first=True.
+        max_episode_frames: truncate episodes that reach this many step() calls (0 = never, like the
+          reference); `self.truncated` [N] bool reports it and the next call resets the env.
+        record_episode_statistics: fuses RecordEpisodeStatistics (record_episode_statistics.py:17-40):
+          `self.episode_return` [N, 2] float64 and `self.episode_length` [N] int32 are valid for env i
+          on the call where terminated[i] (or truncated[i]) is set.
+        """
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -114,18 +156,36 @@ class PikaVecEnv:
             is_player2_computer=is_player2_computer, simplify_action=simplify_action,
             reward_by_ball_position=reward_by_ball_position, autoreset=autoreset,
             action_dtype=action_dtype, reward_dtype=reward_dtype, landing_tables=self.landing_tables,
+            obs_dtype=obs_dtype, normalize_observation=normalize_observation,
+            reward_in_normal_state=reward_in_normal_state, normal_state_first=normal_state_first,
+            max_episode_frames=max_episode_frames, l2_hints=l2_hints,
         )
         self.cfg = make_config(**self._kw)
         self.action_dtype = action_dtype
         self.reward_dtype = reward_dtype
+        self.obs_dtype = obs_dtype
+        self.record_episode_statistics = bool(record_episode_statistics)
+        self.max_episode_frames = int(max_episode_frames)
         self.num_actions = 13 if simplify_action else 18
         n = self.num_envs
         with torch.cuda.device(self.device):
             self.state = torch.zeros(_lib.STATE_WORDS * n, dtype=torch.int32, device=self.device)
-            self.obs = torch.zeros((n, 2, _lib.OBS_WORDS), dtype=torch.int32, device=self.device)
+            self.obs = torch.zeros((n, 2, _lib.OBS_WORDS), dtype=obs_dtype, device=self.device)
             self.reward = torch.zeros((n, 2), dtype=reward_dtype, device=self.device)
             self.done_u8 = torch.zeros((n,), dtype=torch.uint8, device=self.device)
             self.stats = torch.zeros(_lib.NUM_STATS, dtype=torch.int64, device=self.device) if track_stats else None
+            self.episode_return = self.episode_length = self._truncated_u8 = None
+            self._ep = None
+            if self.record_episode_statistics or self.max_episode_frames > 0:
+                self._ep = _lib.PzEpisodeIo()
+                if self.record_episode_statistics:
+                    self.episode_return = torch.zeros((n, 2), dtype=torch.float64, device=self.device)
+                    self.episode_length = torch.zeros((n,), dtype=torch.int32, device=self.device)
+                    self._ep.episode_return_dev = self.episode_return.data_ptr()
+                    self._ep.episode_length_dev = self.episode_length.data_ptr()
+                if self.max_episode_frames > 0:
+                    self._truncated_u8 = torch.zeros((n,), dtype=torch.uint8, device=self.device)
+                    self._ep.truncated_dev = self._truncated_u8.data_ptr()
             _lib.check(
                 self.lib.pz_seed(self.state.data_ptr(), n, self.seed & (2**64 - 1), self.first_env, self._stream()),
                 "pz_seed",
@@ -142,15 +202,25 @@ class PikaVecEnv:
     def _stats_ptr(self):
         return self.stats.data_ptr() if self.stats is not None else None
 
+    def _ep_ref(self):
+        return ctypes.byref(self._ep) if self._ep is not None else None
+
+    @property
+    def truncated(self) -> Optional[torch.Tensor]:
+        """[N] bool (None unless max_episode_frames > 0): the episode hit the frame cap on the last call."""
+        return self._truncated_u8.view(torch.bool) if self._truncated_u8 is not None else None
+
     # ---- reference-shaped API --------------------------------------------------------------
     def reset(self) -> torch.Tensor:
         """reference reset() on every env; returns obs [N, 2, 35] int32 (a view reused by step)."""
         with torch.cuda.device(self.device):
             _lib.check(
-                self.lib.pz_reset(self.state.data_ptr(), self.num_envs, self._cfg_ref(), self.obs.data_ptr(),
-                                  self._stream()),
+                self.lib.pz_reset_ex(self.state.data_ptr(), self.num_envs, self._cfg_ref(), self.obs.data_ptr(),
+                                     self._ep_ref(), self._stream()),
                 "pz_reset",
             )
+            if self._truncated_u8 is not None:
+                self._truncated_u8.zero_()
         return self.obs
 
     def step(self, actions: Optional[torch.Tensor]):
@@ -172,8 +242,9 @@ class PikaVecEnv:
             a_ptr = None
         with torch.cuda.device(self.device):
             _lib.check(
-                self.lib.pz_step(self.state.data_ptr(), self.num_envs, self._cfg_ref(), a_ptr, self.obs.data_ptr(),
-                                 self.reward.data_ptr(), self.done_u8.data_ptr(), self._stats_ptr(), self._stream()),
+                self.lib.pz_step_ex(self.state.data_ptr(), self.num_envs, self._cfg_ref(), a_ptr,
+                                    self.obs.data_ptr(), self.reward.data_ptr(), self.done_u8.data_ptr(),
+                                    self._stats_ptr(), self._ep_ref(), self._stream()),
                 "pz_step",
             )
         self.frame += 1
@@ -227,10 +298,15 @@ class PikaVecEnv:
 
     def state_dict(self) -> dict:
         """The packed SoA state tensor is the checkpoint."""
-        return {"state": self.state.clone(), "frame": self.frame, "kw": dict(self._kw), "seed": self.seed,
-                "first_env": self.first_env, "num_envs": self.num_envs}
+        sd = {"state": self.state.clone(), "frame": self.frame, "kw": dict(self._kw), "seed": self.seed,
+              "first_env": self.first_env, "num_envs": self.num_envs}
+        if self.episode_return is not None:
+            sd["episode_return"] = self.episode_return.clone()
+        return sd
 
     def load_state_dict(self, sd: dict) -> None:
         assert sd["num_envs"] == self.num_envs
         self.state.copy_(sd["state"])
         self.frame = int(sd["frame"])
+        if self.episode_return is not None and "episode_return" in sd:
+            self.episode_return.copy_(sd["episode_return"])

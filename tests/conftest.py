@@ -22,6 +22,15 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_wrappers():
+    """412 games of the reference's own wrapper stacks (oracle/make_golden.py --wrappers)."""
+    import json
+
+    with open(os.path.join(ROOT, "tests", "golden", "wrappers.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def cuda_lib():
     """Build (if needed) and load the CUDA library; GPU tests must run the native path."""
     import importlib

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>  // vector types only; no CUDA call is made
 
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -174,6 +175,19 @@ void emul_simulate_many(int64_t n, const int32_t *xyv, int power, int32_t *out) 
         const int32_t *q = xyv + 4 * i;
         out[i] = power ? simulate_landing_x<true>(1u, q[0], q[1], q[2], q[3], true, g)
                        : simulate_landing_x<false>(1u, q[0], q[1], q[2], q[3], true, g);
+    }
+}
+
+// NormalizeObservation as the kernels compute it: u int32[n][35] -> float32 / float64 [n][35]
+void emul_normalize(int64_t n, const int32_t *u, float *f32, double *f64, int normalize) {
+    for (int64_t i = 0; i < n; i++) {
+        int v[35];
+        for (int k = 0; k < 35; k++) v[k] = u[i * 35 + k];
+        float a[35];
+        double b[35];
+        obs_floats(v, a, normalize != 0);
+        obs_floats(v, b, normalize != 0);
+        for (int k = 0; k < 35; k++) f32[i * 35 + k] = a[k], f64[i * 35 + k] = b[k];
     }
 }
 

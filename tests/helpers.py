@@ -21,8 +21,10 @@ def group_kwargs(group):
 class SessionRecorder:
     """Per-env sha256 / episode bookkeeping for a batch stepped in lock-step with auto-reset."""
 
-    def __init__(self, n, episodes_per_env, max_calls):
+    def __init__(self, n, episodes_per_env, max_calls, normalized=False, record=False):
         self.n = n
+        self.obs_dt = "<f8" if normalized else "<i4"   # NormalizeObservation yields float64
+        self.record = record                             # RecordEpisodeStatistics: hash r / l on termination
         self.h = [hashlib.sha256() for _ in range(n)]
         self.episodes = [[] for _ in range(n)]
         self.calls = np.zeros(n, dtype=np.int64)
@@ -33,13 +35,17 @@ class SessionRecorder:
         self.max_calls = max_calls
 
     def on_reset(self, obs):
-        obs = np.ascontiguousarray(obs, dtype="<i4")
+        assert np.asarray(obs).dtype == np.dtype(self.obs_dt), np.asarray(obs).dtype
+        obs = np.ascontiguousarray(obs, dtype=self.obs_dt)
         for i in range(self.n):
             self.h[i].update(obs[i].tobytes())
 
-    def on_step(self, obs, reward, done, scores_fn):
-        """obs [n,2,35] int32, reward [n,2] float64, done [n] bool — outputs of one batched call."""
-        obs = np.ascontiguousarray(obs, dtype="<i4")
+    def on_step(self, obs, reward, done, scores_fn, episode_fn=None):
+        """obs [n,2,35] int32 (float64 when normalised), reward [n,2] float64, done [n] bool — outputs of
+        one batched call; episode_fn() -> (returns [n,2] float64, lengths [n]) when recording."""
+        assert np.asarray(obs).dtype == np.dtype(self.obs_dt), np.asarray(obs).dtype
+        obs = np.ascontiguousarray(obs, dtype=self.obs_dt)
+        episode = None
         reward = np.ascontiguousarray(reward, dtype="<f8")
         scores = None
         for i in np.nonzero(self.active)[0]:
@@ -55,8 +61,15 @@ class SessionRecorder:
                 if done[i]:
                     if scores is None:
                         scores = scores_fn()
-                    self.episodes[i].append({"frames": int(self.ep_frames[i]),
-                                             "scores": [int(scores[i][0]), int(scores[i][1])]})
+                    ep = {"frames": int(self.ep_frames[i]), "scores": [int(scores[i][0]), int(scores[i][1])]}
+                    if self.record:
+                        if episode is None:
+                            episode = episode_fn()
+                        r = np.ascontiguousarray(episode[0][i], dtype="<f8")
+                        self.h[i].update(r.tobytes())
+                        self.h[i].update(np.array([episode[1][i]], dtype="<i4").tobytes())
+                        ep["returns"] = [float(r[0]), float(r[1])]
+                    self.episodes[i].append(ep)
                     self.ep_frames[i] = 0
                     self.pending_reset[i] = True
             if self.calls[i] >= self.max_calls:
@@ -78,7 +91,9 @@ def replay_group(group, make_stepper, check_final_state=True):
     cfg = group_kwargs(group)
     n_actions = 13 if cfg.get("simplify_action") else 18
     stepper = make_stepper(n, group["base_seed"], cfg)
-    rec = SessionRecorder(n, group["episodes_per_env"], group["max_calls"])
+    rec = SessionRecorder(n, group["episodes_per_env"], group["max_calls"],
+                          normalized=bool(cfg.get("normalize_observation")),
+                          record=bool(cfg.get("record_episode_statistics")))
     rec.on_reset(stepper.reset())
     frame = 0
     final_states = [None] * n
@@ -89,7 +104,7 @@ def replay_group(group, make_stepper, check_final_state=True):
             actions = synth_actions_numpy(0x5EED, 0, n, frame, n_actions)
         was_active = rec.active.copy()
         obs, reward, done = stepper.step(actions)
-        rec.on_step(obs, reward, done, stepper.scores)
+        rec.on_step(obs, reward, done, stepper.scores, getattr(stepper, "episode", None))
         frame += 1
         finished_now = was_active & ~rec.active
         if check_final_state and finished_now.any():
@@ -114,12 +129,21 @@ class OracleStepper:
         from oracle import pyoracle as po
 
         self.env = po.OracleVecEnv(n, seed=base_seed, autoreset=True, **cfg)
+        self.normalized = bool(cfg.get("normalize_observation"))
+
+    def _obs(self):
+        return self.env.normalized_obs() if self.normalized else self.env.obs
 
     def reset(self):
-        return self.env.reset()
+        self.env.reset()
+        return self._obs()
 
     def step(self, actions):
-        return self.env.step(actions)
+        _, reward, done = self.env.step(actions)
+        return self._obs(), reward, done
+
+    def episode(self):
+        return self.env.episode_return, self.env.episode_length
 
     def scores(self):
         return self.env.state[:, 37:39]

@@ -21,7 +21,7 @@ def _declared_symbols():
 def test_header_declares_the_path():
     syms = _declared_symbols()
     assert {"pz_seed", "pz_reset", "pz_step", "pz_rollout", "pz_export_state", "pz_import_state",
-            "pz_host_create", "pz_host_step", "pz_strerror"} <= syms
+            "pz_host_create", "pz_host_step", "pz_strerror", "pz_step_ex", "pz_reset_ex", "pz_obs_elem_bytes"} <= syms
 
 
 def test_library_exports_every_declared_symbol(cuda_lib):
@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(cuda_lib):
 
 
 def test_constants_and_errors(cuda_lib):
-    assert cuda_lib.pz_version() == 1
+    assert cuda_lib.pz_version() == 2
     assert cuda_lib.pz_state_words() == 17
     assert cuda_lib.pz_unpacked_words() == 53
     assert cuda_lib.pz_state_bytes(1000) == 1000 * 17 * 4
@@ -51,6 +51,12 @@ def test_argument_validation_without_gpu(cuda_lib):
     cfg.winning_score = 15
     assert cuda_lib.pz_reset(ctypes.c_void_p(8), 4, ctypes.byref(cfg), None, None) == -3  # misaligned
     assert cuda_lib.pz_reset(ctypes.c_void_p(16), 0, ctypes.byref(cfg), None, None) == 0  # empty batch
+    cfg.obs_dtype = 9
+    assert cuda_lib.pz_reset(ctypes.c_void_p(16), 4, ctypes.byref(cfg), None, None) == -2
+    cfg.obs_dtype, cfg.normalize_observation = 0, 1  # NormalizeObservation needs a float dtype
+    assert cuda_lib.pz_step_ex(ctypes.c_void_p(16), 4, ctypes.byref(cfg), ctypes.c_void_p(16), None, None, None, None,
+                               None, None) == -2
+    assert [cuda_lib.pz_obs_elem_bytes(k) for k in range(7)] == [4, 2, 4, 2, 2, 8, 0]
 
 
 def test_product_does_not_import_oracle():
@@ -70,4 +76,5 @@ def test_config_struct_layout_matches_header(cuda_lib):
     c = PzConfig()
     cuda_lib.pz_default_config(ctypes.byref(c))
     assert (c.winning_score, c.serve, c.x_line, c.y_line, c.autoreset) == (15, 0, 216, 176, 1)
-    assert ctypes.sizeof(PzConfig) == 8 * 4 + 8 * 8 + 4 * 4 and PzConfig.flags.offset == 108
+    assert ctypes.sizeof(PzConfig) == 8 * 4 + 8 * 8 + 8 * 4 + 8 and PzConfig.flags.offset == 108
+    assert PzConfig.normal_state_reward.offset == 128 and c.obs_dtype == 0 and c.max_episode_frames == 0

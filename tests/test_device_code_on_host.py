@@ -208,6 +208,25 @@ def test_random_states_one_step(emul):
             assert np.array_equal(e.export(), o.state)
 
 
+def test_normalisation_is_correctly_rounded_for_every_representable_value(emul):
+    """The division-free float32 NormalizeObservation (reciprocal multiply + two FMAs) equals
+    float32(float64 division) — what `.astype(float32)` of the reference wrapper's output gives — for
+    every value a packed field can hold (the whole int16 range for each of the 35 elements)."""
+    emul.emul_normalize.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 3 + [ctypes.c_int]
+    vals = np.arange(-32768, 32768, dtype=np.int32)
+    u = np.repeat(vals[:, None], 35, axis=1).copy()
+    f32 = np.zeros(u.shape, dtype=np.float32)
+    f64 = np.zeros(u.shape, dtype=np.float64)
+    emul.emul_normalize(len(u), _p(u), _p(f32), _p(f64), 1)
+    low = np.array(po.convert_obs(np.zeros((1, 2, 35), np.int32), np.float64, True)[0, 0])  # = -low / range
+    ref64 = po.normalize_obs(np.concatenate([u, u], axis=1).reshape(-1, 2, 35))[:, 0, :]
+    assert low.shape == (35,)
+    assert np.array_equal(f64.view(np.uint64), ref64.view(np.uint64))
+    assert np.array_equal(f32.view(np.uint32), ref64.astype(np.float32).view(np.uint32))
+    emul.emul_normalize(len(u), _p(u), _p(f32), _p(f64), 0)
+    assert np.array_equal(f32, u.astype(np.float32)) and np.array_equal(f64, u.astype(np.float64))
+
+
 def test_synth_actions_match(emul):
     for env, frame, agent in [(0, 0, 0), (5, 77, 1), (2**40 + 3, 2**33, 0)]:
         for n_actions in (13, 18):

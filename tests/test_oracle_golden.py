@@ -35,3 +35,17 @@ def test_oracle_replays_golden_group(golden, name):
         group = dict(group, num_envs=12, sessions=group["sessions"][:12])
     bad = replay_group(group, OracleStepper)
     assert not bad, bad[:5]
+
+
+WRAPPER_GROUPS = ["normalize_rins_outer_shaped_simplify_ws5", "rins_inner_shaped_record_ws5",
+                  "normalize_record_ai_p2_ws3", "normalize_rins_int_ai_vs_ai_ws2"]
+
+
+@pytest.mark.parametrize("name", WRAPPER_GROUPS)
+def test_oracle_replays_wrapper_stacks(golden_wrappers, name):
+    """NormalizeObservation / RewardInNormalState (inside and outside RewardByBallPosition) /
+    RecordEpisodeStatistics as recorded from the reference's own wrapper classes."""
+    group = next(g for g in golden_wrappers["groups"] if g["name"] == name)
+    assert group["oracle_checked"]
+    bad = replay_group(group, OracleStepper)
+    assert not bad, bad[:5]

@@ -29,3 +29,18 @@ def test_oracle_matches_live_reference(cfg, mode):
     for seed in (11, 12, 13):
         out = run_session((cfg, mode, seed, seed, 2, 20000))
         assert out["calls"] > 100
+
+
+@pytest.mark.parametrize("cfg,mode", [
+    (dict(winning_score=2, serve="random", reward_by_ball_position=((0.5, 0, -0.5, 0.25, 0, 0.125, 0, -1), 216, 176),
+          reward_in_normal_state=0.25, normalize_observation=True, record_episode_statistics=True), "synth"),
+    (dict(winning_score=2, serve="winner", is_player1_computer=True, reward_in_normal_state=-1, normal_state_first=True,
+          reward_by_ball_position=((1, 0, -1, 0, 0, 1, 0, -1), 216, 176), record_episode_statistics=True), "synth"),
+])
+def test_oracle_wrappers_match_live_reference(cfg, mode):
+    """the reference's NormalizeObservation / RewardInNormalState / RecordEpisodeStatistics classes, live"""
+    from oracle.make_golden import run_session
+
+    for seed in (21, 22):
+        out = run_session((cfg, mode, seed, seed, 2, 20000))
+        assert out["calls"] > 100 and all("returns" in e for e in out["episodes"])
