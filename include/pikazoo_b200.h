@@ -111,8 +111,8 @@ typedef struct pz_config {
 #define PZ_FLAG_NO_TABLES 1 /* computer players: always run the trajectory simulations iteratively
                                instead of reading the memoised landing tables (results are identical) */
 
-#define PZ_FLAG_NO_L2_HINTS 2 /* do not ask L2 to keep the env state resident across launches / to evict the
-                                 outputs first; for A/B measurements */
+#define PZ_FLAG_NO_L2_HINTS 2 /* do not mark the output stores evict-first in L2; for A/B
+                                 measurements */
 
 int pz_version(void);
 int pz_state_words(void);

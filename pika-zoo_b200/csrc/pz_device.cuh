@@ -246,6 +246,11 @@ __device__ __forceinline__ bool episode_truncated(const KParams &P, const Env &e
 }
 
 // ---- per-step kernel ---------------------------------------------------------------------------
+// One thread per env, one tile of 128 envs per CTA, six CTAs resident per SM (shared-memory staging and
+// 80 registers both allow exactly six). Measured alternatives that lost (B200, 1,048,576 envs, DESIGN.md
+// §4): 2 or 4 software-prefetched tiles per CTA (73 / 75 us against 62 us: the extra live registers or
+// spills cost more than the hidden latency gains; the hardware's CTA turnover already overlaps loads
+// with the other CTAs' arithmetic), and an evict-last L2 policy on the state words (+2 us).
 template <int AI_MASK, int OBS_DT>
 __global__ void __launch_bounds__(kThreads) pz_step_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(128) int stage[kWarps][32 * kObsRow];
@@ -325,8 +330,8 @@ __global__ void __launch_bounds__(kThreads) pz_step_kernel(const __grid_constant
     if (pending) bulk_store_wait_read();
 }
 
-// Launches pz_step_kernel<AI_MASK, P.obs_dtype>; defined (explicitly instantiated) in pz_step_ai*.cu.
+// Launches pz_step_kernel<AI_MASK, P.obs_dtype> over n envs; defined in pz_step_ai*.cu.
 template <int AI_MASK>
-void launch_step_kernel(unsigned grid, cudaStream_t st, const KParams &P);
+void launch_step_kernel(int64_t n_envs, cudaStream_t st, const KParams &P);
 
 }  // namespace pz

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -308,9 +309,11 @@ static void fill_params(KParams &P, int32_t *state, int64_t n, const pz_config *
     P.obs_dtype = c->obs_dtype;
     P.normalize = c->normalize_observation != 0;
     P.max_frames = c->max_episode_frames;
-    const bool hints = !(c->flags & PZ_FLAG_NO_L2_HINTS);
-    P.state_policy = hints ? kL2EvictLast : kL2EvictNormal;
-    P.out_policy = hints ? kL2EvictFirst : kL2EvictNormal;
+    // outputs are written once and never read back by the simulator: evict them from L2 first
+    // (-1.7 us per 1 M-env launch). The state words keep the normal policy: evict-last on them, meant to
+    // hold them in the 126 MB L2 across launches, measured 2 us SLOWER.
+    P.state_policy = kL2EvictNormal;
+    P.out_policy = (c->flags & PZ_FLAG_NO_L2_HINTS) ? kL2EvictNormal : kL2EvictFirst;
     P.x_line = c->x_line;
     P.y_line = c->y_line;
     for (int agent = 0; agent < 2; agent++)
@@ -396,12 +399,11 @@ int launch_step(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const
         P.ep_length = ep->episode_length_dev;
         P.truncated = ep->truncated_dev;
     }
-    const unsigned grid = grid_for(end - begin);
     switch (am) {
-        case 0: launch_step_kernel<0>(grid, st, P); break;
-        case 1: launch_step_kernel<1>(grid, st, P); break;
-        case 2: launch_step_kernel<2>(grid, st, P); break;
-        default: launch_step_kernel<3>(grid, st, P); break;
+        case 0: launch_step_kernel<0>(end - begin, st, P); break;
+        case 1: launch_step_kernel<1>(end - begin, st, P); break;
+        case 2: launch_step_kernel<2>(end - begin, st, P); break;
+        default: launch_step_kernel<3>(end - begin, st, P); break;
     }
     return launch_status();
 }

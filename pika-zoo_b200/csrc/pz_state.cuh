@@ -57,10 +57,9 @@ struct Rng {
 //   G1 = {B0, B1, B2, ENV}
 //   G2 = PCG64 state (little-endian 32-bit words), G3 = PCG64 inc, U = uinteger
 // L2 eviction policies (the 64-bit operand of `.L2::cache_hint`; values of createpolicy.fractional
-// with fraction 1.0). The env state is re-read by the next launch and is small next to the 126 MB L2
-// (32 MB per million envs without computer players, 71 MB with), while observations / rewards / dones
-// are written once and never read back by the simulator: state accesses ask to be evicted last, output
-// stores first, so the state lives in L2 across launches and never travels to HBM and back.
+// with fraction 1.0). Observations / rewards / dones are written once and never read back by the
+// simulator, so their stores ask to be evicted first; state accesses use the normal policy (see
+// fill_params in pz_kernels.cu for the measurements behind both choices).
 constexpr uint64_t kL2EvictNormal = 0x1000000000000000ULL;
 constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ULL;
 constexpr uint64_t kL2EvictLast = 0x14F0000000000000ULL;
@@ -71,7 +70,7 @@ struct StatePtrs {
     uint64_t policy;  // L2 cache policy of every state access
 };
 
-__host__ __device__ inline StatePtrs state_ptrs(int32_t *base, int64_t n, uint64_t policy = kL2EvictLast) {
+__host__ __device__ inline StatePtrs state_ptrs(int32_t *base, int64_t n, uint64_t policy = kL2EvictNormal) {
     StatePtrs s;
     s.policy = policy;
     s.g0 = reinterpret_cast<int4 *>(base);
