@@ -415,7 +415,7 @@ def run_b200_arm(args):
                              ALGO_BYTES_PER_ENV_STEP, "launch_ms_avg": launch_ms,
                          "launch_ms_p50_with_event_per_launch": per_launch_ms[len(per_launch_ms) // 2],
                          "peak_source": peak_src},
-            "e2e": e2e, "gpu_launches": K,  # pz_step_kernel launches inside the timed region "clocks": clocks.summary(), "episode_stats": stats_dict,
+            "e2e": e2e, "gpu_launches": K, "clocks": clocks.summary(), "episode_stats": stats_dict,
         }
         if e2e_compact:
             line["e2e_compact"] = e2e_compact
