@@ -375,6 +375,32 @@ def run_b200_arm(args):
         ring13 = [torch.randint(0, 13, (65536, 2), generator=gen, device=dev, dtype=torch.int32) for _ in range(4)]
         variants["configs[2]_65536_envs_fused_wrappers"] = time_steps(v, ring13, steps=1000, warm=50)
         del v, ring13
+        # configs[4]: 2 M envs per GPU, serve='random', winning_score=5, both agents' actions sampled on the
+        # device by a torch MLP (bf16 GEMMs + Gumbel-max) from the kernel's normalised bf16 observations
+        from pikazoo_b200.policy import MLPPolicy, policy_rollout
+
+        n5 = 1 << 21
+        v = pikazoo_b200.PikaVecEnv(n5, device=dev, seed=5, first_env=rank * n5, winning_score=5, serve="random",
+                                    obs_dtype=torch.bfloat16, normalize_observation=True, action_dtype=torch.int64)
+        pol = MLPPolicy(device=dev)
+        v.reset()
+        policy_rollout(v, pol.act, 10)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        policy_rollout(v, pol.act, 50)
+        b.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        acts = pol.act(v.obs)
+        env_only = time_steps(v, [acts], steps=50, warm=5)
+        variants["configs[4]_mlp_policy_loop_2M_envs_per_gpu"] = {
+            "ms_per_step": float(tt.item()) / 50, "env_steps_per_sec": n5 * world * 50 / (float(tt.item()) * 1e-3),
+            "of_which_env_step_us": env_only["us_per_launch"],
+            "note": "the policy is ordinary PyTorch (cuBLAS + elementwise kernels), not the product"}
+        del v, pol, acts
 
     # ---- config 4: K = 64 register-resident rollout, computer vs computer (not HBM-bound) ----
     rollout = None

@@ -38,6 +38,7 @@ def main():
     policy = MLPPolicy(device=dev)
     env.reset()
     policy_rollout(env, policy.act, 10)
+    pikazoo_b200.allreduce_stats(env.stats.clone())  # NCCL communicator set-up happens on the first collective
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     done_steps = 0
