@@ -352,12 +352,15 @@ def run_b200_arm(args):
     if not args.no_variants:
         variants = {}
         first, _ = pikazoo_b200.shard_range(total, world, rank)
-        v = pikazoo_b200.PikaVecEnv(n, device=dev, seed=11, first_env=first, obs_dtype=torch.float16,
-                                    normalize_observation=True, action_dtype=torch.uint8, **ENV_KW)
-        v.reset()
         ring_u8 = [r.to(torch.uint8) for r in ring[:4]]
-        variants["f16_normalised_obs_u8_actions"] = dict(time_steps(v, ring_u8), bytes_per_env_step=2 + 140 + 8 + 1 + 64)
-        del v
+        for layout in ("env_major", "feature_major"):
+            v = pikazoo_b200.PikaVecEnv(n, device=dev, seed=11, first_env=first, obs_dtype=torch.float16,
+                                        normalize_observation=True, action_dtype=torch.uint8, obs_layout=layout,
+                                        **ENV_KW)
+            v.reset()
+            variants["f16_normalised_obs_u8_actions" + ("_feature_major" if layout == "feature_major" else "")] = dict(
+                time_steps(v, ring_u8), bytes_per_env_step=2 + 140 + 8 + 1 + 64)
+            del v
         v = pikazoo_b200.PikaVecEnv(n, device=dev, seed=12, first_env=first, is_player1_computer=True,
                                     is_player2_computer=True, **ENV_KW)
         v.reset()
@@ -381,7 +384,8 @@ def run_b200_arm(args):
 
         n5 = 1 << 21
         v = pikazoo_b200.PikaVecEnv(n5, device=dev, seed=5, first_env=rank * n5, winning_score=5, serve="random",
-                                    obs_dtype=torch.bfloat16, normalize_observation=True, action_dtype=torch.int64)
+                                    obs_dtype=torch.bfloat16, normalize_observation=True, action_dtype=torch.int64,
+                                    obs_layout="feature_major", obs_feature_rows=40)
         pol = MLPPolicy(device=dev)
         v.reset()
         policy_rollout(v, pol.act, 10)

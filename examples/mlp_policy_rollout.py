@@ -34,7 +34,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     env = pikazoo_b200.make_sharded_env(a.envs_per_gpu * world, rank, world, dev, seed=5, winning_score=5,
                                         serve="random", obs_dtype=torch.bfloat16, normalize_observation=True,
-                                        action_dtype=torch.int64)
+                                        action_dtype=torch.int64, obs_layout="feature_major", obs_feature_rows=40)
     policy = MLPPolicy(device=dev)
     env.reset()
     policy_rollout(env, policy.act, 10)

@@ -56,6 +56,15 @@ enum { PZ_REW_F32 = 0, PZ_REW_F64 = 1 };
  * wrapper itself produces (numpy true division of int64 arrays); F32 = float32(F64 value) exactly;
  * F16 / BF16 = round-to-nearest-even of the F32 value. */
 enum { PZ_OBS_I32 = 0, PZ_OBS_I16 = 1, PZ_OBS_F32 = 2, PZ_OBS_F16 = 3, PZ_OBS_BF16 = 4, PZ_OBS_F64 = 5 };
+/* memory layout of obs_dev.
+ *   ENV_MAJOR     [n][2][35]: one row per env and agent, the reference's layout (obs[i][a] = env i's
+ *                 observation for player a+1);
+ *   FEATURE_MAJOR [2][obs_feature_rows][n]: element k of agent a's observation of env i at
+ *                 ((a * obs_feature_rows) + k) * n + i — the layout a device-side policy wants (every
+ *                 feature a contiguous vector over envs: GEMM operands with leading dimension n, no
+ *                 transposing pass). Rows >= 35 (padding up to a multiple of 8 for tensor-core GEMMs) are
+ *                 never written; zero them once. Device pointers only (not pz_host_*). */
+enum { PZ_LAYOUT_ENV_MAJOR = 0, PZ_LAYOUT_FEATURE_MAJOR = 1 };
 /* RewardInNormalState composition order relative to RewardByBallPosition */
 enum { PZ_RINS_OFF = 0, PZ_RINS_OUTER = 1 /* RewardInNormalState(RewardByBallPosition(env)) */,
        PZ_RINS_INNER = 2 /* RewardByBallPosition(RewardInNormalState(env)) */ };
@@ -105,6 +114,8 @@ typedef struct pz_config {
                                         reaches this many step() calls without terminating is truncated: it
                                         reports truncated = 1 on that call and is reset (or frozen) by the next */
     double normal_state_reward;      /* RewardInNormalState(env, reward) */
+    int32_t obs_layout;              /* PZ_LAYOUT_* */
+    int32_t obs_feature_rows;        /* FEATURE_MAJOR: rows per agent, >= 35 (0 means 35) */
 } pz_config;
 
 /* pz_config.flags */

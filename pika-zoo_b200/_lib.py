@@ -21,6 +21,7 @@ ACT_I32, ACT_I64, ACT_U8 = 0, 1, 2
 REW_F32, REW_F64 = 0, 1
 OBS_I32, OBS_I16, OBS_F32, OBS_F16, OBS_BF16, OBS_F64 = 0, 1, 2, 3, 4, 5
 RINS_OFF, RINS_OUTER, RINS_INNER = 0, 1, 2
+LAYOUT_ENV_MAJOR, LAYOUT_FEATURE_MAJOR = 0, 1
 ACTIONS_NOOP, ACTIONS_SYNTH = 0, 1
 FLAG_NO_TABLES = 1
 FLAG_NO_L2_HINTS = 2
@@ -54,6 +55,8 @@ class PzConfig(ctypes.Structure):
         ("reward_in_normal_state", ctypes.c_int32),
         ("max_episode_frames", ctypes.c_int32),
         ("normal_state_reward", ctypes.c_double),
+        ("obs_layout", ctypes.c_int32),
+        ("obs_feature_rows", ctypes.c_int32),
     ]
 
 

@@ -42,6 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
              "-I", INCLUDE]
+    flags += os.environ.get("PZ_NVCC_FLAGS", "").split()  # e.g. -DPZ_ROLLOUT_MIN_CTAS=4 for tuning runs
     if verbose:
         flags += ["-Xptxas", "-v"]
     objdir = os.path.join(CSRC, "build")

@@ -34,6 +34,7 @@ struct KParams {
     uint8_t *truncated;   // may be null
     StepCfg cfg;
     int autoreset, simplify, shaped, act_dtype, rew_dtype, obs_dtype, normalize;
+    int obs_layout, obs_rows;  // PZ_LAYOUT_*; FEATURE_MAJOR: rows per agent (leading dimension = n)
     int max_frames;       // 0: never truncate
     uint64_t state_policy, out_policy;  // L2 cache policies (pz_state.cuh), kL2EvictNormal when hints are off
     int x_line, y_line;
@@ -55,17 +56,17 @@ __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)
 template <int DT>
 struct ObsType;
 template <>
-struct ObsType<PZ_OBS_I32> { static constexpr int bytes = 4; };
+struct ObsType<PZ_OBS_I32> { static constexpr int bytes = 4; using elem = int; };
 template <>
-struct ObsType<PZ_OBS_I16> { static constexpr int bytes = 2; };
+struct ObsType<PZ_OBS_I16> { static constexpr int bytes = 2; using elem = short; };
 template <>
-struct ObsType<PZ_OBS_F32> { static constexpr int bytes = 4; };
+struct ObsType<PZ_OBS_F32> { static constexpr int bytes = 4; using elem = float; };
 template <>
-struct ObsType<PZ_OBS_F16> { static constexpr int bytes = 2; };
+struct ObsType<PZ_OBS_F16> { static constexpr int bytes = 2; using elem = unsigned short; };
 template <>
-struct ObsType<PZ_OBS_BF16> { static constexpr int bytes = 2; };
+struct ObsType<PZ_OBS_BF16> { static constexpr int bytes = 2; using elem = unsigned short; };
 template <>
-struct ObsType<PZ_OBS_F64> { static constexpr int bytes = 8; };
+struct ObsType<PZ_OBS_F64> { static constexpr int bytes = 8; using elem = double; };
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
@@ -143,6 +144,54 @@ __device__ __forceinline__ bool emit_obs_as(const Env &e, bool valid, bool norma
         write_obs_row<DT>(e, normalize, g + env_idx * row_bytes);
     }
     return false;
+}
+
+// FEATURE_MAJOR: obs[((a * rows) + k) * ld + i]. Consecutive lanes hold consecutive envs, so every one of
+// the 70 stores of a warp is one contiguous 64 / 128 / 256-byte segment: no staging, no shared memory.
+// Streaming stores (st.global.cs): written once, read by the policy, never by the simulator.
+template <int DT>
+__device__ __forceinline__ void emit_obs_feature_major(const Env &e, bool valid, bool normalize, void *obs,
+                                                       int64_t env_idx, int64_t ld, int rows) {
+    if (!valid) return;
+    using T = typename ObsType<DT>::elem;
+    int u[35];
+    obs_values(e, u);
+    T *p0 = reinterpret_cast<T *>(obs) + env_idx;  // two running pointers instead of 70 hoisted addresses
+    T *p1 = p0 + (int64_t)rows * ld;
+    // agent 0's row k is value k; agent 1's rows are [opponent block | own block | ball block]
+    auto emit = [&](auto K) {
+        constexpr int k = decltype(K)::value;
+        T v;
+        if (DT == PZ_OBS_I32 || DT == PZ_OBS_I16) {
+            v = (T)u[k];
+        } else if (DT == PZ_OBS_F64) {
+            v = (T)obs_float<double, k>(u, normalize);
+        } else {
+            const float f = obs_float<float, k>(u, normalize);
+            if (DT == PZ_OBS_F32)
+                v = (T)f;
+            else
+                v = (T)(DT == PZ_OBS_F16 ? __half_as_ushort(__float2half_rn(f))
+                                         : __bfloat16_as_ushort(__float2bfloat16_rn(f)));
+        }
+        constexpr int k1 = k < 13 ? k + 13 : (k < 26 ? k - 13 : k);  // row of value k in agent 1's observation
+        __stcs(p0 + (int64_t)k * ld, v);
+        __stcs(p1 + (int64_t)k1 * ld, v);
+    };
+    [&]<int... K>(std::integer_sequence<int, K...>) { (emit(std::integral_constant<int, K>{}), ...); }
+    (std::make_integer_sequence<int, 35>{});
+}
+
+__device__ __forceinline__ void emit_obs_feature_major(const Env &e, bool valid, int obs_dtype, bool normalize,
+                                                       void *obs, int64_t env_idx, int64_t ld, int rows) {
+    switch (obs_dtype) {  // launch-uniform
+        case PZ_OBS_I32: emit_obs_feature_major<PZ_OBS_I32>(e, valid, normalize, obs, env_idx, ld, rows); break;
+        case PZ_OBS_I16: emit_obs_feature_major<PZ_OBS_I16>(e, valid, normalize, obs, env_idx, ld, rows); break;
+        case PZ_OBS_F32: emit_obs_feature_major<PZ_OBS_F32>(e, valid, normalize, obs, env_idx, ld, rows); break;
+        case PZ_OBS_F16: emit_obs_feature_major<PZ_OBS_F16>(e, valid, normalize, obs, env_idx, ld, rows); break;
+        case PZ_OBS_BF16: emit_obs_feature_major<PZ_OBS_BF16>(e, valid, normalize, obs, env_idx, ld, rows); break;
+        default: emit_obs_feature_major<PZ_OBS_F64>(e, valid, normalize, obs, env_idx, ld, rows); break;
+    }
 }
 
 __device__ __forceinline__ bool emit_obs(const Env &e, bool valid, int obs_dtype, bool normalize, void *obs,
@@ -251,9 +300,13 @@ __device__ __forceinline__ bool episode_truncated(const KParams &P, const Env &e
 // §4): 2 or 4 software-prefetched tiles per CTA (73 / 75 us against 62 us: the extra live registers or
 // spills cost more than the hidden latency gains; the hardware's CTA turnover already overlaps loads
 // with the other CTAs' arithmetic), and an evict-last L2 policy on the state words (+2 us).
-template <int AI_MASK, int OBS_DT>
+constexpr int kAiScratchInts = 320;  // computer_decide: 32 x int4 inputs + 32 x 6 results per warp
+
+template <int AI_MASK, int OBS_DT, int LAYOUT>
 __global__ void __launch_bounds__(kThreads) pz_step_kernel(const __grid_constant__ KParams P) {
-    __shared__ __align__(128) int stage[kWarps][32 * kObsRow];
+    // ENV_MAJOR stages the observation rows here; FEATURE_MAJOR only needs the computer players' scratch
+    constexpr int kStageInts = LAYOUT == PZ_LAYOUT_ENV_MAJOR ? 32 * kObsRow : (AI_MASK != 0 ? kAiScratchInts : 4);
+    __shared__ __align__(128) int stage[kWarps][kStageInts];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t i = P.begin + (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const bool valid = i < P.end;
@@ -299,7 +352,12 @@ __global__ void __launch_bounds__(kThreads) pz_step_kernel(const __grid_constant
 
     __syncwarp();  // the staging buffer doubled as the computer players' scratch
     bool pending = false;
-    if (P.obs) pending = emit_obs_as<OBS_DT>(e, valid, P.normalize, P.obs, i, P.end, stage[warp], lane, P.out_policy);
+    if (P.obs) {
+        if (LAYOUT == PZ_LAYOUT_ENV_MAJOR)
+            pending = emit_obs_as<OBS_DT>(e, valid, P.normalize, P.obs, i, P.end, stage[warp], lane, P.out_policy);
+        else
+            emit_obs_feature_major<OBS_DT>(e, valid, P.normalize, P.obs, i, P.n, P.obs_rows);
+    }
     const bool truncated = valid && episode_truncated(P, e);  // this call's step reached the cap, or frozen there
     if (valid) {
         if (run || do_reset) {
@@ -330,7 +388,7 @@ __global__ void __launch_bounds__(kThreads) pz_step_kernel(const __grid_constant
     if (pending) bulk_store_wait_read();
 }
 
-// Launches pz_step_kernel<AI_MASK, P.obs_dtype> over n envs; defined in pz_step_ai*.cu.
+// Launches pz_step_kernel<AI_MASK, P.obs_dtype, P.obs_layout> over n envs; defined in pz_step_ai*.cu.
 template <int AI_MASK>
 void launch_step_kernel(int64_t n_envs, cudaStream_t st, const KParams &P);
 

@@ -53,7 +53,7 @@ int pz_host_create(pz_host_ctx **out, int64_t n, const pz_config *cfg, uint64_t 
     c->cfg = *cfg;
     c->act_elem = cfg->action_dtype == PZ_ACT_I64 ? 8 : (cfg->action_dtype == PZ_ACT_U8 ? 1 : 4);
     c->rew_elem = cfg->reward_dtype == PZ_REW_F64 ? 8 : 4;
-    if (pz_obs_elem_bytes(cfg->obs_dtype) == 0) {
+    if (pz_obs_elem_bytes(cfg->obs_dtype) == 0 || cfg->obs_layout != PZ_LAYOUT_ENV_MAJOR) {  // host rows are env-major
         delete c;
         return PZ_E_BADCONFIG;
     }

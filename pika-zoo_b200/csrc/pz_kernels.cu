@@ -16,6 +16,10 @@
 #include "pz_device.cuh"
 #include "pz_kernels.cuh"
 
+#ifndef PZ_ROLLOUT_MIN_CTAS
+#define PZ_ROLLOUT_MIN_CTAS 6  // 80 registers (a few bytes of spill): 2.63 ms per 64 frames x 1 M envs against 2.74 ms at 4 or 5
+#endif
+
 namespace pz {
 
 // Observation rows from non-inlined code, for the kernels that emit them once per launch (reset,
@@ -24,7 +28,7 @@ namespace pz {
 // scalars crosses the call.
 __device__ __noinline__ bool emit_obs_cold(int32_t *state, int64_t n, int64_t env_idx, int64_t end, int obs_dtype,
                                            bool normalize, void *obs, int *warp_stage, uint64_t state_policy,
-                                           uint64_t out_policy) {
+                                           uint64_t out_policy, int layout, int rows) {
     const int lane = threadIdx.x & 31;
     const bool valid = env_idx < end;
     Env e;
@@ -32,12 +36,16 @@ __device__ __noinline__ bool emit_obs_cold(int32_t *state, int64_t n, int64_t en
         load_env(e, state_ptrs(state, n, state_policy), env_idx);
     else
         fresh_env(e);
+    if (layout == PZ_LAYOUT_FEATURE_MAJOR) {
+        emit_obs_feature_major(e, valid, obs_dtype, normalize, obs, env_idx, n, rows);
+        return false;
+    }
     return emit_obs(e, valid, obs_dtype, normalize, obs, env_idx, end, warp_stage, lane, out_policy);
 }
 
 // ---- K-frame register-resident rollout -------------------------------------------------------
 template <int AI_MASK>
-__global__ void __launch_bounds__(kThreads) pz_rollout_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(kThreads, PZ_ROLLOUT_MIN_CTAS) pz_rollout_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(128) int stage[kWarps][32 * kObsRow];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t i = P.begin + (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(kThreads) pz_rollout_kernel(const __grid_const
     }
     bool pending = false;
     if (P.obs) pending = emit_obs_cold(P.state, P.n, i, P.end, P.obs_dtype, P.normalize, P.obs, stage[warp], P.state_policy,
-                                       P.out_policy);
+                                       P.out_policy, P.obs_layout, P.obs_rows);
     if (P.stats) {
         const unsigned ep = __reduce_add_sync(kFullMask, st_ep);
         const unsigned rs = __reduce_add_sync(kFullMask, st_resets);
@@ -151,7 +159,7 @@ __global__ void __launch_bounds__(kThreads) pz_reset_kernel(const __grid_constan
     }
     bool pending = false;
     if (P.obs) pending = emit_obs_cold(P.state, P.n, i, P.end, P.obs_dtype, P.normalize, P.obs, stage[warp], P.state_policy,
-                                       P.out_policy);
+                                       P.out_policy, P.obs_layout, P.obs_rows);
     if (valid && P.ep_return) P.ep_return[i] = make_double2(0.0, 0.0);
     if (valid && P.ep_length) P.ep_length[i] = 0;
     if (pending) bulk_store_wait_read();
@@ -290,6 +298,9 @@ static int check_config(const pz_config *c) {
     if (c->normalize_observation && (c->obs_dtype == PZ_OBS_I32 || c->obs_dtype == PZ_OBS_I16)) return PZ_E_BADCONFIG;
     if (c->reward_in_normal_state < PZ_RINS_OFF || c->reward_in_normal_state > PZ_RINS_INNER) return PZ_E_BADCONFIG;
     if (c->max_episode_frames < 0) return PZ_E_BADCONFIG;
+    if (c->obs_layout != PZ_LAYOUT_ENV_MAJOR && c->obs_layout != PZ_LAYOUT_FEATURE_MAJOR) return PZ_E_BADCONFIG;
+    if (c->obs_layout == PZ_LAYOUT_FEATURE_MAJOR && c->obs_feature_rows != 0 && c->obs_feature_rows < PZ_OBS_WORDS)
+        return PZ_E_BADCONFIG;
     return 0;
 }
 
@@ -309,6 +320,8 @@ static void fill_params(KParams &P, int32_t *state, int64_t n, const pz_config *
     P.obs_dtype = c->obs_dtype;
     P.normalize = c->normalize_observation != 0;
     P.max_frames = c->max_episode_frames;
+    P.obs_layout = c->obs_layout;
+    P.obs_rows = c->obs_feature_rows > 0 ? c->obs_feature_rows : PZ_OBS_WORDS;
     // outputs are written once and never read back by the simulator: evict them from L2 first
     // (-1.7 us per 1 M-env launch). The state words keep the normal policy: evict-last on them, meant to
     // hold them in the 126 MB L2 across launches, measured 2 us SLOWER.

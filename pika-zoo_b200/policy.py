@@ -15,31 +15,67 @@ from .vec_env import PikaVecEnv
 
 
 class MLPPolicy(nn.Module):
-    """obs [*, 35] -> logits [*, n_actions]; one set of weights per agent (self-play shares none)."""
+    """obs -> logits [N, 2, n_actions]; one set of weights per agent, both agents in one batched GEMM.
+    Everything runs feature-major ([agent, feature, N], N contiguous), which is how the simulator can emit
+    its observations (obs_layout="feature_major", obs_feature_rows=40): the [2, 40, N] tensor is the GEMM
+    operand as it is. Biases ride in the GEMMs: padding row 35 of the observations is set to 1 once (the
+    simulator never writes rows >= 35), W1 carries b1 in that column and an extra output row that
+    reproduces the 1 for the second layer, W2 carries b2 there. Sampling reduces over the short dimension
+    with N contiguous — the env-major form (argmax over a last dimension of 18) is several times slower
+    in eager PyTorch."""
+
+    K_PAD = 40
+    ONES_ROW = 35
 
     def __init__(self, n_actions: int = 18, hidden: int = 64, dtype: torch.dtype = torch.bfloat16, device="cuda",
                  seed: int = 0):
         super().__init__()
         g = torch.Generator(device="cpu").manual_seed(seed)
-        self.n_actions = n_actions
-        # [agent, in, out] so both agents run as one batched matmul
-        self.w1 = nn.Parameter((torch.randn(2, 35, hidden, generator=g) / 35 ** 0.5).to(device=device, dtype=dtype))
-        self.b1 = nn.Parameter(torch.zeros(2, 1, hidden, device=device, dtype=dtype))
-        self.w2 = nn.Parameter((torch.randn(2, hidden, n_actions, generator=g) / hidden ** 0.5).to(device=device, dtype=dtype))
-        self.b2 = nn.Parameter(torch.zeros(2, 1, n_actions, device=device, dtype=dtype))
+        self.n_actions, self.hidden = n_actions, hidden
+        w1 = torch.zeros(2, hidden + 8, self.K_PAD)
+        w1[:, :hidden, :35] = torch.randn(2, hidden, 35, generator=g) / 35 ** 0.5
+        w1[:, :hidden, self.ONES_ROW] = 0.0          # b1
+        w1[:, hidden, self.ONES_ROW] = 1.0           # hidden row `hidden` = relu(1) = 1 for the next bias
+        w2 = torch.zeros(2, n_actions, hidden + 8)
+        w2[:, :, :hidden] = torch.randn(2, n_actions, hidden, generator=g) / hidden ** 0.5
+        w2[:, :, hidden] = 0.0                       # b2
+        # [agent, out, in]: logits^T = W2 relu(W1 x^T)
+        self.w1 = nn.Parameter(w1.to(device=device, dtype=dtype))
+        self.w2 = nn.Parameter(w2.to(device=device, dtype=dtype))
+        self._xt = None
+        self._primed = None
+
+    def _operand(self, obs: torch.Tensor) -> torch.Tensor:
+        if obs.dim() == 3 and obs.shape[0] == 2 and obs.shape[1] == self.K_PAD and obs.dtype == self.w1.dtype:
+            if self._primed is not obs:  # first sight of this buffer: the ones row
+                obs[:, self.ONES_ROW, :] = 1
+                self._primed = obs
+            return obs
+        # env-major [N, 2, 35]: transpose here (a slow pass in eager PyTorch)
+        n = obs.shape[0]
+        if self._xt is None or self._xt.shape[2] != n or self._xt.device != obs.device:
+            self._xt = torch.zeros(2, self.K_PAD, n, dtype=self.w1.dtype, device=obs.device)
+            self._xt[:, self.ONES_ROW, :] = 1
+        self._xt[:, :35].copy_(obs.permute(1, 2, 0))
+        return self._xt
+
+    def logits_t(self, obs: torch.Tensor) -> torch.Tensor:
+        """[2, n_actions, N] (agent- and action-major)."""
+        h = torch.bmm(self.w1, self._operand(obs)).relu_()   # [2, hidden + 8, N]
+        return torch.bmm(self.w2, h)                         # [2, n_actions, N]
 
     def forward(self, obs: torch.Tensor) -> torch.Tensor:
-        """obs [N, 2, 35] (any float dtype) -> logits [N, 2, n_actions]."""
-        x = obs.to(self.w1.dtype).transpose(0, 1)                 # [2, N, 35]
-        h = torch.relu(torch.baddbmm(self.b1, x, self.w1))        # [2, N, hidden]
-        return torch.baddbmm(self.b2, h, self.w2).transpose(0, 1)  # [N, 2, n_actions]
+        """logits [N, 2, n_actions]."""
+        return self.logits_t(obs).permute(2, 0, 1)
 
     @torch.no_grad()
     def act(self, obs: torch.Tensor, generator: Optional[torch.Generator] = None) -> torch.Tensor:
-        """Categorical sample by Gumbel-max: int64 actions [N, 2]."""
-        logits = self.forward(obs).float()
-        u = torch.rand(logits.shape, device=logits.device, generator=generator).clamp_(min=1e-20)
-        return (logits - torch.log(-torch.log(u))).argmax(dim=-1)
+        """Categorical sample, int64 actions [N, 2], by the exponential race torch.multinomial itself uses:
+        argmax_a exp(logit_a - max) / E_a with E_a ~ Exp(1)."""
+        z = self.logits_t(obs).float()
+        z = (z - z.amax(dim=1, keepdim=True)).exp_()
+        z.div_(torch.empty_like(z).exponential_(1.0, generator=generator))
+        return z.argmax(dim=1).t().contiguous()
 
 
 @torch.no_grad()

@@ -50,6 +50,8 @@ def make_config(
     normal_state_first: bool = False,
     max_episode_frames: int = 0,
     l2_hints: bool = True,
+    obs_layout: str = "env_major",
+    obs_feature_rows: int = 35,
 ) -> _lib.PzConfig:
     assert serve in ("winner", "alternate", "random")  # pikazoo_env.py:104
     if not 1 <= int(winning_score) <= 1023:
@@ -85,6 +87,12 @@ def make_config(
     if int(max_episode_frames) < 0:
         raise ValueError("max_episode_frames must be >= 0 (0 = never truncate)")
     c.max_episode_frames = int(max_episode_frames)
+    if obs_layout not in ("env_major", "feature_major"):
+        raise ValueError("obs_layout must be 'env_major' or 'feature_major'")
+    c.obs_layout = _lib.LAYOUT_FEATURE_MAJOR if obs_layout == "feature_major" else _lib.LAYOUT_ENV_MAJOR
+    if int(obs_feature_rows) < _lib.OBS_WORDS:
+        raise ValueError("obs_feature_rows must be >= 35")
+    c.obs_feature_rows = int(obs_feature_rows)
     return c
 
 
@@ -119,9 +127,16 @@ class PikaVecEnv:
         max_episode_frames: int = 0,
         record_episode_statistics: bool = False,
         l2_hints: bool = True,
+        obs_layout: str = "env_major",
+        obs_feature_rows: int = 35,
     ):
         """Beyond the reference's constructor arguments:
 
+        obs_layout: "env_major" — obs [N, 2, 35], one row per env and agent like the reference — or
+          "feature_major" — obs [2, obs_feature_rows, N]: every feature a contiguous vector over envs, the
+          layout a device-side policy consumes without a transposing pass (GEMM operand with leading
+          dimension N). Rows 35.. of each agent (obs_feature_rows=40 pads K to a multiple of 8 for
+          tensor-core GEMMs) stay zero.
         obs_dtype: torch.int32 (the reference's declared dtype), int16 (same integers, half the bytes),
           or float32 / float16 / bfloat16 / float64 — `(float)value`, or with normalize_observation=True
           the NormalizeObservation wrapper's output (normalize_observation.py:18-32) computed in the
@@ -158,7 +173,8 @@ class PikaVecEnv:
             action_dtype=action_dtype, reward_dtype=reward_dtype, landing_tables=self.landing_tables,
             obs_dtype=obs_dtype, normalize_observation=normalize_observation,
             reward_in_normal_state=reward_in_normal_state, normal_state_first=normal_state_first,
-            max_episode_frames=max_episode_frames, l2_hints=l2_hints,
+            max_episode_frames=max_episode_frames, l2_hints=l2_hints, obs_layout=obs_layout,
+            obs_feature_rows=obs_feature_rows,
         )
         self.cfg = make_config(**self._kw)
         self.action_dtype = action_dtype
@@ -170,7 +186,11 @@ class PikaVecEnv:
         n = self.num_envs
         with torch.cuda.device(self.device):
             self.state = torch.zeros(_lib.STATE_WORDS * n, dtype=torch.int32, device=self.device)
-            self.obs = torch.zeros((n, 2, _lib.OBS_WORDS), dtype=obs_dtype, device=self.device)
+            self.obs_layout = obs_layout
+            if obs_layout == "feature_major":
+                self.obs = torch.zeros((2, int(obs_feature_rows), n), dtype=obs_dtype, device=self.device)
+            else:
+                self.obs = torch.zeros((n, 2, _lib.OBS_WORDS), dtype=obs_dtype, device=self.device)
             self.reward = torch.zeros((n, 2), dtype=reward_dtype, device=self.device)
             self.done_u8 = torch.zeros((n,), dtype=torch.uint8, device=self.device)
             self.stats = torch.zeros(_lib.NUM_STATS, dtype=torch.int64, device=self.device) if track_stats else None

@@ -57,6 +57,8 @@ def test_argument_validation_without_gpu(cuda_lib):
     assert cuda_lib.pz_step_ex(ctypes.c_void_p(16), 4, ctypes.byref(cfg), ctypes.c_void_p(16), None, None, None, None,
                                None, None) == -2
     assert [cuda_lib.pz_obs_elem_bytes(k) for k in range(7)] == [4, 2, 4, 2, 2, 8, 0]
+    cfg.normalize_observation, cfg.obs_layout, cfg.obs_feature_rows = 0, 1, 20  # fewer rows than an observation
+    assert cuda_lib.pz_reset(ctypes.c_void_p(16), 4, ctypes.byref(cfg), None, None) == -2
 
 
 def test_product_does_not_import_oracle():
@@ -76,5 +78,5 @@ def test_config_struct_layout_matches_header(cuda_lib):
     c = PzConfig()
     cuda_lib.pz_default_config(ctypes.byref(c))
     assert (c.winning_score, c.serve, c.x_line, c.y_line, c.autoreset) == (15, 0, 216, 176, 1)
-    assert ctypes.sizeof(PzConfig) == 8 * 4 + 8 * 8 + 8 * 4 + 8 and PzConfig.flags.offset == 108
+    assert ctypes.sizeof(PzConfig) == 8 * 4 + 8 * 8 + 8 * 4 + 8 + 2 * 4 and PzConfig.flags.offset == 108
     assert PzConfig.normal_state_reward.offset == 128 and c.obs_dtype == 0 and c.max_episode_frames == 0

@@ -44,6 +44,34 @@ def test_mlp_policy_rollout_loop_matches_oracle(cuda_lib):
     assert seen["done"] > n // 2 and len(seen["distinct"]) == 18  # games finish; the policy uses every action
 
 
+def test_policy_consumes_feature_major_observations(cuda_lib):
+    """Same loop with obs_layout='feature_major' ([2, 40, N] bf16, the GEMM operand as it is): the policy
+    must produce the same logits from either layout, and the run must match the oracle."""
+    import pikazoo_b200
+    from pikazoo_b200.policy import MLPPolicy, policy_rollout
+
+    n, steps = 4096, 300
+    cfg = dict(winning_score=5, serve="random")
+    kw = dict(seed=16, obs_dtype=torch.bfloat16, normalize_observation=True, action_dtype=torch.int64, **cfg)
+    fm = pikazoo_b200.PikaVecEnv(n, obs_layout="feature_major", obs_feature_rows=40, **kw)
+    em = pikazoo_b200.PikaVecEnv(n, **kw)
+    orc = po.OracleVecEnv(n, seed=16, **cfg)
+    policy = MLPPolicy(device=fm.device, seed=3)
+    fm.reset(), em.reset(), orc.reset()
+    assert torch.equal(policy.logits_t(fm.obs), policy.logits_t(em.obs))
+    gen = torch.Generator(device=fm.device).manual_seed(7)
+
+    def mirror(t, actions, obs, reward, done):
+        orc.step(actions.cpu().numpy().astype(np.int32))
+        em.step(actions)
+        if t % 50 == 0 or t == steps - 1:
+            assert torch.equal(obs[:, :35, :], em.obs.permute(1, 2, 0))
+            assert np.array_equal(done.cpu().numpy(), orc.done.astype(bool))
+
+    policy_rollout(fm, lambda o: policy.act(o, gen), steps, on_step=mirror)
+    assert np.array_equal(fm.export_state().cpu().numpy(), orc.state)
+
+
 def test_step_loop_is_cuda_graph_capturable(cuda_lib):
     """The launch-bound small-batch regime (configs[1], 4,096 envs): K steps with on-device action
     sampling captured once in a CUDA graph and replayed must equal the same K steps issued eagerly."""

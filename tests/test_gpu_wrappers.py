@@ -103,6 +103,38 @@ def test_observation_dtypes(pz, dtype, normalize, n):
     assert np.array_equal(_bits(obs), _expected_bits(orc.current_obs(), np_dtype, normalize))
 
 
+@pytest.mark.parametrize("dtype,normalize", [(torch.int32, False), (torch.int16, False), (torch.float32, True),
+                                             (torch.bfloat16, True), (torch.float16, False), (torch.float64, True)])
+@pytest.mark.parametrize("n,cfg", [(4096, dict(winning_score=3, serve="random", is_player2_computer=True)),
+                                   (1000 + 7, dict(winning_score=2))])
+def test_feature_major_layout(pz, dtype, normalize, n, cfg):
+    """obs [2, rows, N]: the same values as the env-major rows, transposed; padding rows stay zero."""
+    rows = 40
+    env = pz.PikaVecEnv(n, seed=321, obs_dtype=dtype, normalize_observation=normalize, obs_layout="feature_major",
+                        obs_feature_rows=rows, **cfg)
+    orc = po.OracleVecEnv(n, seed=321, **cfg)
+    np_dtype = TORCH_TO_NP[dtype]
+
+    def check(obs, where):
+        assert tuple(obs.shape) == (2, rows, n) and obs.dtype == dtype
+        exp = _expected_bits(orc.current_obs(), np_dtype, normalize)          # [n, 2, 35]
+        got = _bits(obs)                                                      # [2, rows, n]
+        assert np.array_equal(got[:, :35, :], np.transpose(exp, (1, 2, 0))), where
+        assert not got[:, 35:, :].any(), where
+
+    check(env.reset(), "reset") if not orc.reset() is None else None
+    for t in range(300):
+        a = synth_actions_numpy(9, 0, n, t, 18)
+        obs, _, _ = env.step(torch.from_numpy(a).cuda())
+        orc.step(a)
+        if t % 13 == 0 or t == 299:
+            check(obs, t)
+    obs = env.rollout(16, actions="synth", action_seed=5, write_obs=True)
+    orc.rollout(16, action_mode=1, action_seed=5, first_env=0, frame0=300)
+    check(obs, "rollout")
+    assert np.array_equal(env.export_state().cpu().numpy(), orc.state)
+
+
 def test_normalize_needs_float_dtype(pz):
     with pytest.raises(TypeError):
         pz.PikaVecEnv(8, normalize_observation=True)
