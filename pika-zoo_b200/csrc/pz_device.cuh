@@ -302,10 +302,32 @@ __device__ __forceinline__ bool episode_truncated(const KParams &P, const Env &e
 // with the other CTAs' arithmetic), and an evict-last L2 policy on the state words (+2 us).
 constexpr int kAiScratchInts = 320;  // computer_decide: 32 x int4 inputs + 32 x 6 results per warp
 
+// Resident CTAs per SM the register allocation is held to (0 = leave it to ptxas). Without computer
+// players: 2-byte observation rows stage half as much shared memory, so six CTAs fit if the registers
+// do (80 instead of 96: 48 us against 53-60 us per million envs); feature-major rows use no shared memory
+// at all and run best at eight (64 registers). Measured sweeps in DESIGN.md §4.
+#ifndef PZ_FM_MIN_CTAS
+#define PZ_FM_MIN_CTAS 8
+#endif
+#ifndef PZ_HALF_MIN_CTAS
+#define PZ_HALF_MIN_CTAS 6
+#endif
 template <int AI_MASK, int OBS_DT, int LAYOUT>
-__global__ void __launch_bounds__(kThreads) pz_step_kernel(const __grid_constant__ KParams P) {
-    // ENV_MAJOR stages the observation rows here; FEATURE_MAJOR only needs the computer players' scratch
-    constexpr int kStageInts = LAYOUT == PZ_LAYOUT_ENV_MAJOR ? 32 * kObsRow : (AI_MASK != 0 ? kAiScratchInts : 4);
+constexpr int step_min_ctas() {
+    if (AI_MASK != 0) return 4;  // their natural 96-128 registers
+    if (LAYOUT == PZ_LAYOUT_FEATURE_MAJOR) return OBS_DT == PZ_OBS_F64 ? 4 : PZ_FM_MIN_CTAS;
+    return ObsType<OBS_DT>::bytes == 2 ? PZ_HALF_MIN_CTAS : (OBS_DT == PZ_OBS_F64 ? 4 : 6);
+}
+
+template <int AI_MASK, int OBS_DT, int LAYOUT>
+__global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOUT>())
+    pz_step_kernel(const __grid_constant__ KParams P) {
+    // ENV_MAJOR stages the observation rows here (2-byte elements need half the room); FEATURE_MAJOR only
+    // needs the computer players' scratch
+    constexpr int kRowInts = OBS_DT == PZ_OBS_F64 ? 0 : kObsRow * ObsType<OBS_DT>::bytes / 4;  // f64 rows are not staged
+    constexpr int kStageInts = LAYOUT == PZ_LAYOUT_ENV_MAJOR
+                                   ? (32 * kRowInts > kAiScratchInts ? 32 * kRowInts : kAiScratchInts)
+                                   : (AI_MASK != 0 ? kAiScratchInts : 4);
     __shared__ __align__(128) int stage[kWarps][kStageInts];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t i = P.begin + (int64_t)blockIdx.x * kThreads + threadIdx.x;
