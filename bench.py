@@ -444,6 +444,10 @@ def run_b200_arm(args):
                          "traffic": None, "kernel": "pz_step_kernel<0>", "algorithmic_bytes_per_env_step":
                              ALGO_BYTES_PER_ENV_STEP, "launch_ms_avg": launch_ms,
                          "launch_ms_p50_with_event_per_launch": per_launch_ms[len(per_launch_ms) // 2],
+                         "moved_bytes_per_env_step": 361,
+                         "achieved_moved_bytes": 361 * n / (launch_ms * 1e-3) / 1e9,
+                         "note": "frac can exceed 1: the 425 B algorithmic figure counts the 64 B of PCG64 words "
+                                 "every frame, the kernel touches them only on frames that draw and moves 361 B",
                          "peak_source": peak_src},
             "e2e": e2e, "gpu_launches": K, "clocks": clocks.summary(), "episode_stats": stats_dict,
         }
@@ -456,7 +460,10 @@ def run_b200_arm(args):
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_port_throughput(args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                    "sample": sample}
+                                    "sample": sample,
+                                    "python_reference_note": "the unmodified pure-Python reference cannot travel to "
+                                    "the GPU box; measured in the build container it steps ~70,000 env-steps/s per "
+                                    "core on this workload (BASELINE.md)"}
         traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_path):
             with open(traffic_path) as f:

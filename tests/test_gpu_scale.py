@@ -100,3 +100,61 @@ def test_sharding_is_invisible(pz):
         assert torch.equal(d, torch.cat([x[2] for x in outs]))
     tot = torch.stack([p.stats for p in parts]).sum(0)
     assert torch.equal(tot, whole.stats)
+
+
+def test_sixteen_million_envs_one_device(pz):
+    """configs[4]'s total batch (16,777,216 envs, serve='random', winning_score=5) on a single device:
+    64-bit indexing of the 4.7 GB observation tensor, exact agreement with the oracle on envs sampled
+    from the whole index range (including the last warp), in both observation layouts."""
+    n, steps = 1 << 24, 40
+    cfg = dict(winning_score=5, serve="random")
+    idx = np.concatenate([np.arange(0, 64), np.arange(n // 2 - 32, n // 2 + 32), np.arange(n - 64, n),
+                          np.arange(0, n, 1_000_003)])
+    tidx = torch.from_numpy(idx).cuda()
+    orcs = po.OracleVecEnv(len(idx), seed=0, **cfg)
+    for j, i in enumerate(idx):
+        po.lib().pk_init(po._p(orcs.state[j]), 77 + int(i))
+    env = pz.PikaVecEnv(n, seed=77, obs_dtype=torch.int16, action_dtype=torch.uint8, **cfg)
+    fm = pz.PikaVecEnv(n, seed=77, obs_dtype=torch.int16, action_dtype=torch.uint8, obs_layout="feature_major", **cfg)
+    assert np.array_equal(env.reset()[tidx].cpu().numpy(), orcs.reset().astype(np.int16))
+    fm.reset()
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    for t in range(steps):
+        a = torch.randint(0, 18, (n, 2), generator=gen, device="cuda", dtype=torch.uint8)
+        obs, rew, done = env.step(a)
+        fobs, frew, fdone = fm.step(a)
+        o_obs, o_rew, o_done = orcs.step(a[tidx].cpu().numpy())
+        assert np.array_equal(obs[tidx].cpu().numpy(), o_obs.astype(np.int16)), t
+        assert np.array_equal(fobs[:, :, tidx].permute(2, 0, 1).cpu().numpy(), o_obs.astype(np.int16)), t
+        assert np.array_equal(rew[tidx].cpu().numpy(), o_rew.astype(np.float32))
+        assert torch.equal(done, fdone) and torch.equal(rew, frew)
+    assert torch.equal(env.state, fm.state)
+    assert env.stats_dict()["calls"] == n * steps
+    del env, fm
+    torch.cuda.empty_cache()
+
+
+def test_calls_follow_the_current_stream(pz):
+    """every entry point is asynchronous on torch's current stream: two envs stepped on two side streams,
+    interleaved, must equal the same envs stepped on the default stream"""
+    n, steps = 50_000, 60
+    cfg = dict(winning_score=3, serve="random", is_player1_computer=True)
+    ref = [pz.PikaVecEnv(n, seed=s, **cfg) for s in (1, 2)]
+    side = [pz.PikaVecEnv(n, seed=s, **cfg) for s in (1, 2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    acts = [torch.from_numpy(synth_actions_numpy(3, 0, n, t, 18)).cuda() for t in range(steps)]
+    torch.cuda.synchronize()
+    for e in ref:
+        e.reset()
+        for t in range(steps):
+            e.step(acts[t])
+    for e, s in zip(side, streams):
+        with torch.cuda.stream(s):
+            e.reset()
+    for t in range(steps):
+        for e, s in zip(side, streams):
+            with torch.cuda.stream(s):
+                e.step(acts[t])
+    torch.cuda.synchronize()
+    for a, b in zip(ref, side):
+        assert torch.equal(a.state, b.state) and torch.equal(a.obs, b.obs) and torch.equal(a.stats, b.stats)
