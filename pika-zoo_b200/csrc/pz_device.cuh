@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
     const int64_t i = P.begin + (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const bool valid = i < P.end;
 
-    DrawCtx d;
+    DrawCtxT<AI_MASK == 0> d;  // computer players: the stream is loaded up front
     d.s = state_ptrs(P.state, P.n, P.state_policy);
     d.idx = i;
     d.r.loaded = false;

@@ -17,7 +17,7 @@
 #include "pz_kernels.cuh"
 
 #ifndef PZ_ROLLOUT_MIN_CTAS
-#define PZ_ROLLOUT_MIN_CTAS 6  // 80 registers (a few bytes of spill): 2.63 ms per 64 frames x 1 M envs against 2.74 ms at 4 or 5
+#define PZ_ROLLOUT_MIN_CTAS 5  // 96 registers, no spills: 2.64 ms per 64 frames x 1 M envs (4: 2.94 ms; 6: 80 registers with 176 B of spills, 3.25 ms)
 #endif
 
 namespace pz {
@@ -51,15 +51,14 @@ __global__ void __launch_bounds__(kThreads, PZ_ROLLOUT_MIN_CTAS) pz_rollout_kern
     const int64_t i = P.begin + (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const bool valid = i < P.end;
 
-    DrawCtx d;
-    d.s = state_ptrs(P.state, P.n, P.state_policy);
-    d.idx = i;
+    DrawCtxT<false> d;  // the stream is loaded up front; no pointer stays live across the frame loop
     d.r.loaded = false;
     d.r.dirty = false;
     Env e;
     if (valid) {
-        load_env(e, d.s, i);
-        rng_load(d.r, d.s, i);
+        const StatePtrs sp = state_ptrs(P.state, P.n, P.state_policy);
+        load_env(e, sp, i);
+        rng_load(d.r, sp, i);
     } else {
         fresh_env(e);
     }
@@ -105,8 +104,9 @@ __global__ void __launch_bounds__(kThreads, PZ_ROLLOUT_MIN_CTAS) pz_rollout_kern
 
     __syncwarp();
     if (valid) {
-        store_env(e, d.s, i);
-        if (d.r.dirty) rng_store(d.r, d.s, i);
+        const StatePtrs sp = state_ptrs(P.state, P.n, P.state_policy);
+        store_env(e, sp, i);
+        if (d.r.dirty) rng_store(d.r, sp, i);
     }
     bool pending = false;
     if (P.obs) pending = emit_obs_cold(P.state, P.n, i, P.end, P.obs_dtype, P.normalize, P.obs, stage[warp], P.state_policy,

@@ -44,13 +44,17 @@ struct StepCfg {
     const uint16_t *tab_power;
 };
 
-// Lazily loaded PCG64 stream of the env owned by this thread.
-struct DrawCtx {
+// PCG64 stream of the env owned by this thread. LAZY: loaded from global memory on the first draw
+// (kernels without computer players, where most frames draw nothing); otherwise the caller has loaded it
+// and neither the state pointers nor the env index stay live across the frame (10+ registers in the
+// rollout kernel).
+template <bool LAZY>
+struct DrawCtxT {
     Rng r;
     StatePtrs s;
     int64_t idx;
     __device__ __forceinline__ void ensure() {
-        if (!r.loaded) rng_load(r, s, idx);
+        if (LAZY && !r.loaded) rng_load(r, s, idx);
     }
     template <uint32_t HIGH>
     __device__ __forceinline__ int integers(int &has32) {
@@ -58,6 +62,7 @@ struct DrawCtx {
         return rng_integers<HIGH>(r, has32);
     }
 };
+using DrawCtx = DrawCtxT<true>;
 
 // ---- action decode -------------------------------------------------------------------------
 // action_key_map (pikazoo_env.py:119-141) as key-bit masks: bit0 left, bit1 right, bit2 up,
@@ -120,8 +125,8 @@ __device__ __forceinline__ Input get_input(Player &p, uint32_t keys) {
 
 // ---- round / game initialisation -------------------------------------------------------------
 // Player.initialize_for_new_round, physics.py:181-218
-template <int I>
-__device__ __forceinline__ void player_new_round(Env &e, DrawCtx &d) {
+template <int I, class Ctx>
+__device__ __forceinline__ void player_new_round(Env &e, Ctx &d) {
     Player &p = e.p[I];
     p.x = I ? kGroundWidth - 36 : 36;
     p.y = kPlayerGroundY;
@@ -131,18 +136,19 @@ __device__ __forceinline__ void player_new_round(Env &e, DrawCtx &d) {
     p.frame = 0;
     p.arm = 1;
     p.delay = 0;
-    p.bold = d.integers<5>(e.has32);
+    p.bold = d.template integers<5>(e.has32);
 }
 
 // Ball.initialize_for_new_round (physics.py:258-277) with raw_env.get_server (pikazoo_env.py:242-248)
-__device__ __forceinline__ void new_round(Env &e, DrawCtx &d, const StepCfg &c) {
+template <class Ctx>
+__device__ __forceinline__ void new_round(Env &e, Ctx &d, const StepCfg &c) {
     player_new_round<0>(e, d);
     player_new_round<1>(e, d);
     int p2_serves;
     if (c.serve == 0)
         p2_serves = e.p2serve;
     else if (c.serve == 2)
-        p2_serves = d.integers<2>(e.has32) == 0;
+        p2_serves = d.template integers<2>(e.has32) == 0;
     else
         p2_serves = ((e.score[0] + e.score[1]) & 1);
     Ball &b = e.b;
@@ -156,7 +162,8 @@ __device__ __forceinline__ void new_round(Env &e, DrawCtx &d, const StepCfg &c) 
 
 // raw_env.reset, pikazoo_env.py:149-173 — on a live object: everything not assigned here
 // carries over (previous positions, landing point, diving direction, ..., the RNG stream).
-__device__ __forceinline__ void reset_env(Env &e, DrawCtx &d, const StepCfg &c) {
+template <class Ctx>
+__device__ __forceinline__ void reset_env(Env &e, Ctx &d, const StepCfg &c) {
     e.game_ended = 0;
     e.round_ended = 0;
     e.p2serve = 0;
@@ -329,8 +336,8 @@ __device__ __forceinline__ void update_landing(unsigned mask, Env &e, const Step
 // ---- computer player ---------------------------------------------------------------------------
 // let_computer_decide_user_input (physics.py:689-771) + decide_whether_input_power_hit (:774-817).
 // Warp-collective over `mask`.
-template <int I>
-__device__ __forceinline__ void computer_decide(unsigned mask, Env &e, DrawCtx &d, const StepCfg &cfg, Input &in,
+template <int I, class Ctx>
+__device__ __forceinline__ void computer_decide(unsigned mask, Env &e, Ctx &d, const StepCfg &cfg, Input &in,
                                                 int *scratch) {
     Player &p = e.p[I];
     const Player &o = e.p[1 - I];
@@ -351,8 +358,8 @@ __device__ __forceinline__ void computer_decide(unsigned mask, Env &e, DrawCtx &
     }
     if (iabs(virt - p.x) > p.bold + 8) {
         in.xdir = (p.x < virt) ? 1 : -1;
-    } else if (d.integers<20>(e.has32) == 0) {  // :728
-        p.standby = d.integers<2>(e.has32);      // :729
+    } else if (d.template integers<20>(e.has32) == 0) {  // :728
+        p.standby = d.template integers<2>(e.has32);      // :729
     }
 
     bool search = false;
@@ -375,25 +382,48 @@ __device__ __forceinline__ void computer_decide(unsigned mask, Env &e, DrawCtx &
     // memoised table when the ball is inside its domain, otherwise iteratively, spread over the
     // lanes of the warp (one (searcher, candidate) pair per lane and pass, through the warp's scratch).
     int y_first = 0;
-    if (search) y_first = (d.integers<2>(e.has32) == 0) ? -1 : 1;  // :795 scan order of y_direction
+    if (search) y_first = (d.template integers<2>(e.has32) == 0) ? -1 : 1;  // :795 scan order of y_direction
     const int ayv = iabs(b.yv);
     bool found = false;
-    if (cfg.tab_power != nullptr && search && ayv <= kTabYv && tab_pos_ok(b.x, b.y)) {
-        // memoised: six independent loads, scanned in the reference's order
-        int lx[6];
-#pragma unroll
-        for (int c = 0; c < 6; c++)
-            lx[c] = (int)(__ldg(cfg.tab_power + tab_power_index(b.x, b.y, (c < 3) ? 1 : 0,
-                                                                 ayv * y_first * (1 - (c % 3)))) & 0x7FFFu);
-#pragma unroll
-        for (int c = 0; c < 6; c++) {
-            if (!found && (lx[c] <= left_boundary || lx[c] >= far_boundary) && iabs(lx[c] - o.x) > kPlayerLength) {
+    // memoised: one table load per (searcher, candidate) pair, the pairs of all searching lanes spread
+    // over the lanes of the warp — a searcher alone would run six dependent lookups with one or two lanes
+    // of the warp active. Inputs travel by shuffle, verdicts come back through a byte each in scratch.
+    const bool tab_ok = cfg.tab_power != nullptr && search && ayv <= kTabYv && tab_pos_ok(b.x, b.y);
+    const unsigned tm = __ballot_sync(mask, tab_ok);
+    if (tm) {  // warp-uniform
+        const int lane = threadIdx.x & 31;
+        unsigned char *s_ok = reinterpret_cast<unsigned char *>(scratch);  // [32][8] verdict of candidate c
+        const int total = 6 * __popc(tm), workers = __popc(mask);
+        const int w = __popc(mask & ((1u << lane) - 1u));
+#pragma unroll 1
+        for (int base = 0; base < total; base += workers) {
+            const int q = base + w;
+            const bool act = q < total;
+            const int r = act ? q / 6 : 0, c = act ? q - 6 * r : 0;
+            const int src = __fns(tm, 0, r + 1);  // lane of the r-th searcher
+            const int sx = __shfl_sync(mask, b.x, src), sy = __shfl_sync(mask, b.y, src);
+            const int sa = __shfl_sync(mask, ayv, src), sf = __shfl_sync(mask, y_first, src);
+            const int so = __shfl_sync(mask, o.x, src);
+            if (act) {
+                const int lx = (int)(__ldg(cfg.tab_power + tab_power_index(sx, sy, (c < 3) ? 1 : 0,
+                                                                           sa * sf * (1 - (c % 3)))) & 0x7FFFu);
+                s_ok[src * 8 + c] =
+                    ((lx <= left_boundary || lx >= far_boundary) && iabs(lx - so) > kPlayerLength) ? 1 : 0;
+            }
+        }
+        __syncwarp(mask);
+        if (tab_ok) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(s_ok + lane * 8);
+            const unsigned lo4 = v.x, hi2 = v.y & 0xFFFFu;  // candidates 0..3 | 4..5, one byte each
+            if (lo4 | hi2) {  // the first acceptable candidate in the reference's scan order
+                const int c = lo4 ? ((__ffs((int)lo4) - 1) >> 3) : (4 + ((__ffs((int)hi2) - 1) >> 3));
                 in.xdir = (c < 3) ? 1 : 0;
                 in.ydir = y_first * (1 - (c % 3));
                 found = true;
             }
+            search = false;
         }
-        search = false;
+        __syncwarp(mask);  // scratch is reused below and by the other player
     }
     const unsigned sm = __ballot_sync(mask, search);
     if (sm) {  // warp-uniform: lanes outside the memoised domain, or tables off
@@ -487,7 +517,7 @@ __device__ __forceinline__ void player_move(Player &p, const Input &in) {
         }
     }
     if (p.state == 1) {
-        p.frame = (p.frame + 1) % 3;
+        p.frame = p.frame >= 2 ? p.frame - 2 : p.frame + 1;  // (frame + 1) % 3 for frame in 0..4
     } else if (p.state == 2) {
         if (p.delay < 1) {
             p.frame += 1;
@@ -512,8 +542,8 @@ __device__ __forceinline__ void player_move(Player &p, const Input &in) {
 
 // is_collision_between_ball_and_player_happened (physics.py:340-356) and
 // process_collision_between_ball_and_player (physics.py:580-640). Returns true on a NEW collision.
-template <int I>
-__device__ __forceinline__ bool ball_player(Env &e, DrawCtx &d, const Input &in) {
+template <int I, class Ctx>
+__device__ __forceinline__ bool ball_player(Env &e, Ctx &d, const Input &in) {
     Player &p = e.p[I];
     Ball &b = e.b;
     const bool hit = iabs(b.x - p.x) <= kPlayerHalfLength && iabs(b.y - p.y) <= kPlayerHalfLength;
@@ -527,7 +557,7 @@ __device__ __forceinline__ bool ball_player(Env &e, DrawCtx &d, const Input &in)
         b.xv = -(iabs(b.x - p.x) / 3);
     else if (b.x > p.x)
         b.xv = iabs(b.x - p.x) / 3;
-    if (b.xv == 0) b.xv = d.integers<3>(e.has32) - 1;  // :613
+    if (b.xv == 0) b.xv = d.template integers<3>(e.has32) - 1;  // :613
     const int ayv = iabs(b.yv);
     b.yv = (ayv < 15) ? -15 : -ayv;
     if (p.state == 2) {  // jumping and power hitting
@@ -545,8 +575,8 @@ __device__ __forceinline__ bool ball_player(Env &e, DrawCtx &d, const Input &in)
 // raw_env.step (pikazoo_env.py:175-240) for an env that has not terminated. keys1/keys2 are the
 // decoded key bits. AI_MASK bit I = player I+1 is a computer. Warp-collective over `mask` when
 // AI_MASK != 0. Returns player_1's base reward (-1, 0, +1).
-template <int AI_MASK>
-__device__ __forceinline__ int step_frame(unsigned mask, Env &e, DrawCtx &d, const StepCfg &c, uint32_t keys1,
+template <int AI_MASK, class Ctx>
+__device__ __forceinline__ int step_frame(unsigned mask, Env &e, Ctx &d, const StepCfg &c, uint32_t keys1,
                                           uint32_t keys2, int *scratch) {
     if (e.round_ended) {  // :176-180 (game_ended is false here)
         new_round(e, d, c);

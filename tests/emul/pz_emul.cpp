@@ -34,6 +34,9 @@ static inline int __fns(unsigned mask, unsigned base, int offset) {
 static inline uint64_t __umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 template <typename T>
 static inline T __ldg(const T *p) { return *p; }
+template <typename T>
+static inline T __shfl_sync(unsigned, T v, int) { return v; }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 
 #include "../../pika-zoo_b200/csrc/pz_physics.cuh"
 
