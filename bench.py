@@ -366,10 +366,13 @@ def run_b200_arm(args):
         v.reset()
         variants["computer_vs_computer_per_step"] = time_steps(v, None)
         del v
-        for hints in (True, False):  # A/B of the L2 cache-policy hints on the main workload, timed alike
-            v = pikazoo_b200.PikaVecEnv(n, device=dev, seed=2026, first_env=first, l2_hints=hints, **ENV_KW)
+        # A/B on the main workload, timed alike: the evict-first L2 policy on the outputs, and programmatic
+        # dependent launch
+        for name, kw in (("main_workload_defaults", {}), ("main_workload_l2_hints_off", dict(l2_hints=False)),
+                         ("main_workload_pdl_off", dict(pdl=False))):
+            v = pikazoo_b200.PikaVecEnv(n, device=dev, seed=2026, first_env=first, **kw, **ENV_KW)
             v.reset()
-            variants["main_workload_l2_hints_" + ("on" if hints else "off")] = time_steps(v, ring, steps=1000, warm=50)
+            variants[name] = time_steps(v, ring, steps=1000, warm=50)
             del v
         shaped = ((0.1, 0.2, 0.3, 0.4, -0.1, -0.2, -0.3, -0.4), 216, 176)
         v = pikazoo_b200.PikaVecEnv(65536, device=dev, seed=13, first_env=rank * 65536, simplify_action=True,

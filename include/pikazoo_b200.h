@@ -125,6 +125,9 @@ typedef struct pz_config {
 #define PZ_FLAG_NO_L2_HINTS 2 /* do not mark the output stores evict-first in L2; for A/B
                                  measurements */
 
+#define PZ_FLAG_NO_PDL 4 /* launch pz_step without programmatic stream serialization; for A/B
+                            measurements */
+
 int pz_version(void);
 int pz_state_words(void);
 int pz_unpacked_words(void);

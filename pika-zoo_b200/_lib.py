@@ -25,6 +25,7 @@ LAYOUT_ENV_MAJOR, LAYOUT_FEATURE_MAJOR = 0, 1
 ACTIONS_NOOP, ACTIONS_SYNTH = 0, 1
 FLAG_NO_TABLES = 1
 FLAG_NO_L2_HINTS = 2
+FLAG_NO_PDL = 4
 VERSION = 2
 
 STAT_NAMES = (

@@ -37,6 +37,7 @@ struct KParams {
     int obs_layout, obs_rows;  // PZ_LAYOUT_*; FEATURE_MAJOR: rows per agent (leading dimension = n)
     int max_frames;       // 0: never truncate
     uint64_t state_policy, out_policy;  // L2 cache policies (pz_state.cuh), kL2EvictNormal when hints are off
+    int pdl;              // launch the step kernel with programmatic stream serialization
     int x_line, y_line;
     // rollout only
     int K, action_source;
@@ -332,6 +333,12 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t i = P.begin + (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const bool valid = i < P.end;
+    // Programmatic dependent launch: let the next launch in the stream be scheduled into the SM slots
+    // this grid's tail frees (it parks in its own cudaGridDependencySynchronize), and wait here for the
+    // previous launch to have completed and flushed before the first read. Both are no-ops when the
+    // launch did not ask for programmatic stream serialization.
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
 
     DrawCtxT<AI_MASK == 0> d;  // computer players: the stream is loaded up front
     d.s = state_ptrs(P.state, P.n, P.state_policy);

@@ -325,6 +325,7 @@ static void fill_params(KParams &P, int32_t *state, int64_t n, const pz_config *
     // outputs are written once and never read back by the simulator: evict them from L2 first
     // (-1.7 us per 1 M-env launch). The state words keep the normal policy: evict-last on them, meant to
     // hold them in the 126 MB L2 across launches, measured 2 us SLOWER.
+    P.pdl = (c->flags & PZ_FLAG_NO_PDL) ? 0 : 1;
     P.state_policy = kL2EvictNormal;
     P.out_policy = (c->flags & PZ_FLAG_NO_L2_HINTS) ? kL2EvictNormal : kL2EvictFirst;
     P.x_line = c->x_line;

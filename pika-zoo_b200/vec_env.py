@@ -52,6 +52,7 @@ def make_config(
     l2_hints: bool = True,
     obs_layout: str = "env_major",
     obs_feature_rows: int = 35,
+    pdl: bool = True,
 ) -> _lib.PzConfig:
     assert serve in ("winner", "alternate", "random")  # pikazoo_env.py:104
     if not 1 <= int(winning_score) <= 1023:
@@ -73,7 +74,8 @@ def make_config(
     c.autoreset = int(bool(autoreset))
     c.action_dtype = _ACT_DTYPES[action_dtype]
     c.reward_dtype = _REW_DTYPES[reward_dtype]
-    c.flags = (0 if landing_tables else _lib.FLAG_NO_TABLES) | (0 if l2_hints else _lib.FLAG_NO_L2_HINTS)
+    c.flags = ((0 if landing_tables else _lib.FLAG_NO_TABLES) | (0 if l2_hints else _lib.FLAG_NO_L2_HINTS)
+               | (0 if pdl else _lib.FLAG_NO_PDL))
     if obs_dtype not in _OBS_DTYPES:
         raise TypeError(f"obs_dtype must be one of {sorted(str(k) for k in _OBS_DTYPES)}")
     c.obs_dtype = _OBS_DTYPES[obs_dtype]
@@ -129,6 +131,7 @@ class PikaVecEnv:
         l2_hints: bool = True,
         obs_layout: str = "env_major",
         obs_feature_rows: int = 35,
+        pdl: bool = True,
     ):
         """Beyond the reference's constructor arguments:
 
@@ -174,7 +177,7 @@ class PikaVecEnv:
             obs_dtype=obs_dtype, normalize_observation=normalize_observation,
             reward_in_normal_state=reward_in_normal_state, normal_state_first=normal_state_first,
             max_episode_frames=max_episode_frames, l2_hints=l2_hints, obs_layout=obs_layout,
-            obs_feature_rows=obs_feature_rows,
+            obs_feature_rows=obs_feature_rows, pdl=pdl,
         )
         self.cfg = make_config(**self._kw)
         self.action_dtype = action_dtype
