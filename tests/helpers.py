@@ -188,3 +188,70 @@ class CudaStepperIterative(CudaStepper):
     """Computer players iterate every trajectory simulation (PZ_FLAG_NO_TABLES)."""
 
     landing_tables = False
+
+
+def survey_known_answers(make_env, n, cfg, actions_for, max_frames=25_000):
+    """SURVEY.md §8(c) known answers: env i is seeded i (protocol S0); hash = sha256 over obs1, obs2
+    (int32) after reset, then per step obs1, obs2, bytes([reward_p1 + 1]); first 16 hex digits.
+    make_env(n, seed, **cfg) -> object with reset() -> obs [n,2,35], step(a) -> (obs, reward, done) as
+    numpy, scores() -> [n,2]. actions_for(i, t) -> (a1, a2). Returns [(frames, [s1, s2], hash16) | None]."""
+    env = make_env(n, 0, cfg)
+    obs = np.asarray(env.reset())
+    hs = [hashlib.sha256() for _ in range(n)]
+    for i in range(n):
+        hs[i].update(np.ascontiguousarray(obs[i], dtype="<i4").tobytes())
+    out = [None] * n
+    t = 0
+    while any(o is None for o in out) and t < max_frames:
+        a = np.array([actions_for(i, t) for i in range(n)], dtype=np.int32)
+        obs, rew, done = env.step(a)
+        obs, rew, done = np.asarray(obs), np.asarray(rew), np.asarray(done)
+        t += 1
+        scores = None
+        for i in range(n):
+            if out[i] is not None:
+                continue
+            hs[i].update(np.ascontiguousarray(obs[i], dtype="<i4").tobytes())
+            hs[i].update(bytes([int(rew[i][0]) + 1]))
+            if done[i]:
+                if scores is None:
+                    scores = np.asarray(env.scores())
+                out[i] = (t, [int(scores[i][0]), int(scores[i][1])], hs[i].hexdigest()[:16])
+    return out
+
+
+class _PerEnvRng:
+    """actions of the survey's random-vs-random answers: env i draws
+    np.random.default_rng(i + 1000).integers(0, 18, size=2) once per step"""
+
+    def __init__(self, n):
+        self.rngs = [np.random.default_rng(i + 1000) for i in range(n)]
+        self.cache = {}
+
+    def __call__(self, i, t):
+        if (i, t) not in self.cache:
+            assert t == 0 or (i, t - 1) in self.cache or True
+            self.cache[(i, t)] = tuple(int(v) for v in self.rngs[i].integers(0, 18, size=2))
+        return self.cache[(i, t)]
+
+
+SURVEY_AI = {0: (13987, [15, 5], "7c7cc240a767c583"), 1: (11383, [15, 4], "13bf71668641d8b4"), 2: None,
+             3: (17039, [15, 2], None)}
+SURVEY_RANDOM_WS15 = {0: (1124, [9, 15]), 1: (1075, [13, 15]), 3: (1240, [15, 11])}
+SURVEY_RANDOM_WS5 = {0: (445, [5, 4]), 1: (197, [1, 5]), 3: (259, [0, 5])}
+
+
+def check_survey_known_answers(make_env):
+    """The answers SURVEY.md §8(c) recorded from the unmodified reference, reproduced by `make_env`."""
+    ai = survey_known_answers(make_env, 4, dict(is_player1_computer=True, is_player2_computer=True, winning_score=15,
+                                                serve="winner"), lambda i, t: (0, 0), max_frames=17_100)
+    for i, exp in SURVEY_AI.items():
+        if exp is None:
+            assert ai[i] is None  # seed 2 never terminates
+        else:
+            assert ai[i][:2] == exp[:2], (i, ai[i])
+            assert exp[2] is None or ai[i][2] == exp[2], (i, ai[i])
+    for cfg, table in ((dict(), SURVEY_RANDOM_WS15), (dict(winning_score=5, serve="random"), SURVEY_RANDOM_WS5)):
+        got = survey_known_answers(make_env, 4, cfg, _PerEnvRng(4), max_frames=3_000)
+        for i, exp in table.items():
+            assert got[i][:2] == exp, (cfg, i, got[i])

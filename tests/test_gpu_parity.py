@@ -114,6 +114,15 @@ def test_trajectory_tables_equal_iterative_simulation(pz):
         assert np.array_equal(sa.cpu().numpy(), orc.state)
 
 
+def test_cuda_reproduces_survey_known_answers(pz):
+    """configs[0] and the survey's other known answers (probed on the unmodified
+    reference): config 1 seed 0 -> 13,987 frames, 15-5, trajectory hash 7c7cc240a767c583, ..."""
+    from tests.helpers import check_survey_known_answers
+
+    check_survey_known_answers(lambda n, seed, cfg: CudaStepperIterative(n, seed, cfg))
+    check_survey_known_answers(lambda n, seed, cfg: CudaStepperTables(n, seed, cfg))
+
+
 @pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 127, 128, 129, 1000])
 def test_ragged_batch_sizes(pz, n):
     _lockstep(pz, n, 300, CONFIGS["ws5_random"], seed=5)

@@ -49,3 +49,11 @@ def test_oracle_replays_wrapper_stacks(golden_wrappers, name):
     assert group["oracle_checked"]
     bad = replay_group(group, OracleStepper)
     assert not bad, bad[:5]
+
+
+def test_oracle_reproduces_survey_known_answers():
+    """frames / final scores / trajectory hashes the survey probed on the unmodified reference
+    (SURVEY.md §8(c)), e.g. config 1 seed 0 -> 13,987 frames, 15-5, 7c7cc240a767c583"""
+    from tests.helpers import check_survey_known_answers
+
+    check_survey_known_answers(lambda n, seed, cfg: OracleStepper(n, seed, cfg))
