@@ -1,10 +1,11 @@
 // sm_100a kernels + C ABI (include/pikazoo_b200.h) of the batched Pikachu-Volleyball simulator.
 //
-//   pz_step_kernel     one frame per env per launch; HBM-bound: 2x128-bit state
-//                      loads, 2x128-bit state stores, observation rows staged in shared memory
-//                      and written with one bulk async copy (TMA engine, cp.async.bulk) per warp.
+//   pz_step_kernel     (pz_device.cuh, instantiated in pz_step_ai*.cu) one frame per env per launch;
+//                      HBM-bound: 2x128-bit state loads, 2x128-bit state stores,
+//                      observation rows staged in shared memory and written with one bulk async copy
+//                      (TMA engine, cp.async.bulk) per warp, or stored feature-major without staging.
 //   pz_rollout_kernel  K frames per launch with the env and its PCG64 stream in registers.
-//   pz_reset_kernel / pz_seed_kernel / export / import.
+//   pz_reset_kernel / pz_seed_kernel / export / import / the memoised trajectory tables.
 #include <cuda_runtime.h>
 
 #include <cstdint>

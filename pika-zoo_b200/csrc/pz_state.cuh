@@ -114,7 +114,8 @@ __device__ __forceinline__ void unpack_player(Player &p, uint32_t lo, uint32_t h
 //   B1  = x:9 | px:9 << 9 | ppx:9 << 18 | has_uint32 << 27 | land_ok << 28
 //   B2  = (y+512):10 | (py+512):10 << 10 | (ppy+512):10 << 20
 //   ENV = score1:10 | score2:10 << 10 | round_ended << 20 | game_ended << 21 | p2serve << 22 | punch:9 << 23
-// Ball y is signed: with |yv| > 176 the net-top bounce (physics.py:412-414, applied after the
+// Ball x is unsigned: the wall rule (physics.py:392-404) keeps it in [20, 432] from either serve position
+// (a flip turns x + xv < 20 into x + |xv| > x). Ball y is signed: with |yv| > 176 the net-top bounce (physics.py:412-414, applied after the
 // ceiling test :408-409) throws the ball above the ceiling for one frame, y = 177 - |yv| at the
 // lowest; 10 bits cover |yv| <= 689, 16 bits of yv cover every velocity the doubling power hits
 // can build before the ball leaves the court.

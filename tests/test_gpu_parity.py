@@ -265,3 +265,60 @@ def test_state_dict_checkpoint_resume(pz):
     env2.load_state_dict(sd)
     b = env2.rollout(50, write_obs=True)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("tables", [True, False], ids=["tables", "iterative"])
+def test_random_states_fuzz(pz, tables):
+    """States drawn uniformly from the packed ranges (far outside what play reaches, including the
+    corners of the memoised tables' domain: x 20 / 432, y 0 / 252, yv +-100, xv +-20) imported, stepped
+    four frames and compared with the oracle — the GPU twin of tests/test_device_code_on_host.py."""
+    rng = np.random.default_rng(2024)
+    n = 200_000
+    base = po.OracleVecEnv(n, seed=5)
+    base.reset()
+    st = base.state.copy()
+    for k in (0, 13):
+        lo, hi = (32, 184) if k == 0 else (248, 400)
+        st[:, k + 0] = rng.integers(lo, hi + 1, n)
+        st[:, k + 1] = rng.integers(108, 245, n)
+        st[:, k + 2] = rng.integers(-16, 17, n)
+        st[:, k + 3] = rng.integers(0, 5, n)
+        st[:, k + 4] = rng.integers(0, 5, n)
+        st[:, k + 5] = rng.integers(0, 6, n)
+        st[:, k + 6] = rng.choice([-1, 1], n)
+        st[:, k + 7] = rng.integers(-1, 2, n)
+        st[:, k + 8] = rng.integers(-2, 4, n)
+        st[:, k + 9] = rng.integers(0, 2, n)
+        st[:, k + 10] = rng.integers(0, 5, n)
+        st[:, k + 11] = rng.integers(0, 2, n)
+        st[:, k + 12] = rng.integers(0, 2, n)
+    st[:, 26] = rng.integers(20, 433, n)  # the wall rule keeps the ball's x in [20, 432] (9 unsigned bits)
+    st[:, 27] = rng.integers(-100, 253, n)
+    st[:, 28] = rng.integers(-20, 21, n)
+    st[:, 29] = rng.integers(-130, 131, n)
+    edge = rng.integers(0, 4, n) == 0  # a quarter of the envs on the table domain's corners
+    st[edge, 26] = rng.choice([20, 21, 191, 192, 216, 240, 241, 431, 432], int(edge.sum()))
+    st[edge, 27] = rng.choice([0, 176, 177, 192, 193, 252], int(edge.sum()))
+    st[edge, 28] = rng.choice([-20, 0, 20], int(edge.sum()))
+    st[edge, 29] = rng.choice([-101, -100, -1, 0, 1, 100, 101], int(edge.sum()))
+    st[:, 30:34] = rng.integers(0, 253, (n, 4))
+    st[:, 34] = rng.integers(0, 2, n)
+    st[:, 35] = rng.integers(0, 433, n)
+    st[:, 36] = rng.integers(0, 433, n)
+    st[:, 37:39] = rng.integers(0, 4, (n, 2))
+    st[:, 39] = rng.integers(0, 2, n) * (rng.integers(0, 4, n) == 0)
+    st[:, 41] = rng.integers(0, 2, n)
+    for cfg in (dict(is_player1_computer=True, is_player2_computer=True, serve="random"),
+                dict(is_player2_computer=True, winning_score=5), dict(is_player1_computer=True, serve="alternate")):
+        env = pz.PikaVecEnv(n, seed=0, landing_tables=tables, **cfg)
+        orc = po.OracleVecEnv(n, seed=0, **cfg)
+        env.import_state(torch.from_numpy(st).cuda())
+        orc.state[:] = st
+        assert np.array_equal(env.export_state().cpu().numpy(), st)
+        for t in range(4):
+            a = synth_actions_numpy(4, 0, n, t, 18)
+            obs, rew, done = env.step(torch.from_numpy(a).cuda())
+            o_obs, o_rew, o_done = orc.step(a)
+            bad = np.nonzero((obs.cpu().numpy() != o_obs).any(axis=(1, 2)))[0]
+            assert len(bad) == 0, (cfg, t, len(bad), st[bad[0]].tolist())
+            assert np.array_equal(env.export_state().cpu().numpy(), orc.state)
