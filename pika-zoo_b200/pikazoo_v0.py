@@ -90,6 +90,13 @@ class raw_env:
             **self._kwargs,
         )
         self._actions = torch.zeros((1, 2), dtype=torch.int32, device=self._vec.device)
+        # pinned host mirrors: one step = one async H2D, the kernel, four async D2H and ONE stream sync
+        v = self._vec
+        self._h_actions = torch.zeros((1, 2), dtype=torch.int32).pin_memory()
+        self._h_obs = torch.zeros(tuple(v.obs.shape), dtype=v.obs.dtype).pin_memory()
+        self._h_reward = torch.zeros((1, 2), dtype=torch.float64).pin_memory()
+        self._h_done = torch.zeros((1,), dtype=torch.uint8).pin_memory()
+        self._h_state = torch.zeros((v.state.numel(),), dtype=torch.int32).pin_memory()
 
     def _configure(self, **opts):
         """Used by the wrappers to fuse themselves into the kernel configuration."""
@@ -100,11 +107,23 @@ class raw_env:
             self._build()
             self._vec.load_state_dict(state)
 
-    def _obs_dict(self, obs: torch.Tensor) -> Dict[str, np.ndarray]:
+    def _fetch(self, with_step_outputs: bool):
+        """async copies of this call's outputs into the pinned mirrors, then one synchronisation"""
+        v = self._vec
+        self._h_obs.copy_(v.obs, non_blocking=True)
+        self._h_state.copy_(v.state, non_blocking=True)
+        if with_step_outputs:
+            self._h_reward.copy_(v.reward, non_blocking=True)
+            self._h_done.copy_(v.done_u8, non_blocking=True)
+        torch.cuda.current_stream(v.device).synchronize()
+        # scores live in the packed state's ENV word (csrc/pz_state.cuh: G1.w = score1:10 | score2:10 << 10 | ...)
+        env_word = int(self._h_state[7]) & 0xFFFFFFFF
+        self.scores[0], self.scores[1] = env_word & 1023, (env_word >> 10) & 1023
+
+    def _obs_dict(self) -> Dict[str, np.ndarray]:
         # the reference returns np.array of Python ints (int64); NormalizeObservation makes them float64
-        o = obs[0].cpu().numpy()
-        if not self._normalize_observation:
-            o = o.astype(np.int64)
+        o = self._h_obs[0].numpy()
+        o = o.copy() if self._normalize_observation else o.astype(np.int64)
         return {self.possible_agents[0]: o[0], self.possible_agents[1]: o[1]}
 
     def _get_infos(self):
@@ -118,9 +137,9 @@ class raw_env:
         if self._vec is None:
             self._build()
         self.agents = self.possible_agents[:]
-        obs = self._vec.reset()
-        self.scores[0] = self.scores[1] = 0
-        return self._obs_dict(obs), self._get_infos()
+        self._vec.reset()
+        self._fetch(with_step_outputs=False)
+        return self._obs_dict(), self._get_infos()
 
     def step(self, actions):
         if not self.agents:
@@ -132,13 +151,13 @@ class raw_env:
         for v in a:
             if not 0 <= v < n:
                 raise IndexError(f"action {v} is out of range for Discrete({n})")
-        self._actions.copy_(torch.tensor([a], dtype=torch.int32))
-        obs, reward, term = self._vec.step(self._actions)
-        r = reward[0].cpu().tolist()
-        terminated = bool(term[0].item())
-        s = self._vec.scores()[0].cpu().tolist()
-        self.scores[0], self.scores[1] = int(s[0]), int(s[1])
-        observations = self._obs_dict(obs)
+        self._h_actions[0, 0], self._h_actions[0, 1] = a[0], a[1]
+        self._actions.copy_(self._h_actions, non_blocking=True)
+        self._vec.step(self._actions)
+        self._fetch(with_step_outputs=True)
+        r = self._h_reward[0].tolist()
+        terminated = bool(self._h_done[0])
+        observations = self._obs_dict()
         if self._reward_by_ball_position is None and not isinstance(self._reward_in_normal_state, float):
             r = [int(r[0]), int(r[1])]  # the reference's base rewards are Python ints
         rewards = {self.agents[0]: r[0], self.agents[1]: r[1]}
