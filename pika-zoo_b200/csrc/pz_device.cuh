@@ -310,12 +310,15 @@ constexpr int kAiScratchInts = 320;  // computer_decide: 32 x int4 inputs + 32 x
 #ifndef PZ_FM_MIN_CTAS
 #define PZ_FM_MIN_CTAS 8
 #endif
+#ifndef PZ_AI_MIN_CTAS
+#define PZ_AI_MIN_CTAS 5  // 94 registers, no spills: 72 us per million envs (4: 101 registers, 79 us; 6: 80 with spills, 77 us)
+#endif
 #ifndef PZ_HALF_MIN_CTAS
 #define PZ_HALF_MIN_CTAS 6
 #endif
 template <int AI_MASK, int OBS_DT, int LAYOUT>
 constexpr int step_min_ctas() {
-    if (AI_MASK != 0) return 4;  // their natural 96-128 registers
+    if (AI_MASK != 0) return PZ_AI_MIN_CTAS;
     if (LAYOUT == PZ_LAYOUT_FEATURE_MAJOR) return OBS_DT == PZ_OBS_F64 ? 4 : PZ_FM_MIN_CTAS;
     return ObsType<OBS_DT>::bytes == 2 ? PZ_HALF_MIN_CTAS : (OBS_DT == PZ_OBS_F64 ? 4 : 6);
 }
