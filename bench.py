@@ -512,8 +512,9 @@ def run_b200_arm(args):
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                     "sample": sample,
                                     "python_reference_note": "the unmodified pure-Python reference cannot travel to "
-                                    "the GPU box; measured in the build container it steps ~70,000 env-steps/s per "
-                                    "core on this workload (BASELINE.md)"}
+                                    "the GPU box; measured in the build container (oracle/time_reference.py, one env "
+                                    "process per core, 8 vCPU) it steps 457 k env-steps/s in total, 57 k per core, on "
+                                    "this workload (profiles/r01_python_reference_cpu_container.json)"}
         traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_path):
             with open(traffic_path) as f:
