@@ -230,7 +230,6 @@ class _PerEnvRng:
 
     def __call__(self, i, t):
         if (i, t) not in self.cache:
-            assert t == 0 or (i, t - 1) in self.cache or True
             self.cache[(i, t)] = tuple(int(v) for v in self.rngs[i].integers(0, 18, size=2))
         return self.cache[(i, t)]
 

@@ -54,7 +54,6 @@ def _parallel_api_cycles(env, cycles, n_actions):
             assert obs[a].shape == space.shape
             assert isinstance(term[a], bool) and isinstance(trunc[a], bool) and isinstance(infos[a], dict)
             assert np.isfinite(float(rew[a]))
-            assert env.observation_space(a) is env.observation_space(a) or True
         assert term[live[0]] == term[live[1]]
         if term[live[0]]:
             assert env.agents == []  # terminated agents leave the env (pikazoo_env.py:237-238)

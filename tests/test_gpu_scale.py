@@ -42,7 +42,6 @@ def test_one_million_envs_per_step_path(pz):
     obs = env.reset()
     assert np.array_equal(obs[sample].cpu().numpy(), orcs.reset())
     gen = torch.Generator(device="cuda").manual_seed(5)
-    prev_total = torch.zeros(N, dtype=torch.int32, device="cuda")
     for t in range(steps):
         a = torch.randint(0, 18, (N, 2), generator=gen, device="cuda", dtype=torch.int32)
         obs, rew, done = env.step(a)

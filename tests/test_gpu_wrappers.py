@@ -122,7 +122,8 @@ def test_feature_major_layout(pz, dtype, normalize, n, cfg):
         assert np.array_equal(got[:, :35, :], np.transpose(exp, (1, 2, 0))), where
         assert not got[:, 35:, :].any(), where
 
-    check(env.reset(), "reset") if not orc.reset() is None else None
+    orc.reset()
+    check(env.reset(), "reset")
     for t in range(300):
         a = synth_actions_numpy(9, 0, n, t, 18)
         obs, _, _ = env.step(torch.from_numpy(a).cuda())

@@ -1,7 +1,6 @@
 """CPU: the C oracle reproduces every golden session recorded from the unmodified reference
 (tests/golden/sessions.json, 1,039 full games; generator: oracle/make_golden.py)."""
 
-import numpy as np
 import pytest
 
 from tests.helpers import OracleStepper, replay_group

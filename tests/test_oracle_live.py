@@ -1,7 +1,6 @@
 """CPU, build container only: the C oracle against the LIVE unmodified reference, frame by
 frame including the full hidden state. Skipped where /root/reference is absent (GPU box)."""
 
-import numpy as np
 import pytest
 
 from oracle import ref_harness as rh
