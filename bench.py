@@ -116,18 +116,19 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # each "step" of this arm is a bounded sample: all host cores stepping their env batches for a
-    # fixed wall time; value = env-steps/sec averaged over the K timed samples.
-    steps = max(1, min(args.steps, 20))
-    warmup = max(1, min(args.warmup, 3))
-    per_step_seconds = 1.0
+    # each "step" of this arm is a bounded sample: all host cores stepping their env batches for a fixed
+    # wall time, sized so that the K timed steps take about a minute in total; value = env-steps/sec over
+    # the K timed samples.
+    steps = max(1, args.steps)
+    warmup = max(1, args.warmup)
+    per_step_seconds = min(1.0, max(0.02, 60.0 / steps))
     port = CpuPort()
-    for _ in range(warmup):
+    for _ in range(min(warmup, max(1, int(3.0 / per_step_seconds)))):  # at most ~3 s of warm-up
         port.sample(per_step_seconds)
     vals = [port.sample(per_step_seconds) for _ in range(steps)]
     value = sum(vals) / len(vals)
     cores = port.cores
-    sample = (f"{steps} timed samples of {per_step_seconds:.1f} s each: {cores} threads x {port.envs_per_thread} envs "
+    sample = (f"{steps} timed samples of {per_step_seconds:.2f} s each: {cores} threads x {port.envs_per_thread} envs "
               f"stepping the C port of the reference path (oracle/pika_oracle.c); the pure-Python reference cannot "
               f"travel to the GPU box (DESIGN.md)")
     line = {
