@@ -393,14 +393,18 @@ __device__ __forceinline__ void computer_decide(unsigned mask, Env &e, Ctx &d, c
     if (tm) {  // warp-uniform
         const int lane = threadIdx.x & 31;
         unsigned char *s_ok = reinterpret_cast<unsigned char *>(scratch);  // [32][8] verdict of candidate c
+        unsigned char *s_lane = s_ok + 256;                                 // [32] lane of the r-th searcher
+        const unsigned lt = (1u << lane) - 1u;
+        if (tab_ok) s_lane[__popc(tm & lt)] = (unsigned char)lane;  // (__fns is a ~40-instruction software loop)
+        __syncwarp(mask);
         const int total = 6 * __popc(tm), workers = __popc(mask);
-        const int w = __popc(mask & ((1u << lane) - 1u));
+        const int w = __popc(mask & lt);
 #pragma unroll 1
         for (int base = 0; base < total; base += workers) {
             const int q = base + w;
             const bool act = q < total;
             const int r = act ? q / 6 : 0, c = act ? q - 6 * r : 0;
-            const int src = __fns(tm, 0, r + 1);  // lane of the r-th searcher
+            const int src = s_lane[r];
             const int sx = __shfl_sync(mask, b.x, src), sy = __shfl_sync(mask, b.y, src);
             const int sa = __shfl_sync(mask, ayv, src), sf = __shfl_sync(mask, y_first, src);
             const int so = __shfl_sync(mask, o.x, src);
