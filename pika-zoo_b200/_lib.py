@@ -9,7 +9,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libpikazoo_b200.so")
+# PIKAZOO_B200_LIB points at another build of the same library (tuning runs: profiles/time_kernels.py)
+LIB_PATH = os.environ.get("PIKAZOO_B200_LIB") or os.path.join(HERE, "csrc", "libpikazoo_b200.so")
 
 STATE_WORDS = 17
 UNPACKED_WORDS = 53

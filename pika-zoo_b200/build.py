@@ -1,6 +1,9 @@
 """Build the sm_100a shared library (csrc/libpikazoo_b200.so) in-tree with nvcc.
 
-    python pika-zoo_b200/build.py [--force] [--verbose]
+    python pika-zoo_b200/build.py [--force] [--verbose] [--out variants/NAME.so]
+
+--out builds a tuning variant (with PZ_NVCC_FLAGS=-D...) beside the product library instead of replacing it;
+PIKAZOO_B200_LIB=<that path> makes the package load it.
 
 nvcc cross-compiles without a GPU; the built .so is git-ignored and travels with the tree.
 """
@@ -36,8 +39,8 @@ def needs_build() -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str | None = None) -> str:
+    if out is None and not force and not needs_build():
         return LIB_PATH
     nvcc = _nvcc()
     flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -45,7 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     flags += os.environ.get("PZ_NVCC_FLAGS", "").split()  # e.g. -DPZ_ROLLOUT_MIN_CTAS=4 for tuning runs
     if verbose:
         flags += ["-Xptxas", "-v"]
-    objdir = os.path.join(CSRC, "build")
+    lib_path = LIB_PATH if out is None else os.path.abspath(out)
+    objdir = os.path.join(CSRC, "build") if out is None else os.path.splitext(lib_path)[0] + "_obj"
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
@@ -62,9 +66,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(f"---- {src}\n{r.stdout}{r.stderr}")
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.run([nvcc, "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB_PATH] + [obj for _, obj, _ in results], check=True)
-    return LIB_PATH
+    subprocess.run([nvcc, "-Wno-deprecated-gpu-targets", "-shared", "-o", lib_path] + [obj for _, obj, _ in results], check=True)
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    out_path = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, out=out_path))

@@ -133,7 +133,7 @@ __device__ __forceinline__ bool emit_obs_as(const Env &e, bool valid, bool norma
     constexpr int row_bytes = kObsRow * ObsType<DT>::bytes;
     const int64_t warp_first = env_idx - lane;
     char *g = reinterpret_cast<char *>(obs);
-    if (DT != PZ_OBS_F64 && warp_first + 32 <= end) {  // warp-uniform: full warp
+    if (DT != PZ_OBS_F64 && warp_stage != nullptr && warp_first + 32 <= end) {  // warp-uniform: full warp
         write_obs_row<DT>(e, normalize, reinterpret_cast<char *>(warp_stage) + lane * row_bytes);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -141,7 +141,7 @@ __device__ __forceinline__ bool emit_obs_as(const Env &e, bool valid, bool norma
             bulk_store_issue(g + warp_first * row_bytes, warp_stage, 32 * row_bytes, policy);
             return true;
         }
-    } else if (valid) {  // ragged tail (and float64 rows, 17,920 B per warp): plain vector stores
+    } else if (valid) {  // ragged tail, no staging buffer, float64 rows (17,920 B per warp): plain vector stores
         write_obs_row<DT>(e, normalize, g + env_idx * row_bytes);
     }
     return false;

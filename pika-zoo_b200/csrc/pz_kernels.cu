@@ -45,11 +45,24 @@ __device__ __noinline__ bool emit_obs_cold(int32_t *state, int64_t n, int64_t en
 }
 
 // ---- K-frame register-resident rollout -------------------------------------------------------
+// Shared memory holds only the computer players' scratch (1,280 B per warp): the observation rows, written
+// once per K frames, go out with plain vector stores, so that registers alone decide the occupancy.
+#ifndef PZ_ROLLOUT_THREADS
+#define PZ_ROLLOUT_THREADS 128
+#endif
+constexpr int kRolloutThreads = PZ_ROLLOUT_THREADS;
+
+#ifdef PZ_ROLLOUT_MAXNREG
+#define PZ_ROLLOUT_BOUNDS __maxnreg__(PZ_ROLLOUT_MAXNREG)
+#else
+#define PZ_ROLLOUT_BOUNDS __launch_bounds__(kRolloutThreads, PZ_ROLLOUT_MIN_CTAS)
+#endif
+
 template <int AI_MASK>
-__global__ void __launch_bounds__(kThreads, PZ_ROLLOUT_MIN_CTAS) pz_rollout_kernel(const __grid_constant__ KParams P) {
-    __shared__ __align__(128) int stage[kWarps][32 * kObsRow];
+__global__ void PZ_ROLLOUT_BOUNDS pz_rollout_kernel(const __grid_constant__ KParams P) {
+    __shared__ __align__(16) int stage[kRolloutThreads / 32][kAiScratchInts];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t i = P.begin + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t i = P.begin + (int64_t)blockIdx.x * kRolloutThreads + threadIdx.x;
     const bool valid = i < P.end;
 
     DrawCtxT<false> d;  // the stream is loaded up front; no pointer stays live across the frame loop
@@ -110,7 +123,7 @@ __global__ void __launch_bounds__(kThreads, PZ_ROLLOUT_MIN_CTAS) pz_rollout_kern
         if (d.r.dirty) rng_store(d.r, sp, i);
     }
     bool pending = false;
-    if (P.obs) pending = emit_obs_cold(P.state, P.n, i, P.end, P.obs_dtype, P.normalize, P.obs, stage[warp], P.state_policy,
+    if (P.obs) pending = emit_obs_cold(P.state, P.n, i, P.end, P.obs_dtype, P.normalize, P.obs, nullptr, P.state_policy,
                                        P.out_policy, P.obs_layout, P.obs_rows);
     if (P.stats) {
         const unsigned ep = __reduce_add_sync(kFullMask, st_ep);
@@ -523,11 +536,12 @@ int pz_rollout(int32_t *state_dev, int64_t n, const pz_config *cfg, int32_t K, i
     P.first_env = first_env;
     P.frame0 = frame0;
     cudaStream_t st = (cudaStream_t)stream;
+    const unsigned rollout_grid = (unsigned)((n + kRolloutThreads - 1) / kRolloutThreads);
     switch (ai_mask(cfg)) {
-        case 0: pz_rollout_kernel<0><<<grid_for(n), kThreads, 0, st>>>(P); break;
-        case 1: pz_rollout_kernel<1><<<grid_for(n), kThreads, 0, st>>>(P); break;
-        case 2: pz_rollout_kernel<2><<<grid_for(n), kThreads, 0, st>>>(P); break;
-        default: pz_rollout_kernel<3><<<grid_for(n), kThreads, 0, st>>>(P); break;
+        case 0: pz_rollout_kernel<0><<<rollout_grid, kRolloutThreads, 0, st>>>(P); break;
+        case 1: pz_rollout_kernel<1><<<rollout_grid, kRolloutThreads, 0, st>>>(P); break;
+        case 2: pz_rollout_kernel<2><<<rollout_grid, kRolloutThreads, 0, st>>>(P); break;
+        default: pz_rollout_kernel<3><<<rollout_grid, kRolloutThreads, 0, st>>>(P); break;
     }
     return launch_status();
 }

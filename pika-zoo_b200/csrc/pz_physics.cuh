@@ -61,6 +61,14 @@ struct DrawCtxT {
         ensure();
         return rng_integers<HIGH>(r, has32);
     }
+    __device__ __forceinline__ int integers20_then_2(int &has32) {
+        ensure();
+        return rng_integers20_then_2(r, has32);
+    }
+    __device__ __forceinline__ void integers5_twice(int &has32, int &a, int &b) {
+        ensure();
+        rng_integers5_twice(r, has32, a, b);
+    }
 };
 using DrawCtx = DrawCtxT<true>;
 
@@ -124,9 +132,9 @@ __device__ __forceinline__ Input get_input(Player &p, uint32_t keys) {
 }
 
 // ---- round / game initialisation -------------------------------------------------------------
-// Player.initialize_for_new_round, physics.py:181-218
-template <int I, class Ctx>
-__device__ __forceinline__ void player_new_round(Env &e, Ctx &d) {
+// Player.initialize_for_new_round, physics.py:181-218 (computer_boldness, :218, is drawn by new_round)
+template <int I>
+__device__ __forceinline__ void player_new_round(Env &e) {
     Player &p = e.p[I];
     p.x = I ? kGroundWidth - 36 : 36;
     p.y = kPlayerGroundY;
@@ -136,14 +144,14 @@ __device__ __forceinline__ void player_new_round(Env &e, Ctx &d) {
     p.frame = 0;
     p.arm = 1;
     p.delay = 0;
-    p.bold = d.template integers<5>(e.has32);
 }
 
 // Ball.initialize_for_new_round (physics.py:258-277) with raw_env.get_server (pikazoo_env.py:242-248)
 template <class Ctx>
 __device__ __forceinline__ void new_round(Env &e, Ctx &d, const StepCfg &c) {
-    player_new_round<0>(e, d);
-    player_new_round<1>(e, d);
+    player_new_round<0>(e);
+    player_new_round<1>(e);
+    d.integers5_twice(e.has32, e.p[0].bold, e.p[1].bold);  // :218, player 1 then player 2
     int p2_serves;
     if (c.serve == 0)
         p2_serves = e.p2serve;
@@ -358,8 +366,9 @@ __device__ __forceinline__ void computer_decide(unsigned mask, Env &e, Ctx &d, c
     }
     if (iabs(virt - p.x) > p.bold + 8) {
         in.xdir = (p.x < virt) ? 1 : -1;
-    } else if (d.template integers<20>(e.has32) == 0) {  // :728
-        p.standby = d.template integers<2>(e.has32);      // :729
+    } else {
+        const int v = d.integers20_then_2(e.has32);  // :728 `integers(0, 20) == 0`, then :729 `integers(0, 2)`
+        if (v >= 0) p.standby = v;
     }
 
     bool search = false;

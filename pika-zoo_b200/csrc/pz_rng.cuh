@@ -61,6 +61,63 @@ __device__ __forceinline__ int rng_integers(Rng &r, int &has32) {
     return (int)(m >> 32);
 }
 
+// Fused call sites. The lanes of a warp are uncorrelated in has32, so the branch inside pcg_next32 makes a
+// warp run the generator step AND the buffered path at every draw, once per draw of a chain. Two draws that
+// follow each other consume exactly two 32-bit halves, i.e. at most ONE new 64-bit output whatever has32 is:
+// the step is taken speculatively once, the halves are selected, and the stream state is committed by
+// selects. Lemire's rejection (leftover < HIGH, p < 5e-9 per draw) leaves through the general path from
+// the untouched stream, so the values and the stream are those of the reference's calls, always.
+
+// `integers(0, 20) == 0 ? integers(0, 2) : -1`  (physics.py:728-729)
+__device__ __forceinline__ int rng_integers20_then_2(Rng &r, int &has32) {
+    uint64_t lo = r.s_lo, hi = r.s_hi;
+    pcg_step(lo, hi, r.inc_lo, r.inc_hi);
+    const uint64_t x = hi ^ lo;
+    const unsigned rot = (unsigned)(hi >> 58);
+    const uint64_t n = (x >> rot) | (x << ((64u - rot) & 63u));
+    const bool buffered = has32 != 0;
+    const uint64_t m1 = (uint64_t)(buffered ? r.uinteger : (uint32_t)n) * 20u;
+    if ((uint32_t)m1 < 20u) {  // the rejection test applies: general path
+        const int first = rng_integers<20>(r, has32);
+        return first == 0 ? rng_integers<2>(r, has32) : -1;
+    }
+    const bool second = (uint32_t)(m1 >> 32) == 0u;
+    const uint32_t v2 = buffered ? (uint32_t)n : (uint32_t)(n >> 32);
+    if (!buffered || second) {  // the new output was consumed (at least its low half)
+        r.s_lo = lo;
+        r.s_hi = hi;
+        r.uinteger = (uint32_t)(n >> 32);
+    }
+    has32 = (buffered == second) ? 1 : 0;
+    r.dirty = true;
+    return second ? (int)(v2 >> 31) : -1;  // integers(0, 2) = (v * 2) >> 32, never rejects (threshold 0)
+}
+
+// `a = integers(0, 5); b = integers(0, 5)`  (physics.py:218 for player 1 then player 2)
+__device__ __forceinline__ void rng_integers5_twice(Rng &r, int &has32, int &a, int &b) {
+    uint64_t lo = r.s_lo, hi = r.s_hi;
+    pcg_step(lo, hi, r.inc_lo, r.inc_hi);
+    const uint64_t x = hi ^ lo;
+    const unsigned rot = (unsigned)(hi >> 58);
+    const uint64_t n = (x >> rot) | (x << ((64u - rot) & 63u));
+    const bool buffered = has32 != 0;
+    const uint64_t m1 = (uint64_t)(buffered ? r.uinteger : (uint32_t)n) * 5u;
+    const uint64_t m2 = (uint64_t)(buffered ? (uint32_t)n : (uint32_t)(n >> 32)) * 5u;
+    if ((uint32_t)m1 < 5u || (uint32_t)m2 < 5u) {  // the rejection test applies: general path
+        a = rng_integers<5>(r, has32);
+        b = rng_integers<5>(r, has32);
+        return;
+    }
+    // buffered: the second draw stepped and buffered the new high half; otherwise the first did and the
+    // second consumed it — has32 ends where it started, uinteger holds the new high half either way
+    r.s_lo = lo;
+    r.s_hi = hi;
+    r.uinteger = (uint32_t)(n >> 32);
+    r.dirty = true;
+    a = (int)(m1 >> 32);
+    b = (int)(m2 >> 32);
+}
+
 // ---- SeedSequence(seed) -> PCG64 state/inc (numpy bit_generator.pyx) ----------------------
 __device__ __forceinline__ uint32_t ss_hashmix(uint32_t value, uint32_t &hash_const) {
     value ^= hash_const;

@@ -208,6 +208,38 @@ def test_random_states_one_step(emul):
             assert np.array_equal(e.export(), o.state)
 
 
+def test_rng_rejection_corners(emul):
+    """The fused draw sites (two boldness draws; `integers(0, 20)` then `integers(0, 2)`) leave through the
+    general path when Lemire's rejection test applies to a value they look at. Force it: the buffered half
+    is set to the values v whose v * HIGH mod 2**32 < HIGH (and their neighbours) for every bound in use,
+    on states that are about to start a round or stand within reach of their target."""
+    rng = np.random.default_rng(7)
+    corners = sorted({(k * 2**32 + h - 1) // h + d for h in (2, 3, 5, 20) for k in range(h) for d in (-1, 0, 1)}
+                     - {-1, 2**32})
+    corners = np.array([c % 2**32 for c in corners], dtype=np.uint64)
+    n = 4096
+    for name in ("ai_vs_ai", "ai_p2_random_serve", "random18"):
+        cfg = CONFIGS[name]
+        o = po.OracleVecEnv(n, seed=11, **cfg)
+        o.reset()
+        for t in range(40):  # into play: some envs near a round end, computer players at their targets
+            o.step(synth_actions_numpy(3, 0, n, t, 18))
+        st = o.state.copy()
+        st[:, 39] = rng.integers(0, 2, n)  # round_ended: half of the envs draw their new-round values next
+        st[:, 39] *= 1 - st[:, 40]
+        st[:, 50] = 1
+        st[:, 51] = corners[rng.integers(0, len(corners), n)].astype(np.uint32).view(np.int32)
+        e = EmulVecEnv(emul, n, 0, **cfg)
+        e.load(st)
+        o.state[:] = st
+        for t in range(6):
+            a = synth_actions_numpy(5, 0, n, t, 18)
+            obs, base_r, done = e.step(a)
+            o_obs, o_rew, o_done = o.step(a)
+            assert np.array_equal(obs, o_obs), (name, t)
+            assert np.array_equal(e.export(), o.state), (name, t)
+
+
 def test_normalisation_is_correctly_rounded_for_every_representable_value(emul):
     """The division-free float32 NormalizeObservation (reciprocal multiply + two FMAs) equals
     float32(float64 division) — what `.astype(float32)` of the reference wrapper's output gives — for
