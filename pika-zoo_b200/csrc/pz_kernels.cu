@@ -17,8 +17,13 @@
 #include "pz_device.cuh"
 #include "pz_kernels.cuh"
 
-#ifndef PZ_ROLLOUT_MIN_CTAS
-#define PZ_ROLLOUT_MIN_CTAS 5  // 96 registers, no spills: 2.64 ms per 64 frames x 1 M envs (4: 2.94 ms; 6: 80 registers with 176 B of spills, 3.25 ms)
+// Register cap of the rollout kernel. Its shared memory is 1,280 B per warp, so registers alone set the
+// occupancy, and the frame loop is latency-bound (issue slots 65 % busy at 20 warps per SM): a tighter cap
+// with a few spills to L1 wins. Measured per 64 frames x 1 M envs, computer vs computer (B200):
+// 104 regs 2.69 ms | 96 (no spills, 20 warps) 2.36 | 88 2.53 | 80 2.36 | 72 (188 B of spill loads, 28 warps) 2.23 |
+// 64 2.23-2.26 | 56 2.43 | 48 3.09.
+#ifndef PZ_ROLLOUT_MAXNREG
+#define PZ_ROLLOUT_MAXNREG 72
 #endif
 
 namespace pz {
@@ -52,14 +57,8 @@ __device__ __noinline__ bool emit_obs_cold(int32_t *state, int64_t n, int64_t en
 #endif
 constexpr int kRolloutThreads = PZ_ROLLOUT_THREADS;
 
-#ifdef PZ_ROLLOUT_MAXNREG
-#define PZ_ROLLOUT_BOUNDS __maxnreg__(PZ_ROLLOUT_MAXNREG)
-#else
-#define PZ_ROLLOUT_BOUNDS __launch_bounds__(kRolloutThreads, PZ_ROLLOUT_MIN_CTAS)
-#endif
-
 template <int AI_MASK>
-__global__ void PZ_ROLLOUT_BOUNDS pz_rollout_kernel(const __grid_constant__ KParams P) {
+__global__ void __maxnreg__(PZ_ROLLOUT_MAXNREG) pz_rollout_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(16) int stage[kRolloutThreads / 32][kAiScratchInts];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t i = P.begin + (int64_t)blockIdx.x * kRolloutThreads + threadIdx.x;

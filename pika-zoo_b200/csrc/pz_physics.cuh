@@ -61,9 +61,9 @@ struct DrawCtxT {
         ensure();
         return rng_integers<HIGH>(r, has32);
     }
-    __device__ __forceinline__ int integers20_then_2(int &has32) {
+    __device__ __forceinline__ void computer_draws(int &has32, bool near, bool search, int &standby, int &y_first) {
         ensure();
-        return rng_integers20_then_2(r, has32);
+        rng_computer_draws(r, has32, near, search, standby, y_first);
     }
     __device__ __forceinline__ void integers5_twice(int &has32, int &a, int &b) {
         ensure();
@@ -364,12 +364,8 @@ __device__ __forceinline__ void computer_decide(unsigned mask, Env &e, Ctx &d, c
         if ((b.land <= left_boundary || b.land >= far_boundary) && p.standby == 0)
             virt = left_boundary + kGroundHalfWidth / 2;
     }
-    if (iabs(virt - p.x) > p.bold + 8) {
-        in.xdir = (p.x < virt) ? 1 : -1;
-    } else {
-        const int v = d.integers20_then_2(e.has32);  // :728 `integers(0, 20) == 0`, then :729 `integers(0, 2)`
-        if (v >= 0) p.standby = v;
-    }
+    const bool near = iabs(virt - p.x) <= p.bold + 8;
+    if (!near) in.xdir = (p.x < virt) ? 1 : -1;
 
     bool search = false;
     if (p.state == 0) {
@@ -390,8 +386,12 @@ __device__ __forceinline__ void computer_decide(unsigned mask, Env &e, Ctx &d, c
     // side effects, so all 6 are evaluated and then scanned in the reference's order: from the
     // memoised table when the ball is inside its domain, otherwise iteratively, spread over the
     // lanes of the warp (one (searcher, candidate) pair per lane and pass, through the warp's scratch).
-    int y_first = 0;
-    if (search) y_first = (d.template integers<2>(e.has32) == 0) ? -1 : 1;  // :795 scan order of y_direction
+    // This frame's draws in the reference's order: :728 `integers(0, 20) == 0` and then :729 `integers(0, 2)`
+    // if near, :795 `integers(0, 2)` (scan order of y_direction) if a power hit is searched for.
+    int standby_draw, y_draw;
+    d.computer_draws(e.has32, near, search, standby_draw, y_draw);
+    if (standby_draw >= 0) p.standby = standby_draw;
+    const int y_first = search ? (y_draw == 0 ? -1 : 1) : 0;
     const int ayv = iabs(b.yv);
     bool found = false;
     // memoised: one table load per (searcher, candidate) pair, the pairs of all searching lanes spread

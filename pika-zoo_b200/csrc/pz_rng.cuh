@@ -68,29 +68,40 @@ __device__ __forceinline__ int rng_integers(Rng &r, int &has32) {
 // selects. Lemire's rejection (leftover < HIGH, p < 5e-9 per draw) leaves through the general path from
 // the untouched stream, so the values and the stream are those of the reference's calls, always.
 
-// `integers(0, 20) == 0 ? integers(0, 2) : -1`  (physics.py:728-729)
-__device__ __forceinline__ int rng_integers20_then_2(Rng &r, int &has32) {
+// All draws of one computer player in one frame (let_computer_decide_user_input, physics.py:689-771); which of
+// them happen is known before the first one:
+//   near   (within reach of the target, :727):  a = integers(0, 20) (:728); if a == 0: standby = integers(0, 2) (:729)
+//   search (a power hit is considered, :766):   y_first = integers(0, 2) (decide_whether_input_power_hit, :795)
+// standby = -1 when :729 did not run. Two halves at most are served from the one speculative step; the
+// 1-in-20 frame that needs three takes the general path, like the rejection corner.
+__device__ __forceinline__ void rng_computer_draws(Rng &r, int &has32, bool near, bool search, int &standby,
+                                                   int &y_first) {
     uint64_t lo = r.s_lo, hi = r.s_hi;
     pcg_step(lo, hi, r.inc_lo, r.inc_hi);
     const uint64_t x = hi ^ lo;
     const unsigned rot = (unsigned)(hi >> 58);
     const uint64_t n = (x >> rot) | (x << ((64u - rot) & 63u));
     const bool buffered = has32 != 0;
-    const uint64_t m1 = (uint64_t)(buffered ? r.uinteger : (uint32_t)n) * 20u;
-    if ((uint32_t)m1 < 20u) {  // the rejection test applies: general path
-        const int first = rng_integers<20>(r, has32);
-        return first == 0 ? rng_integers<2>(r, has32) : -1;
+    const uint32_t h0 = buffered ? r.uinteger : (uint32_t)n;                // the next two 32-bit halves
+    const uint32_t h1 = buffered ? (uint32_t)n : (uint32_t)(n >> 32);
+    const uint64_t m1 = (uint64_t)h0 * 20u;
+    const bool second = near && (uint32_t)(m1 >> 32) == 0u;
+    const int k = (near ? 1 : 0) + (second ? 1 : 0) + (search ? 1 : 0);  // halves consumed
+    if ((near && (uint32_t)m1 < 20u) || k == 3) {  // general path, from the untouched stream
+        standby = -1;
+        if (near && rng_integers<20>(r, has32) == 0) standby = rng_integers<2>(r, has32);
+        if (search) y_first = rng_integers<2>(r, has32);
+        return;
     }
-    const bool second = (uint32_t)(m1 >> 32) == 0u;
-    const uint32_t v2 = buffered ? (uint32_t)n : (uint32_t)(n >> 32);
-    if (!buffered || second) {  // the new output was consumed (at least its low half)
+    standby = second ? (int)(h1 >> 31) : -1;       // integers(0, 2) = (v * 2) >> 32, never rejects (threshold 0)
+    y_first = (int)((near ? h1 : h0) >> 31);       // meaningful only if search (then `second` is false)
+    if (buffered ? (k == 2) : (k != 0)) {          // the new output was consumed (at least its low half)
         r.s_lo = lo;
         r.s_hi = hi;
         r.uinteger = (uint32_t)(n >> 32);
     }
-    has32 = (buffered == second) ? 1 : 0;
-    r.dirty = true;
-    return second ? (int)(v2 >> 31) : -1;  // integers(0, 2) = (v * 2) >> 32, never rejects (threshold 0)
+    has32 = (buffered ? 1 : 0) ^ (k & 1);
+    if (k != 0) r.dirty = true;
 }
 
 // `a = integers(0, 5); b = integers(0, 5)`  (physics.py:218 for player 1 then player 2)
