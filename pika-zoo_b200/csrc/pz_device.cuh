@@ -304,8 +304,8 @@ __device__ __forceinline__ bool episode_truncated(const KParams &P, const Env &e
 constexpr int kAiScratchInts = 320;  // computer_decide: 32 x int4 inputs + 32 x 6 results per warp
 
 // Resident CTAs per SM the register allocation is held to (0 = leave it to ptxas). Without computer
-// players: 2-byte observation rows stage half as much shared memory, so six CTAs fit if the registers
-// do (80 instead of 96: 48 us against 53-60 us per million envs); feature-major rows use no shared memory
+// players: 2-byte observation rows stage half as much shared memory, so seven CTAs fit if the registers
+// do (72 with a few spills to L1; the kernel waits on its loads, so warps in flight count); feature-major rows use no shared memory
 // at all and run best at eight (64 registers). Measured sweeps in DESIGN.md §4.
 #ifndef PZ_FM_MIN_CTAS
 #define PZ_FM_MIN_CTAS 8
@@ -314,7 +314,7 @@ constexpr int kAiScratchInts = 320;  // computer_decide: 32 x int4 inputs + 32 x
 #define PZ_AI_MIN_CTAS 5  // 94 registers, no spills: 72 us per million envs (4: 101 registers, 79 us; 6: 80 with spills, 77 us)
 #endif
 #ifndef PZ_HALF_MIN_CTAS
-#define PZ_HALF_MIN_CTAS 6
+#define PZ_HALF_MIN_CTAS 7  // 72 registers, 28 B of spill loads: 47.6 us per million envs (6: 80 registers, 49.6 us; 8: 64, 53.4 us)
 #endif
 template <int AI_MASK, int OBS_DT, int LAYOUT>
 constexpr int step_min_ctas() {
