@@ -80,23 +80,26 @@ class raw_env:
 
     # -- internals ---------------------------------------------------------------------------
     def _build(self):
+        # host_mapped: state, observations, rewards, ... of the one env live in pinned host memory that the
+        # kernel addresses directly, so a step is one launch and ONE stream synchronisation, no copies
         self._vec = PikaVecEnv(
             1, device=self._device, seed=self._seed_value, autoreset=False, reward_dtype=torch.float64,
             simplify_action=self._simplify_action, reward_by_ball_position=self._reward_by_ball_position,
             reward_in_normal_state=self._reward_in_normal_state, normal_state_first=self._normal_state_first,
             normalize_observation=self._normalize_observation,
             obs_dtype=torch.float64 if self._normalize_observation else torch.int32,
-            record_episode_statistics=self._record_episode_statistics,
+            record_episode_statistics=self._record_episode_statistics, track_stats=False, host_mapped=True,
             **self._kwargs,
         )
-        self._actions = torch.zeros((1, 2), dtype=torch.int32, device=self._vec.device)
-        # pinned host mirrors: one step = one async H2D, the kernel, four async D2H and ONE stream sync
         v = self._vec
-        self._h_actions = torch.zeros((1, 2), dtype=torch.int32).pin_memory()
-        self._h_obs = torch.zeros(tuple(v.obs.shape), dtype=v.obs.dtype).pin_memory()
-        self._h_reward = torch.zeros((1, 2), dtype=torch.float64).pin_memory()
-        self._h_done = torch.zeros((1,), dtype=torch.uint8).pin_memory()
-        self._h_state = torch.zeros((v.state.numel(),), dtype=torch.int32).pin_memory()
+        self._actions = torch.zeros((1, 2), dtype=torch.int32).pin_memory()
+        # numpy views of the mapped buffers, read after the synchronisation
+        self._np_actions = self._actions.numpy()
+        self._np_obs = v.obs.numpy()
+        self._np_reward = v.reward.numpy()
+        self._np_done = v.done_u8.numpy()
+        self._np_state = v.state.numpy()
+        self._sync = torch.cuda.current_stream(v.device).synchronize
 
     def _configure(self, **opts):
         """Used by the wrappers to fuse themselves into the kernel configuration."""
@@ -107,22 +110,16 @@ class raw_env:
             self._build()
             self._vec.load_state_dict(state)
 
-    def _fetch(self, with_step_outputs: bool):
-        """async copies of this call's outputs into the pinned mirrors, then one synchronisation"""
-        v = self._vec
-        self._h_obs.copy_(v.obs, non_blocking=True)
-        self._h_state.copy_(v.state, non_blocking=True)
-        if with_step_outputs:
-            self._h_reward.copy_(v.reward, non_blocking=True)
-            self._h_done.copy_(v.done_u8, non_blocking=True)
-        torch.cuda.current_stream(v.device).synchronize()
+    def _fetch(self):
+        """wait for the launch; the outputs are then in the mapped buffers"""
+        self._sync()
         # scores live in the packed state's ENV word (csrc/pz_state.cuh: G1.w = score1:10 | score2:10 << 10 | ...)
-        env_word = int(self._h_state[7]) & 0xFFFFFFFF
+        env_word = int(self._np_state[7]) & 0xFFFFFFFF
         self.scores[0], self.scores[1] = env_word & 1023, (env_word >> 10) & 1023
 
     def _obs_dict(self) -> Dict[str, np.ndarray]:
         # the reference returns np.array of Python ints (int64); NormalizeObservation makes them float64
-        o = self._h_obs[0].numpy()
+        o = self._np_obs[0]
         o = o.copy() if self._normalize_observation else o.astype(np.int64)
         return {self.possible_agents[0]: o[0], self.possible_agents[1]: o[1]}
 
@@ -138,7 +135,7 @@ class raw_env:
             self._build()
         self.agents = self.possible_agents[:]
         self._vec.reset()
-        self._fetch(with_step_outputs=False)
+        self._fetch()
         return self._obs_dict(), self._get_infos()
 
     def step(self, actions):
@@ -151,12 +148,11 @@ class raw_env:
         for v in a:
             if not 0 <= v < n:
                 raise IndexError(f"action {v} is out of range for Discrete({n})")
-        self._h_actions[0, 0], self._h_actions[0, 1] = a[0], a[1]
-        self._actions.copy_(self._h_actions, non_blocking=True)
+        self._np_actions[0, 0], self._np_actions[0, 1] = a[0], a[1]
         self._vec.step(self._actions)
-        self._fetch(with_step_outputs=True)
-        r = self._h_reward[0].tolist()
-        terminated = bool(self._h_done[0])
+        self._fetch()
+        r = self._np_reward[0].tolist()
+        terminated = bool(self._np_done[0])
         observations = self._obs_dict()
         if self._reward_by_ball_position is None and not isinstance(self._reward_in_normal_state, float):
             r = [int(r[0]), int(r[1])]  # the reference's base rewards are Python ints

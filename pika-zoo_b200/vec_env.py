@@ -132,6 +132,7 @@ class PikaVecEnv:
         obs_layout: str = "env_major",
         obs_feature_rows: int = 35,
         pdl: bool = True,
+        host_mapped: bool = False,
     ):
         """Beyond the reference's constructor arguments:
 
@@ -148,6 +149,11 @@ class PikaVecEnv:
           applied outside RewardByBallPosition, or inside it with normal_state_first=True.
         max_episode_frames: truncate episodes that reach this many step() calls (0 = never, like the
           reference); `self.truncated` [N] bool reports it and the next call resets the env.
+        host_mapped: every per-env buffer (state, obs, reward, done, episode statistics) is pinned host memory,
+          which the device addresses directly (unified addressing): the kernels read and write it over PCIe, so a
+          host-driven step of a tiny batch is one launch and one stream synchronisation, no copies — the
+          single-env facade's mode. `step()` then takes a pinned CPU action tensor and the returned tensors are
+          CPU tensors, valid after a synchronisation of the stream. Pointless for large batches.
         record_episode_statistics: fuses RecordEpisodeStatistics (record_episode_statistics.py:17-40):
           `self.episode_return` [N, 2] float64 and `self.episode_length` [N] int32 are valid for env i
           on the call where terminated[i] (or truncated[i]) is set.
@@ -187,27 +193,35 @@ class PikaVecEnv:
         self.max_episode_frames = int(max_episode_frames)
         self.num_actions = 13 if simplify_action else 18
         n = self.num_envs
+        self.host_mapped = bool(host_mapped)
+
+        def zeros(shape, dtype):
+            if self.host_mapped:  # cudaHostAlloc'ed by torch: device-accessible at the same address
+                return torch.zeros(shape, dtype=dtype).pin_memory()
+            return torch.zeros(shape, dtype=dtype, device=self.device)
+
+        self._io_device = torch.device("cpu") if self.host_mapped else self.device
         with torch.cuda.device(self.device):
-            self.state = torch.zeros(_lib.STATE_WORDS * n, dtype=torch.int32, device=self.device)
+            self.state = zeros(_lib.STATE_WORDS * n, torch.int32)
             self.obs_layout = obs_layout
             if obs_layout == "feature_major":
-                self.obs = torch.zeros((2, int(obs_feature_rows), n), dtype=obs_dtype, device=self.device)
+                self.obs = zeros((2, int(obs_feature_rows), n), obs_dtype)
             else:
-                self.obs = torch.zeros((n, 2, _lib.OBS_WORDS), dtype=obs_dtype, device=self.device)
-            self.reward = torch.zeros((n, 2), dtype=reward_dtype, device=self.device)
-            self.done_u8 = torch.zeros((n,), dtype=torch.uint8, device=self.device)
+                self.obs = zeros((n, 2, _lib.OBS_WORDS), obs_dtype)
+            self.reward = zeros((n, 2), reward_dtype)
+            self.done_u8 = zeros((n,), torch.uint8)
             self.stats = torch.zeros(_lib.NUM_STATS, dtype=torch.int64, device=self.device) if track_stats else None
             self.episode_return = self.episode_length = self._truncated_u8 = None
             self._ep = None
             if self.record_episode_statistics or self.max_episode_frames > 0:
                 self._ep = _lib.PzEpisodeIo()
                 if self.record_episode_statistics:
-                    self.episode_return = torch.zeros((n, 2), dtype=torch.float64, device=self.device)
-                    self.episode_length = torch.zeros((n,), dtype=torch.int32, device=self.device)
+                    self.episode_return = zeros((n, 2), torch.float64)
+                    self.episode_length = zeros((n,), torch.int32)
                     self._ep.episode_return_dev = self.episode_return.data_ptr()
                     self._ep.episode_length_dev = self.episode_length.data_ptr()
                 if self.max_episode_frames > 0:
-                    self._truncated_u8 = torch.zeros((n,), dtype=torch.uint8, device=self.device)
+                    self._truncated_u8 = zeros((n,), torch.uint8)
                     self._ep.truncated_dev = self._truncated_u8.data_ptr()
             _lib.check(
                 self.lib.pz_seed(self.state.data_ptr(), n, self.seed & (2**64 - 1), self.first_env, self._stream()),
@@ -259,8 +273,10 @@ class PikaVecEnv:
             if actions.dtype != self.action_dtype:
                 raise TypeError(f"actions must be {self.action_dtype} (got {actions.dtype}); "
                                 "pass action_dtype= to the constructor")
-            if actions.device != self.device or actions.shape != self._action_shape:
-                raise ValueError(f"actions must be a [{self.num_envs}, 2] tensor on {self.device}")
+            if actions.device != self._io_device or actions.shape != self._action_shape:
+                raise ValueError(f"actions must be a [{self.num_envs}, 2] tensor on {self._io_device}")
+            if self.host_mapped and not actions.is_pinned():
+                raise ValueError("host_mapped: actions must live in pinned host memory (tensor.pin_memory())")
             if not actions.is_contiguous():
                 actions = actions.contiguous()
             a_ptr = actions.data_ptr()
@@ -312,7 +328,7 @@ class PikaVecEnv:
         return out
 
     def import_state(self, unpacked: torch.Tensor) -> None:
-        u = unpacked.to(device=self.device, dtype=torch.int32).contiguous()
+        u = unpacked.to(device=self.device, dtype=torch.int32).contiguous()  # staged on the device in every mode
         assert tuple(u.shape) == (self.num_envs, _lib.UNPACKED_WORDS)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pz_import_state(self.state.data_ptr(), self.num_envs, u.data_ptr(), self._stream()),

@@ -94,3 +94,37 @@ def test_wrappers_fused_in_kernel(pikazoo_v0):
     with pytest.raises(IndexError):
         env.reset()
         env.step({"player_1": 13, "player_2": 0})
+
+
+@pytest.mark.parametrize("n", [1, 100, 4096])
+def test_host_mapped_buffers_equal_device_buffers(cuda_lib, n):
+    """PikaVecEnv(host_mapped=True): every per-env buffer is pinned host memory addressed by the kernels
+    directly (the facade's mode; full warps leave through the bulk copy, ragged tails through vector stores).
+    Same trajectories, bit for bit, as the device-resident env, with computer players and statistics on."""
+    import torch
+
+    import pikazoo_b200
+
+    kw = dict(seed=77, winning_score=3, serve="random", is_player2_computer=True, record_episode_statistics=True,
+              max_episode_frames=400)
+    dev = pikazoo_b200.PikaVecEnv(n, **kw)
+    host = pikazoo_b200.PikaVecEnv(n, host_mapped=True, **kw)
+    assert host.obs.device.type == "cpu" and host.obs.is_pinned()
+    o_d, o_h = dev.reset(), host.reset()
+    torch.cuda.synchronize()
+    assert torch.equal(o_d.cpu(), o_h)
+    g = torch.Generator().manual_seed(5)
+    a_h = torch.zeros((n, 2), dtype=torch.int32).pin_memory()
+    for t in range(600):
+        a_h.copy_(torch.randint(0, 18, (n, 2), generator=g, dtype=torch.int32))
+        od, rd, dd = dev.step(a_h.cuda())
+        oh, rh, dh = host.step(a_h)
+        torch.cuda.synchronize()
+        assert torch.equal(od.cpu(), oh) and torch.equal(rd.cpu(), rh) and torch.equal(dd.cpu(), dh), t
+        assert torch.equal(dev.truncated.cpu(), host.truncated)
+    assert torch.equal(dev.state.cpu(), host.state)
+    assert torch.equal(dev.episode_return.cpu(), host.episode_return)
+    assert torch.equal(dev.export_state().cpu(), host.export_state().cpu())
+    assert dev.stats_dict() == host.stats_dict()
+    with pytest.raises(ValueError):
+        host.step(torch.zeros((n, 2), dtype=torch.int32))  # not pinned
