@@ -440,7 +440,36 @@ def run_b200_arm(args):
             "ms_per_step": float(tt.item()) / 50, "env_steps_per_sec": n5 * world * 50 / (float(tt.item()) * 1e-3),
             "of_which_env_step_us": env_only["us_per_launch"],
             "note": "the policy is ordinary PyTorch (cuBLAS + elementwise kernels), not the product"}
-        del v, pol, acts
+        del v, acts
+        # the same loop acting through the library's fused policy kernel (pz_policy_mlp_act: both layers and the
+        # categorical sample in one pass over the observations, uint8 actions straight into the step kernel)
+        from pikazoo_b200.policy import FusedActor
+
+        v = pikazoo_b200.PikaVecEnv(n5, device=dev, seed=5, first_env=rank * n5, winning_score=5, serve="random",
+                                    obs_dtype=torch.bfloat16, normalize_observation=True, action_dtype=torch.uint8,
+                                    obs_layout="feature_major", obs_feature_rows=40)
+        actor = FusedActor(pol, v, seed=1)
+        v.reset()
+        policy_rollout(v, actor, 10)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        policy_rollout(v, actor, 200)
+        b.record()
+        torch.cuda.synchronize()
+        tf = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        a.record()
+        for _ in range(200):
+            actor(v.obs)
+        b.record()
+        torch.cuda.synchronize()
+        variants["configs[4]_fused_policy_kernel_loop_2M_envs_per_gpu"] = {
+            "ms_per_step": float(tf.item()) / 200, "env_steps_per_sec": n5 * world * 200 / (float(tf.item()) * 1e-3),
+            "of_which_policy_kernel_us": a.elapsed_time(b) * 1e3 / 200,
+            "note": "policy = pz_policy_mlp_act (mma.sync bf16, one pass over the 160 B of observations per env)"}
+        del v, pol, actor
         return variants
 
     variants = None

@@ -17,7 +17,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import pikazoo_b200  # noqa: E402
-from pikazoo_b200.policy import MLPPolicy, policy_rollout  # noqa: E402
+from pikazoo_b200.policy import FusedActor, MLPPolicy, policy_rollout  # noqa: E402
 
 
 def main():
@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 21)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--stats-every", type=int, default=50)
+    ap.add_argument("--actor", choices=["fused", "eager"], default="fused",
+                    help="fused: the library's policy kernel (pz_policy_mlp_act); eager: MLPPolicy.act in PyTorch")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -34,17 +36,19 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     env = pikazoo_b200.make_sharded_env(a.envs_per_gpu * world, rank, world, dev, seed=5, winning_score=5,
                                         serve="random", obs_dtype=torch.bfloat16, normalize_observation=True,
-                                        action_dtype=torch.int64, obs_layout="feature_major", obs_feature_rows=40)
+                                        action_dtype=torch.uint8 if a.actor == "fused" else torch.int64,
+                                        obs_layout="feature_major", obs_feature_rows=40)
     policy = MLPPolicy(device=dev)
+    act = FusedActor(policy, env, seed=1) if a.actor == "fused" else policy.act
     env.reset()
-    policy_rollout(env, policy.act, 10)
+    policy_rollout(env, act, 10)
     pikazoo_b200.allreduce_stats(env.stats.clone())  # NCCL communicator set-up happens on the first collective
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     done_steps = 0
     while done_steps < a.steps:
         k = min(a.stats_every, a.steps - done_steps)
-        policy_rollout(env, policy.act, k)
+        policy_rollout(env, act, k)
         done_steps += k
         stats = env.stats.clone()
         pikazoo_b200.allreduce_stats(stats)  # the one collective: 16 int64 over NVLink
@@ -53,7 +57,7 @@ def main():
     if rank == 0:
         names = pikazoo_b200._lib.STAT_NAMES
         print({n: int(stats[i]) for i, n in enumerate(names)})
-        print(f"{a.envs_per_gpu * world * a.steps / dt / 1e9:.2f} G env-steps/s over {world} GPU(s), policy in the loop")
+        print(f"{a.envs_per_gpu * world * a.steps / dt / 1e9:.2f} G env-steps/s over {world} GPU(s), {a.actor} policy in the loop")
     if world > 1:
         dist.destroy_process_group()
 

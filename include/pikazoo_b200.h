@@ -215,6 +215,25 @@ int pz_host_stats(pz_host_ctx *ctx, int64_t stats_host[PZ_NUM_STATS]);
 int32_t *pz_host_state_dev(pz_host_ctx *ctx);
 void pz_host_destroy(pz_host_ctx *ctx);
 
+/* ---- caller side: the MLP policy of BASELINE.json configs[4], evaluated and sampled in one kernel ----
+ * The reference has no policy; this is the product's own helper for the loop `obs -> policy -> step`
+ * (pika-zoo_b200/policy.py), fed by the feature-major bf16 observations of pz_step (PZ_LAYOUT_FEATURE_MAJOR).
+ *   obs_dev      bf16 [2][rows][ld]: element (agent, feature k, env) at (agent * rows + k) * ld + env; rows
+ *                0 .. features-1 enter the contraction (policy.py folds the biases in through a row of ones)
+ *   w1_dev       bf16 [2][hidden_rows][features], w2_dev bf16 [2][n_actions][w2_cols] (row-major, per agent)
+ *   logits       = W2 . relu(W1 . x), fp32 accumulation, hidden activations rounded to bf16
+ *   actions_dev  [n][2] of action_dtype (PZ_ACT_*): argmax_a(logits[a] + Gumbel(seed, step, first_env + env,
+ *                agent, a)) — a categorical sample from softmax(logits), reproducible from the counters
+ *                (restated in policy.py gumbel_noise_reference); greedy != 0: plain argmax
+ *   logits_dev   optional fp32 [n][2][n_actions] */
+#define PZ_POLICY_MAX_FEATURES 48
+#define PZ_POLICY_MAX_HIDDEN 80
+#define PZ_POLICY_MAX_ACTIONS 24
+int pz_policy_mlp_act(const void *obs_dev, int64_t n, int64_t ld, int32_t rows, const void *w1_dev,
+                      int32_t hidden_rows, int32_t features, const void *w2_dev, int32_t n_actions,
+                      int32_t w2_cols, uint64_t seed, uint64_t step, uint64_t first_env, void *actions_dev,
+                      int32_t action_dtype, int32_t greedy, float *logits_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -134,6 +134,9 @@ def load() -> ctypes.CDLL:
     L.pz_host_state_dev.restype = vp
     L.pz_host_destroy.argtypes = [vp]
     L.pz_host_destroy.restype = None
+    # caller side: fused MLP policy (pz_policy.cu)
+    L.pz_policy_mlp_act.argtypes = [vp, i64, i64, i32, vp, i32, i32, vp, i32, i32, u64, u64, u64, vp, i32, i32, vp, vp]
+    L.pz_policy_mlp_act.restype = ctypes.c_int
     if L.pz_version() != VERSION or L.pz_state_words() != STATE_WORDS or L.pz_unpacked_words() != UNPACKED_WORDS:
         raise PikaLibraryError("libpikazoo_b200.so does not match this Python package (rebuild it)")
     _lib = L

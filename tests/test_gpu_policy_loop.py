@@ -114,3 +114,143 @@ def test_step_loop_is_cuda_graph_capturable(cuda_lib):
     assert int(frame_g) == int(frame_e) == K * (replays + 2)
     assert torch.equal(graphed.export_state(), eager.export_state())
     assert torch.equal(graphed.obs, eager.obs) and torch.equal(graphed.stats, eager.stats)
+
+
+# ---- the fused policy kernel (csrc/pz_policy.cu) -------------------------------------------------------
+def _reference_logits(policy, obs):
+    """[N, 2, A] float32 from plain PyTorch fp32 arithmetic on the same bf16 values, hidden activations rounded
+    to bf16 where the kernel rounds them."""
+    x = obs[:, : policy.K_PAD, :].float()                                 # [2, 40, N]
+    h = torch.bmm(policy.w1.float(), x).to(torch.bfloat16).float().relu_()  # [2, 72, N]
+    return torch.bmm(policy.w2.float(), h).permute(2, 0, 1).contiguous()
+
+
+def _played_env(n, **kw):
+    import pikazoo_b200
+
+    env = pikazoo_b200.PikaVecEnv(n, seed=31, winning_score=5, serve="random", obs_dtype=torch.bfloat16,
+                                  normalize_observation=True, obs_layout="feature_major", obs_feature_rows=40, **kw)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for _ in range(40):  # spread the envs over different states
+        env.step(torch.randint(0, 18, (n, 2), generator=g, device="cuda", dtype=env.action_dtype))
+    return env
+
+
+@pytest.mark.parametrize("n", [64, 1000, 4096 + 8, 100_003])
+def test_fused_policy_logits_and_greedy_actions(cuda_lib, n):
+    """Floating point: the fused kernel's logits against a PyTorch fp32 reference of the same network.
+    Tolerance 2e-3 absolute (fp32 sums in another order can round a hidden activation to the neighbouring
+    bf16, 2^-8 relative, which reaches a logit through one weight of magnitude ~0.1). Greedy actions are the
+    arg-max of the kernel's own logits, exactly. Sizes cover full tiles, the ragged last tile and the
+    unaligned-row path (n % 8 != 0)."""
+    from pikazoo_b200.policy import MLPPolicy
+
+    env = _played_env(n)
+    policy = MLPPolicy(device=env.device, seed=3)
+    logits = torch.full((n, 2, 18), float("nan"), device="cuda")
+    for dtype in (torch.uint8, torch.int32, torch.int64):
+        a = policy.act_fused(env.obs, step=0, action_dtype=dtype, greedy=True, logits_out=logits)
+        assert a.dtype == dtype and a.shape == (n, 2)
+        assert torch.equal(a.long(), logits.argmax(dim=2))
+    ref = _reference_logits(policy, env.obs)
+    assert torch.isfinite(logits).all()
+    assert (logits - ref).abs().max().item() < 2e-3
+    # and the eager policy (bf16 logits) agrees to bf16 resolution
+    eager = policy.logits_t(env.obs).permute(2, 0, 1).float()
+    assert (logits - eager).abs().max().item() < 0.05
+
+
+def test_fused_policy_sampling_is_the_documented_argmax(cuda_lib):
+    """actions == argmax(logits + Gumbel noise) with the noise restated in numpy from the counters. The kernel
+    takes its logarithms from the hardware approximation, so keys differ by a few float32 ulp: every mismatch
+    must be a near-tie, and there must be next to none."""
+    from pikazoo_b200.policy import MLPPolicy, gumbel_noise_reference
+
+    n = 50_000
+    env = _played_env(n)
+    policy = MLPPolicy(device=env.device, seed=4)
+    logits = torch.empty((n, 2, 18), device="cuda")
+    for step, seed, first in ((0, 0, 0), (7, 123456789, 10**6), (2**40, 2**63 + 5, 3)):
+        a = policy.act_fused(env.obs, step=step, seed=seed, first_env=first, logits_out=logits).cpu().numpy()
+        keys = logits.cpu().numpy() + gumbel_noise_reference(seed, step, first, n, 18)
+        expect = keys.argmax(axis=2)
+        bad = np.argwhere(a != expect)
+        assert len(bad) <= 2 * n * 2e-4, len(bad)
+        for e, ag in bad:
+            top = np.sort(keys[e, ag])[-2:]
+            assert top[1] - top[0] < 1e-4
+    # a different step gives different samples; the same counters give the same ones
+    a0 = policy.act_fused(env.obs, step=1).clone()
+    assert not torch.equal(a0, policy.act_fused(env.obs, step=2))
+    assert torch.equal(a0, policy.act_fused(env.obs, step=1))
+
+
+def test_fused_policy_samples_follow_softmax(cuda_lib):
+    """Statistics: after reset every env shows the same observation, so N envs are N independent samples of
+    one categorical distribution; the frequencies must match softmax(logits) within five standard errors."""
+    import pikazoo_b200
+    from pikazoo_b200.policy import MLPPolicy
+
+    n = 400_000
+    env = pikazoo_b200.PikaVecEnv(n, seed=1, obs_dtype=torch.bfloat16, normalize_observation=True,
+                                  obs_layout="feature_major", obs_feature_rows=40)
+    env.reset()
+    assert bool((env.obs == env.obs[:, :, :1]).all())
+    policy = MLPPolicy(device=env.device, seed=9)
+    with torch.no_grad():
+        policy.w2.mul_(4.0)  # a peaked distribution
+    logits = torch.empty((n, 2, 18), device="cuda")
+    a = policy.act_fused(env.obs, step=11, seed=5, logits_out=logits)
+    p = torch.softmax(logits[0].double(), dim=1).cpu().numpy()  # [2, 18]
+    for agent in range(2):
+        freq = np.bincount(a[:, agent].cpu().numpy(), minlength=18) / n
+        se = np.sqrt(p[agent] * (1 - p[agent]) / n)
+        assert np.all(np.abs(freq - p[agent]) < 5 * se + 1e-6), (agent, freq, p[agent])
+
+
+def test_fused_actor_rollout_loop_matches_oracle(cuda_lib):
+    """configs[4] with the fused actor: uint8 actions straight from the policy kernel into the step kernel; the
+    oracle replays them."""
+    import pikazoo_b200
+    from pikazoo_b200.policy import FusedActor, MLPPolicy, policy_rollout
+
+    n, steps = 8192, 400
+    cfg = dict(winning_score=5, serve="random")
+    env = pikazoo_b200.PikaVecEnv(n, seed=16, obs_dtype=torch.bfloat16, normalize_observation=True,
+                                  action_dtype=torch.uint8, obs_layout="feature_major", obs_feature_rows=40, **cfg)
+    orc = po.OracleVecEnv(n, seed=16, **cfg)
+    actor = FusedActor(MLPPolicy(device=env.device, seed=3), env, seed=77)
+    env.reset(), orc.reset()
+    seen = {"done": 0, "distinct": set()}
+
+    def mirror(t, actions, obs, reward, done):
+        a = actions.cpu().numpy()
+        assert a.dtype == np.uint8 and a.max() < 18
+        orc.step(a.astype(np.int32))
+        assert np.array_equal(done.cpu().numpy(), orc.done.astype(bool)), t
+        seen["done"] += int(done.sum())
+        seen["distinct"] |= set(np.unique(a).tolist())
+
+    policy_rollout(env, actor, steps, on_step=mirror)
+    assert np.array_equal(env.export_state().cpu().numpy(), orc.state)
+    assert seen["done"] > n // 4 and len(seen["distinct"]) == 18
+
+
+def test_fused_policy_rejects_bad_arguments(cuda_lib):
+    from pikazoo_b200 import _lib
+    from pikazoo_b200.policy import MLPPolicy
+
+    policy = MLPPolicy(device="cuda", seed=1)
+    with pytest.raises(ValueError):
+        policy.act_fused(torch.zeros((64, 2, 35), dtype=torch.bfloat16, device="cuda"), step=0)  # env-major
+    obs = torch.zeros((2, 40, 64), dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros((64, 2), dtype=torch.uint8, device="cuda")
+    L = _lib.load()
+    args = [obs.data_ptr(), 64, 64, 40, policy.w1.data_ptr(), 72, 40, policy.w2.data_ptr(), 18, 72, 0, 0, 0,
+            out.data_ptr(), _lib.ACT_U8, 0, None, None]
+    assert L.pz_policy_mlp_act(*args) == 0
+    for pos, bad in ((6, 49), (5, 81), (8, 25), (9, 81), (3, 39), (14, 7), (2, 63), (0, None)):
+        b = list(args)
+        b[pos] = bad
+        assert L.pz_policy_mlp_act(*b) < 0, pos
