@@ -136,12 +136,14 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) pz_policy_mlp_kernel(const
         const int64_t env0 = tile * kTileEnvs;
         __syncthreads();  // the previous tile has been consumed (and, first time, the fills above are done)
         if (vec_ok && env0 + kTileEnvs <= P.n) {
-            constexpr int kPieces = kTileEnvs / 8;  // 16-byte pieces of 8 envs per row
-            const int rows2 = 2 * P.k1;           // (agent, feature) rows of the tile
-            for (int c = tid; c < rows2 * kPieces; c += kThreads) {
-                const int piece = c % kPieces, row = c / kPieces, a = row >= P.k1 ? 1 : 0, k = row - a * P.k1;
-                const __nv_bfloat16 *src = P.obs + ((int64_t)a * P.rows + k) * P.ld + env0 + piece * 8;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&xs[a][k][piece * 8])), "l"(src)
+            // 16-byte pieces of 8 envs; a pass of the CTA covers kThreads / kPieces (agent, feature) rows
+            constexpr int kPieces = kTileEnvs / 8, kRowsPerPass = kThreads / kPieces;
+            const int piece = tid % kPieces;
+            const __nv_bfloat16 *src0 = P.obs + env0 + piece * 8;
+            for (int row = tid / kPieces; row < 2 * P.k1; row += kRowsPerPass) {
+                const int a = row >= P.k1 ? 1 : 0, k = row - a * P.k1;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&xs[a][k][piece * 8])),
+                             "l"(src0 + (int64_t)(a * P.rows + k) * P.ld)
                              : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -200,10 +202,24 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) pz_policy_mlp_kernel(const
                 mma_bf16(c2[1], af, b01.z, b01.w);
                 mma_bf16(c2[2], af, b2.x, b2.y);
             }
-            // sample: this thread holds actions 8 nt + 2 t + {0, 1} of rows env_a (c[0], c[1]) and env_b (c[2], c[3])
+            // this thread holds actions 8 nt + 2 t + {0, 1} of rows env_a (c[0], c[1]) and env_b (c[2], c[3])
+            if (P.logits != nullptr) {  // launch-uniform
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int64_t env = h ? env_b : env_a;
+#pragma unroll
+                    for (int nt = 0; nt < kAP / 8; nt++)
+#pragma unroll
+                        for (int q = 0; q < 2; q++) {
+                            const int action = 8 * nt + 2 * t + q;
+                            if (action < P.n_actions && env < P.n)
+                                P.logits[(env * 2 + a) * P.n_actions + action] = c2[nt][2 * h + q];
+                        }
+                }
+            }
+            // sample
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                const int64_t env = h ? env_b : env_a;
                 float best = -INFINITY;
                 int best_a = 0x7fffffff;
 #pragma unroll
@@ -213,8 +229,6 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) pz_policy_mlp_kernel(const
                         const int action = 8 * nt + 2 * t + q;  // visited in increasing order: ties keep the lower one
                         const float logit = c2[nt][2 * h + q];
                         if (action < P.n_actions) {
-                            if (P.logits != nullptr && env < P.n)
-                                P.logits[(env * 2 + a) * P.n_actions + action] = logit;
                             const float key = P.greedy ? logit : gumbel_key(logit, nbase[h], a, action);
                             if (key > best) {
                                 best = key;
