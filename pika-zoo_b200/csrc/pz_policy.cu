@@ -4,6 +4,7 @@
 //
 //   logits[env][agent][:] = W2[agent] . relu(W1[agent] . x[agent][:, env])         bf16 in, fp32 accumulate
 //   action = argmax_a (logits[a] + Gumbel noise(seed, step, global env, agent, a))   == a categorical sample
+//            (on keys truncated to 27 bits that carry the action in their low mantissa bits, see pack_key)
 //
 // In eager PyTorch the same step is two batched GEMMs and nine elementwise / reduction passes over
 // [2, 72, N] and [2, 18, N] tensors (5.4 GB of HBM traffic per 2 M envs, 1.45 ms); here the observations are
@@ -29,9 +30,9 @@ namespace pzp {
 constexpr int kThreads = 256;    // 8 warps x 16 envs
 constexpr int kTileEnvs = 128;
 #ifndef PZ_POLICY_MIN_CTAS
-#define PZ_POLICY_MIN_CTAS 3
+#define PZ_POLICY_MIN_CTAS 4
 #endif
-constexpr int kMinCtas = PZ_POLICY_MIN_CTAS;  // 3: 80 registers without spills, 24 warps per SM (4: 64 registers with spills, 5 % slower)
+constexpr int kMinCtas = PZ_POLICY_MIN_CTAS;  // 4: 64 registers (44 B of spill loads), 32 warps per SM: 0.250 ms per 2 M envs; 3: 80 registers, 0.260 ms
 constexpr int kKP = PZ_POLICY_MAX_FEATURES;  // 48: features padded to 3 k-steps of 16
 constexpr int kHP = PZ_POLICY_MAX_HIDDEN;    // 80: hidden units padded to 10 n-tiles of 8 / 5 k-steps of 16
 constexpr int kAP = PZ_POLICY_MAX_ACTIONS;   // 24: actions padded to 3 n-tiles of 8
@@ -91,14 +92,21 @@ __device__ __forceinline__ uint32_t noise_base(uint64_t seed, uint64_t step, uin
     return (uint32_t)z;
 }
 __device__ __forceinline__ float gumbel_key(float logit, uint32_t base, int agent, int action) {
-    uint32_t x = base + (uint32_t)(32 * agent + action + 1) * 0x9E3779B9u;
-    x ^= x >> 16;
+    uint32_t x = base + (uint32_t)(32 * agent + action + 1) * 0x9E3779B9u;  // base is already well mixed
     x *= 0x7feb352du;
     x ^= x >> 15;
     x *= 0x846ca68bu;
     x ^= x >> 16;
     const float u = fmaf((float)(x >> 9), 1.0f / 8388608.0f, 0.5f / 8388608.0f);  // (0, 1), exact
     return fmaf(-0.693147182f, lg2_approx(-lg2_approx(u)), logit);
+}
+
+// The arg-max runs on keys that carry their action in the five low mantissa bits (31 - action, so that among
+// positive keys equal in the upper 27 bits the lower action wins): one LOP3 + one FMNMX per candidate and one
+// shuffle + one FMNMX per reduction step instead of compare-and-select pairs on (key, action). The 2^-19
+// relative truncation of the key is far below the noise resolution.
+__device__ __forceinline__ float pack_key(float key, int action) {
+    return __uint_as_float((__float_as_uint(key) & ~31u) | (uint32_t)(31 - action));
 }
 
 constexpr size_t kSmemBytes = sizeof(__nv_bfloat16) * 2 * kKP * kXS + sizeof(uint32_t) * (kW1Words + kW2Words);
@@ -220,32 +228,20 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) pz_policy_mlp_kernel(const
             // sample
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                float best = -INFINITY;
-                int best_a = 0x7fffffff;
+                float best = pack_key(-INFINITY, 31);
 #pragma unroll
                 for (int nt = 0; nt < kAP / 8; nt++)
 #pragma unroll
                     for (int q = 0; q < 2; q++) {
-                        const int action = 8 * nt + 2 * t + q;  // visited in increasing order: ties keep the lower one
+                        const int action = 8 * nt + 2 * t + q;
                         const float logit = c2[nt][2 * h + q];
-                        if (action < P.n_actions) {
-                            const float key = P.greedy ? logit : gumbel_key(logit, nbase[h], a, action);
-                            if (key > best) {
-                                best = key;
-                                best_a = action;
-                            }
-                        }
+                        if (action < P.n_actions)
+                            best = fmaxf(best, pack_key(P.greedy ? logit : gumbel_key(logit, nbase[h], a, action), action));
                     }
-#pragma unroll
-                for (int d = 1; d <= 2; d <<= 1) {  // over the quad (t = 0..3); ties go to the lower action
-                    const float ok = __shfl_xor_sync(0xFFFFFFFFu, best, d);
-                    const int oa = __shfl_xor_sync(0xFFFFFFFFu, best_a, d);
-                    if (ok > best || (ok == best && oa < best_a)) {
-                        best = ok;
-                        best_a = oa;
-                    }
-                }
-                act[h][a] = best_a == 0x7fffffff ? 0 : best_a;  // every key NaN: action 0
+                best = fmaxf(best, __shfl_xor_sync(0xFFFFFFFFu, best, 1));  // over the quad (t = 0..3)
+                best = fmaxf(best, __shfl_xor_sync(0xFFFFFFFFu, best, 2));
+                const int chosen = 31 - (int)(__float_as_uint(best) & 31u);
+                act[h][a] = chosen < P.n_actions ? chosen : 0;  // every key NaN: action 0
             }
         }
         if (t == 0) {

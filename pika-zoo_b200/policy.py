@@ -38,13 +38,21 @@ def gumbel_noise_reference(seed: int, step: int, first_env: int, n: int, n_actio
         k = (np.uint32(32) * np.arange(2, dtype=np.uint32)[None, :, None]
              + np.arange(n_actions, dtype=np.uint32)[None, None, :] + np.uint32(1))
         x = base + k * np.uint32(0x9E3779B9)
-        x ^= x >> np.uint32(16)
         x *= np.uint32(0x7FEB352D)
         x ^= x >> np.uint32(15)
         x *= np.uint32(0x846CA68B)
         x ^= x >> np.uint32(16)
     u = (x >> np.uint32(9)).astype(np.float32) * np.float32(1.0 / 8388608.0) + np.float32(0.5 / 8388608.0)  # exact
     return np.float32(-0.693147182) * np.log2(-np.log2(u))
+
+
+def sample_reference(logits: np.ndarray, noise: Optional[np.ndarray]) -> np.ndarray:
+    """int64 [n, 2]: the arg-max pz_policy_mlp_act takes, restated in numpy (csrc/pz_policy.cu pack_key): keys
+    = logits (+ noise) in float32, their five low mantissa bits replaced by 31 - action, maximum as floats."""
+    key = np.asarray(logits, dtype=np.float32) if noise is None else (logits.astype(np.float32) + noise.astype(np.float32))
+    a = np.arange(key.shape[-1], dtype=np.uint32)
+    packed = ((np.ascontiguousarray(key).view(np.uint32) & np.uint32(0xFFFFFFE0)) | (np.uint32(31) - a)).view(np.float32)
+    return packed.argmax(axis=-1).astype(np.int64)
 
 
 class MLPPolicy(nn.Module):

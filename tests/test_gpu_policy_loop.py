@@ -144,7 +144,7 @@ def test_fused_policy_logits_and_greedy_actions(cuda_lib, n):
     bf16, 2^-8 relative, which reaches a logit through one weight of magnitude ~0.1). Greedy actions are the
     arg-max of the kernel's own logits, exactly. Sizes cover full tiles, the ragged last tile and the
     unaligned-row path (n % 8 != 0)."""
-    from pikazoo_b200.policy import MLPPolicy
+    from pikazoo_b200.policy import MLPPolicy, sample_reference
 
     env = _played_env(n)
     policy = MLPPolicy(device=env.device, seed=3)
@@ -152,7 +152,12 @@ def test_fused_policy_logits_and_greedy_actions(cuda_lib, n):
     for dtype in (torch.uint8, torch.int32, torch.int64):
         a = policy.act_fused(env.obs, step=0, action_dtype=dtype, greedy=True, logits_out=logits)
         assert a.dtype == dtype and a.shape == (n, 2)
-        assert torch.equal(a.long(), logits.argmax(dim=2))
+        assert np.array_equal(a.cpu().numpy().astype(np.int64), sample_reference(logits.cpu().numpy(), None))
+        # i.e. the arg-max of the logits, except between logits equal in their upper 27 bits
+        differ = a.long() != logits.argmax(dim=2)
+        if bool(differ.any()):
+            top2 = logits[differ].topk(2, dim=-1).values
+            assert float((top2[:, 0] - top2[:, 1]).abs().max()) < 1e-4 and int(differ.sum()) < 5
     ref = _reference_logits(policy, env.obs)
     assert torch.isfinite(logits).all()
     assert (logits - ref).abs().max().item() < 2e-3
@@ -165,7 +170,7 @@ def test_fused_policy_sampling_is_the_documented_argmax(cuda_lib):
     """actions == argmax(logits + Gumbel noise) with the noise restated in numpy from the counters. The kernel
     takes its logarithms from the hardware approximation, so keys differ by a few float32 ulp: every mismatch
     must be a near-tie, and there must be next to none."""
-    from pikazoo_b200.policy import MLPPolicy, gumbel_noise_reference
+    from pikazoo_b200.policy import MLPPolicy, gumbel_noise_reference, sample_reference
 
     n = 50_000
     env = _played_env(n)
@@ -173,8 +178,9 @@ def test_fused_policy_sampling_is_the_documented_argmax(cuda_lib):
     logits = torch.empty((n, 2, 18), device="cuda")
     for step, seed, first in ((0, 0, 0), (7, 123456789, 10**6), (2**40, 2**63 + 5, 3)):
         a = policy.act_fused(env.obs, step=step, seed=seed, first_env=first, logits_out=logits).cpu().numpy()
-        keys = logits.cpu().numpy() + gumbel_noise_reference(seed, step, first, n, 18)
-        expect = keys.argmax(axis=2)
+        noise = gumbel_noise_reference(seed, step, first, n, 18)
+        keys = logits.cpu().numpy() + noise
+        expect = sample_reference(logits.cpu().numpy(), noise)
         bad = np.argwhere(a != expect)
         assert len(bad) <= 2 * n * 2e-4, len(bad)
         for e, ag in bad:
