@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "../../include/pikazoo_b200.h"
 #include "pz_physics.cuh"
@@ -183,6 +184,50 @@ __device__ __forceinline__ void emit_obs_feature_major(const Env &e, bool valid,
     (std::make_integer_sequence<int, 35>{});
 }
 
+// The same rows from a whole CTA of kThreads consecutive envs, transposed through shared memory: every thread
+// stages its 35 distinct values as column threadIdx.x of stage[35][kThreads] (35 shared stores at immediate
+// offsets instead of 70 global stores with 64-bit address arithmetic each), then every warp writes whole rows —
+// kThreads envs of one feature, 256 or 512 contiguous bytes per store instruction — to both agents' copies of
+// the row. Needs full CTAs and 4-element-aligned rows (ld % 4 == 0); everything else takes the direct path.
+template <int DT>
+__device__ __forceinline__ void emit_obs_feature_major_staged(const Env &e, bool normalize, void *obs,
+                                                              int64_t cta_first, int64_t ld, int rows, void *stage_raw) {
+    using T = typename ObsType<DT>::elem;
+    static_assert(sizeof(T) == 2 || sizeof(T) == 4, "staged rows are 2- or 4-byte elements");
+    T(*stage)[kThreads] = reinterpret_cast<T(*)[kThreads]>(stage_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int u[35];
+    obs_values(e, u);
+    auto put = [&](auto K) {
+        constexpr int k = decltype(K)::value;
+        T v;
+        if (DT == PZ_OBS_I32 || DT == PZ_OBS_I16) {
+            v = (T)u[k];
+        } else {
+            const float f = obs_float<float, k>(u, normalize);
+            if (DT == PZ_OBS_F32)
+                v = (T)f;
+            else
+                v = (T)(DT == PZ_OBS_F16 ? __half_as_ushort(__float2half_rn(f))
+                                         : __bfloat16_as_ushort(__float2bfloat16_rn(f)));
+        }
+        stage[k][tid] = v;
+    };
+    [&]<int... K>(std::integer_sequence<int, K...>) { (put(std::integral_constant<int, K>{}), ...); }
+    (std::make_integer_sequence<int, 35>{});
+    __syncthreads();
+    using V = typename std::conditional<sizeof(T) == 2, uint2, uint4>::type;  // four elements per lane
+    char *g = reinterpret_cast<char *>(obs);
+#pragma unroll 1
+    for (int k = warp; k < 35; k += kWarps) {
+        const V v = reinterpret_cast<const V *>(stage[k])[lane];
+        const int k1 = k < 13 ? k + 13 : (k < 26 ? k - 13 : k);  // row of value k in agent 1's observation
+        const int64_t col = cta_first + 4 * lane;
+        __stcs(reinterpret_cast<V *>(g + ((int64_t)k * ld + col) * sizeof(T)), v);
+        __stcs(reinterpret_cast<V *>(g + ((int64_t)(rows + k1) * ld + col) * sizeof(T)), v);
+    }
+}
+
 __device__ __forceinline__ void emit_obs_feature_major(const Env &e, bool valid, int obs_dtype, bool normalize,
                                                        void *obs, int64_t env_idx, int64_t ld, int rows) {
     switch (obs_dtype) {  // launch-uniform
@@ -305,10 +350,10 @@ constexpr int kAiScratchInts = 320;  // computer_decide: 32 x int4 inputs + 32 x
 
 // Resident CTAs per SM the register allocation is held to (0 = leave it to ptxas). Without computer
 // players: 2-byte observation rows stage half as much shared memory, so seven CTAs fit if the registers
-// do (72 with a few spills to L1; the kernel waits on its loads, so warps in flight count); feature-major rows use no shared memory
-// at all and run best at eight (64 registers). Measured sweeps in DESIGN.md §4.
+// do (72 with a few spills to L1; the kernel waits on its loads, so warps in flight count); feature-major rows stage
+// 35 x 128 elements per CTA and run best at seven as well. Measured sweeps in DESIGN.md §4.
 #ifndef PZ_FM_MIN_CTAS
-#define PZ_FM_MIN_CTAS 8
+#define PZ_FM_MIN_CTAS 7  // bf16 rows per million envs: 52.4 us (6: 58.0, 8: 55.5; direct stores instead of the staged rows: 54.7)
 #endif
 #ifndef PZ_AI_MIN_CTAS
 #define PZ_AI_MIN_CTAS 5  // 94 registers, no spills: 72 us per million envs (4: 101 registers, 79 us; 6: 80 with spills, 77 us)
@@ -333,6 +378,12 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
                                    ? (32 * kRowInts > kAiScratchInts ? 32 * kRowInts : kAiScratchInts)
                                    : (AI_MASK != 0 ? kAiScratchInts : 4);
     __shared__ __align__(128) int stage[kWarps][kStageInts];
+#ifdef PZ_FM_NO_STAGING
+    constexpr bool kFmStaged = false;
+#else
+    constexpr bool kFmStaged = LAYOUT == PZ_LAYOUT_FEATURE_MAJOR && OBS_DT != PZ_OBS_F64;
+#endif
+    __shared__ __align__(16) unsigned char fm_stage[kFmStaged ? 35 * kThreads * ObsType<OBS_DT>::bytes : 16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t i = P.begin + (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const bool valid = i < P.end;
@@ -387,8 +438,16 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
     if (P.obs) {
         if (LAYOUT == PZ_LAYOUT_ENV_MAJOR)
             pending = emit_obs_as<OBS_DT>(e, valid, P.normalize, P.obs, i, P.end, stage[warp], lane, P.out_policy);
-        else
-            emit_obs_feature_major<OBS_DT>(e, valid, P.normalize, P.obs, i, P.n, P.obs_rows);
+        else {
+            bool staged = false;
+            if constexpr (kFmStaged) {
+                if ((i - threadIdx.x) + kThreads <= P.end && (P.n & 3) == 0) {  // CTA-uniform
+                    emit_obs_feature_major_staged<OBS_DT>(e, P.normalize, P.obs, i - threadIdx.x, P.n, P.obs_rows, fm_stage);
+                    staged = true;
+                }
+            }
+            if (!staged) emit_obs_feature_major<OBS_DT>(e, valid, P.normalize, P.obs, i, P.n, P.obs_rows);
+        }
     }
     const bool truncated = valid && episode_truncated(P, e);  // this call's step reached the cap, or frozen there
     if (valid) {
