@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <mutex>
 
 #include "../../include/pikazoo_b200.h"
 
@@ -296,12 +297,16 @@ extern "C" int pz_policy_mlp_act(const void *obs_dev, int64_t n, int64_t ld, int
     const int64_t tiles = (n + kTileEnvs - 1) / kTileEnvs;
     const int64_t resident = (int64_t)sms * kMinCtas;  // persistent over tiles: the weights are staged once per CTA
     const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
-    static bool attr_set[64] = {};
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {  // 52.5 KB of dynamic shared memory needs the opt-in
-        cudaError_t e = cudaFuncSetAttribute(pz_policy_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)kSmemBytes);
-        if (e != cudaSuccess) return (int)e;
-        attr_set[dev] = true;
+    {  // more than 48 KB of dynamic shared memory needs the opt-in, once per device
+        static std::mutex mu;
+        static bool attr_set[64] = {};
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(pz_policy_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)kSmemBytes);
+            if (e != cudaSuccess) return (int)e;
+            attr_set[dev] = true;
+        }
     }
     pz_policy_mlp_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
     cudaError_t err = cudaGetLastError();
