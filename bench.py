@@ -317,10 +317,12 @@ def run_b200_arm(args):
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         L.pz_host_destroy(ctx)
+        h2d, d2h = n * 2 * h_act[0].element_size(), n * (70 * h_obs.element_size() + 8 + 1)
         return {
             "value": total * E / float(te.item()), "unit": "env-steps/s",
-            "h2d_bytes_per_step": n * 2 * h_act[0].element_size(),
-            "d2h_bytes_per_step": n * (70 * h_obs.element_size() + 8 + 1),
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            # what bounds this number: the link, per GPU (PCIe Gen5 x16 delivers ~55 GB/s device-to-host)
+            "pcie_gbs_per_gpu": (h2d + d2h) * E / float(te.item()) / 1e9,
             "steps": E, "dtypes": label,
             "api": "pz_host_step (C ABI, pinned host buffers, 8 chunks on 8 streams; host-blocking call timed "
                    "with perf_counter, max over ranks)",
