@@ -204,6 +204,8 @@ int pz_import_state(int32_t *state_dev, int64_t n, const int32_t *unpacked_dev, 
  * current device; pz_host_step copies actions host->device, runs pz_step and copies
  * obs/reward/done device->host, chunked so that copies overlap the kernel. Host buffers
  * should be pinned (cudaHostAlloc / torch pin_memory) for full PCIe speed; pageable works. */
+/* chunks: env ranges stepped on their own streams (copies of one overlap the kernel of the others);
+ * <= 0 picks it from n (1 for small batches, 8 from a million envs up). */
 typedef struct pz_host_ctx pz_host_ctx;
 int pz_host_create(pz_host_ctx **out, int64_t n, const pz_config *cfg, uint64_t base_seed,
                    uint64_t first_env, int32_t chunks);

@@ -58,7 +58,10 @@ int pz_host_create(pz_host_ctx **out, int64_t n, const pz_config *cfg, uint64_t 
         return PZ_E_BADCONFIG;
     }
     c->obs_row = 2 * PZ_OBS_WORDS * pz_obs_elem_bytes(cfg->obs_dtype);
-    if (chunks < 1) chunks = 1;
+    if (chunks < 1) {  // automatic: one chunk per 128 Ki envs, at most 8 — small batches are bound by API calls, not PCIe
+        const int64_t want = n / (128 * 1024);
+        chunks = (int32_t)(want < 1 ? 1 : (want > 8 ? 8 : want));
+    }
     // chunk boundaries on multiples of 128 envs (whole CTAs, 16-byte aligned slices of every array)
     int64_t blocks = (n + 127) / 128;
     if (chunks > blocks) chunks = (int32_t)blocks;

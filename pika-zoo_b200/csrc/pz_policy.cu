@@ -112,7 +112,11 @@ __device__ __forceinline__ float pack_key(float key, int action) {
 
 constexpr size_t kSmemBytes = sizeof(__nv_bfloat16) * 2 * kKP * kXS + sizeof(uint32_t) * (kW1Words + kW2Words);
 
+// NA: the action count when it is one of the two the simulator has (18, or 13 under SimplifyAction), so that the
+// padded candidates fall away at compile time; 0 = read it from the parameters.
+template <int NA>
 __global__ void __launch_bounds__(kThreads, kMinCtas) pz_policy_mlp_kernel(const __grid_constant__ Params P) {
+    const int n_actions = NA ? NA : P.n_actions;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __nv_bfloat16(*xs)[kKP][kXS] = reinterpret_cast<__nv_bfloat16(*)[kKP][kXS]>(smem_raw);
     uint32_t *w1f = reinterpret_cast<uint32_t *>(xs + 2);
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) pz_policy_mlp_kernel(const
         const int nt = 2 * grp + (idx >> 1);  // action tile; tile 3 does not exist
         const int r = 8 * nt + (ln >> 2), c = 16 * j + 8 * (idx & 1) + 2 * (ln & 3) + e;
         reinterpret_cast<__nv_bfloat16 *>(w2f)[i] =
-            (nt < kAP / 8 && r < P.n_actions && c < P.k2) ? P.w2[((int64_t)a * P.n_actions + r) * P.k2 + c] : zero;
+            (nt < kAP / 8 && r < n_actions && c < P.k2) ? P.w2[((int64_t)a * n_actions + r) * P.k2 + c] : zero;
     }
     for (int i = tid; i < 2 * kKP * kXS; i += kThreads) (&xs[0][0][0])[i] = zero;
 
@@ -145,14 +149,17 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) pz_policy_mlp_kernel(const
         const int64_t env0 = tile * kTileEnvs;
         __syncthreads();  // the previous tile has been consumed (and, first time, the fills above are done)
         if (vec_ok && env0 + kTileEnvs <= P.n) {
-            // 16-byte pieces of 8 envs; a pass of the CTA covers kThreads / kPieces (agent, feature) rows
+            // 16-byte pieces of 8 envs; a pass of the CTA covers kThreads / kPieces (agent, feature) rows. Row r of
+            // the tile is global row r + (r >= k1) * (rows - k1) and shared row r + (r >= k1) * (kKP - k1).
             constexpr int kPieces = kTileEnvs / 8, kRowsPerPass = kThreads / kPieces;
             const int piece = tid % kPieces;
             const __nv_bfloat16 *src0 = P.obs + env0 + piece * 8;
+            const uint32_t dst0 = smem_u32(&xs[0][0][piece * 8]);
             for (int row = tid / kPieces; row < 2 * P.k1; row += kRowsPerPass) {
-                const int a = row >= P.k1 ? 1 : 0, k = row - a * P.k1;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&xs[a][k][piece * 8])),
-                             "l"(src0 + (int64_t)(a * P.rows + k) * P.ld)
+                const int second = row >= P.k1 ? 1 : 0;
+                const int grow = row + second * (P.rows - P.k1), srow = row + second * (kKP - P.k1);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(srow * kXS * 2)),
+                             "l"(src0 + (int64_t)grow * P.ld)
                              : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -221,8 +228,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) pz_policy_mlp_kernel(const
 #pragma unroll
                         for (int q = 0; q < 2; q++) {
                             const int action = 8 * nt + 2 * t + q;
-                            if (action < P.n_actions && env < P.n)
-                                P.logits[(env * 2 + a) * P.n_actions + action] = c2[nt][2 * h + q];
+                            if (action < n_actions && env < P.n)
+                                P.logits[(env * 2 + a) * n_actions + action] = c2[nt][2 * h + q];
                         }
                 }
             }
@@ -236,13 +243,13 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) pz_policy_mlp_kernel(const
                     for (int q = 0; q < 2; q++) {
                         const int action = 8 * nt + 2 * t + q;
                         const float logit = c2[nt][2 * h + q];
-                        if (action < P.n_actions)
+                        if (action < n_actions)
                             best = fmaxf(best, pack_key(P.greedy ? logit : gumbel_key(logit, nbase[h], a, action), action));
                     }
                 best = fmaxf(best, __shfl_xor_sync(0xFFFFFFFFu, best, 1));  // over the quad (t = 0..3)
                 best = fmaxf(best, __shfl_xor_sync(0xFFFFFFFFu, best, 2));
                 const int chosen = 31 - (int)(__float_as_uint(best) & 31u);
-                act[h][a] = chosen < P.n_actions ? chosen : 0;  // every key NaN: action 0
+                act[h][a] = chosen < n_actions ? chosen : 0;  // every key NaN: action 0
             }
         }
         if (t == 0) {
@@ -302,13 +309,24 @@ extern "C" int pz_policy_mlp_act(const void *obs_dev, int64_t n, int64_t ld, int
         static bool attr_set[64] = {};
         std::lock_guard<std::mutex> lock(mu);
         if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(pz_policy_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaError_t e = cudaFuncSetAttribute(pz_policy_mlp_kernel<18>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)kSmemBytes);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(pz_policy_mlp_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kSmemBytes);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(pz_policy_mlp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kSmemBytes);
             if (e != cudaSuccess) return (int)e;
             attr_set[dev] = true;
         }
     }
-    pz_policy_mlp_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
+    if (n_actions == 18)
+        pz_policy_mlp_kernel<18><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
+    else if (n_actions == 13)
+        pz_policy_mlp_kernel<13><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
+    else
+        pz_policy_mlp_kernel<0><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
     cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? 0 : (int)err;
 }

@@ -4,7 +4,7 @@ loop optimises; `act()` is cuBLAS GEMMs and elementwise kernels): the simulator'
 take its sampled actions without ever leaving the device — observations arrive as normalised bf16 rows
 straight from the step kernel (NormalizeObservation fused). `act_fused()` / `FusedActor` run the same
 network for acting through the library's own kernel (csrc/pz_policy.cu: both layers and the categorical
-sample in one pass over the observations, 0.09 ms instead of 1.45 ms per 2 M envs)."""
+sample in one pass over the observations, 0.23 ms instead of 1.45 ms per 2 M envs)."""
 
 from __future__ import annotations
 

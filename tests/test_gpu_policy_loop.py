@@ -166,6 +166,24 @@ def test_fused_policy_logits_and_greedy_actions(cuda_lib, n):
     assert (logits - eager).abs().max().item() < 0.05
 
 
+@pytest.mark.parametrize("n_actions", [13, 7, 24])
+def test_fused_policy_other_action_counts(cuda_lib, n_actions):
+    """13 actions (SimplifyAction) has its own instantiation, other counts take the generic one."""
+    from pikazoo_b200.policy import MLPPolicy, gumbel_noise_reference, sample_reference
+
+    n = 20_000
+    env = _played_env(n)
+    policy = MLPPolicy(n_actions=n_actions, device=env.device, seed=5)
+    logits = torch.full((n, 2, n_actions), float("nan"), device="cuda")
+    a = policy.act_fused(env.obs, step=3, seed=9, logits_out=logits)
+    ref = _reference_logits(policy, env.obs)
+    assert (logits - ref).abs().max().item() < 2e-3
+    expect = sample_reference(logits.cpu().numpy(), gumbel_noise_reference(9, 3, 0, n, n_actions))
+    assert int((a.cpu().numpy() != expect).sum()) <= 8 and int(a.max()) < n_actions
+    g = policy.act_fused(env.obs, step=3, greedy=True, logits_out=logits)
+    assert np.array_equal(g.cpu().numpy().astype(np.int64), sample_reference(logits.cpu().numpy(), None))
+
+
 def test_fused_policy_sampling_is_the_documented_argmax(cuda_lib):
     """actions == argmax(logits + Gumbel noise) with the noise restated in numpy from the counters. The kernel
     takes its logarithms from the hardware approximation, so keys differ by a few float32 ulp: every mismatch
