@@ -107,3 +107,32 @@ def test_allreduce_is_noop_without_process_group():
     s = torch.arange(16, dtype=torch.int64)
     assert pikazoo_b200.allreduce_stats(s) is None
     assert s.tolist() == list(range(16))
+
+
+def test_policy_noise_and_sampling_restatements():
+    """The numpy restatements the GPU tests check the fused policy kernel against: the counter-based noise is a
+    pure function of its counters, differs between envs / agents / actions / steps, and is Gumbel-distributed (up
+    to the constant ln ln 2); the packed-key arg-max is the plain arg-max except between keys equal in their upper
+    27 bits, where positive keys prefer the lower action."""
+    from pikazoo_b200.policy import gumbel_noise_reference, sample_reference
+
+    a = gumbel_noise_reference(7, 3, 100, 4096, 18)
+    assert a.shape == (4096, 2, 18) and a.dtype == np.float32 and np.isfinite(a).all()
+    assert np.array_equal(a, gumbel_noise_reference(7, 3, 100, 4096, 18))
+    assert np.array_equal(a[50:60], gumbel_noise_reference(7, 3, 150, 10, 18))  # keyed by the GLOBAL env index
+    assert not np.array_equal(a, gumbel_noise_reference(7, 4, 100, 4096, 18))
+    assert not np.array_equal(a, gumbel_noise_reference(8, 3, 100, 4096, 18))
+    assert len(np.unique(a)) > 0.99 * a.size
+    g = a.astype(np.float64) - np.log(np.log(2.0))  # standard Gumbel: mean 0.5772, variance pi^2 / 6
+    assert abs(g.mean() - 0.5772) < 0.02 and abs(g.var() - np.pi ** 2 / 6) < 0.05
+    # uniform logits: every action equally likely
+    counts = np.bincount(sample_reference(np.zeros((4096, 2, 18), np.float32), a).ravel(), minlength=18)
+    assert counts.min() > 0.8 * counts.mean() and counts.max() < 1.2 * counts.mean()
+    logits = np.random.default_rng(0).normal(size=(1000, 2, 18)).astype(np.float32)
+    got, plain = sample_reference(logits, None), logits.argmax(axis=-1)
+    for e, ag in np.argwhere(got != plain):  # only between keys closer than the 5 truncated mantissa bits
+        assert abs(logits[e, ag, got[e, ag]] - logits[e, ag, plain[e, ag]]) < 32 * np.spacing(np.float32(abs(logits[e, ag]).max()))
+    assert (got != plain).sum() <= 3
+    tie = np.zeros((1, 2, 18), np.float32)
+    tie[0, :, 5] = tie[0, :, 11] = 2.0
+    assert sample_reference(tie, None).tolist() == [[5, 5]]
