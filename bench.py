@@ -136,7 +136,9 @@ def run_reference_arm(args):
         "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": per_step_seconds * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs_per_gpu},
+        "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs_per_gpu,
+                   "total_envs": args.envs_per_gpu * args.gpus, "parallelism": f"env-shard x{args.gpus}",
+                   "note": "same workload as the b200 arm; this arm steps it on the host cores of rank 0's box"},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
