@@ -387,6 +387,33 @@ def run_b200_arm(args):
         v.reset()
         ring13 = [torch.randint(0, 13, (65536, 2), generator=gen, device=dev, dtype=torch.int32) for _ in range(4)]
         variants["configs[2]_65536_envs_fused_wrappers"] = time_steps(v, ring13, steps=1000, warm=50)
+
+        def graph_us_per_step(env, ring_, replays=50):
+            """the same steps captured once in a CUDA graph: what the kernel costs without the Python launch path"""
+            side_ = torch.cuda.Stream(device=dev)
+            side_.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side_):
+                for a_ in ring_:
+                    env.step(a_)
+            torch.cuda.current_stream().wait_stream(side_)
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                for a_ in ring_:
+                    env.step(a_)
+            g_.replay()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(replays):
+                g_.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e3 / (replays * len(ring_))
+
+        ring13 = ring13 * 8  # 32 steps per graph
+        g13 = graph_us_per_step(v, ring13)
+        variants["configs[2]_65536_envs_fused_wrappers"].update(
+            cuda_graph_us_per_step=g13, cuda_graph_env_steps_per_sec=65536 * world / (g13 * 1e-6))
         del v, ring13
         # configs[1] as stated: 4,096 envs, random Discrete(18) actions, device obs/reward, auto-reset. This
         # size is bound by the host launch path: eager Python loop, and the same steps captured in a CUDA graph
@@ -394,30 +421,12 @@ def run_b200_arm(args):
         small.reset()
         ring4k = [torch.randint(0, 18, (4096, 2), generator=gen, device=dev, dtype=torch.int32) for _ in range(64)]
         eager = time_steps(small, ring4k, steps=2000, warm=100)
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for a4 in ring4k:
-                small.step(a4)
-        torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            for a4 in ring4k:
-                small.step(a4)
-        graph.replay()
-        barrier()
-        ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ga.record()
-        for _ in range(50):
-            graph.replay()
-        gb.record()
-        torch.cuda.synchronize()
-        g_us = ga.elapsed_time(gb) * 1e3 / (50 * 64)
+        g_us = graph_us_per_step(small, ring4k)
         variants["configs[1]_4096_envs"] = {
             "eager_us_per_step": eager["us_per_launch"], "eager_env_steps_per_sec": eager["env_steps_per_sec"],
             "cuda_graph_us_per_step": g_us, "cuda_graph_env_steps_per_sec": 4096 * world / (g_us * 1e-6),
             "env_steps_per_sec": 4096 * world / (g_us * 1e-6)}
-        del small, graph, ring4k
+        del small, ring4k
         # configs[4]: 2 M envs per GPU, serve='random', winning_score=5, both agents' actions sampled on the
         # device by a torch MLP (bf16 GEMMs + Gumbel-max) from the kernel's normalised bf16 observations
         from pikazoo_b200.policy import MLPPolicy, policy_rollout
