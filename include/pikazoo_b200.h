@@ -227,7 +227,16 @@ void pz_host_destroy(pz_host_ctx *ctx);
  *   actions_dev  [n][2] of action_dtype (PZ_ACT_*): argmax_a(logits[a] + Gumbel(seed, step, first_env + env,
  *                agent, a)) — a categorical sample from softmax(logits), reproducible from the counters
  *                (restated in policy.py gumbel_noise_reference); greedy != 0: plain argmax
- *   logits_dev   optional fp32 [n][2][n_actions] */
+ *   logits_dev   optional fp32 [n][2][n_actions]
+ *
+ * Two implementations of the same definition: PZ_POLICY_IMPL_TCGEN05 (csrc/pz_policy_tc.cu: tcgen05.mma with the
+ * accumulators and the hidden activations in TMEM, one thread per env in the epilogues) and
+ * PZ_POLICY_IMPL_MMA_SYNC (csrc/pz_policy.cu: warp-level mma.sync, kept for A/B measurements). pz_policy_select
+ * switches process-wide and returns the previous choice, or -1 for an unknown code. */
+#define PZ_POLICY_IMPL_TCGEN05 0
+#define PZ_POLICY_IMPL_MMA_SYNC 1
+#define PZ_POLICY_IMPL_DEFAULT PZ_POLICY_IMPL_MMA_SYNC
+int pz_policy_select(int32_t impl);
 #define PZ_POLICY_MAX_FEATURES 48
 #define PZ_POLICY_MAX_HIDDEN 80
 #define PZ_POLICY_MAX_ACTIONS 24

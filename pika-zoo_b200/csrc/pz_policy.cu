@@ -21,10 +21,12 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <mutex>
 
 #include "../../include/pikazoo_b200.h"
+#include "pz_policy.cuh"
 
 namespace pzp {
 
@@ -48,19 +50,6 @@ constexpr int kW1Words = 2 * (kHP / 16) * (kKP / 16) * 32 * 4;
 constexpr int kW2Words = 2 * (kHP / 16) * 2 * 32 * 4;
 static_assert(kAP == 24 && kHP % 16 == 0 && kKP % 16 == 0, "fragment layout");
 
-struct Params {
-    const __nv_bfloat16 *obs;  // [2][rows][ld], element (a, k, env)
-    int64_t n, ld;
-    int rows;
-    const __nv_bfloat16 *w1;  // [2][h1][k1]
-    const __nv_bfloat16 *w2;  // [2][n_actions][k2]
-    int h1, k1, n_actions, k2;
-    uint64_t seed, step, first_env;
-    void *actions;
-    int act_dtype, greedy;
-    float *logits;  // optional [n][2][n_actions]
-};
-
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -74,40 +63,6 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ uint32_t relu_pack(float lo, float hi) {
     const __nv_bfloat162 v = __hmax2(__floats2bfloat162_rn(lo, hi), __floats2bfloat162_rn(0.0f, 0.0f));
     return *reinterpret_cast<const uint32_t *>(&v);
-}
-
-__device__ __forceinline__ float lg2_approx(float x) {  // MUFU.LG2; the arguments here are normal numbers
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// Counter-based noise, restated in pika-zoo_b200/policy.py (gumbel_noise_reference) for the tests: one 64-bit
-// mix per (seed, step, global env), one 32-bit mix per (agent, action). The key added to a logit is
-//   key = fma(-ln2, log2(-log2(u)), logit) = logit + Gumbel(u) + ln(ln 2): the constant does not move the arg-max.
-__device__ __forceinline__ uint32_t noise_base(uint64_t seed, uint64_t step, uint64_t genv) {
-    uint64_t z = (seed + 0x9E3779B97F4A7C15ULL * (genv + 1ULL)) ^ (step * 0xD1B54A32D192ED03ULL);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    z = z ^ (z >> 31);
-    return (uint32_t)z;
-}
-__device__ __forceinline__ float gumbel_key(float logit, uint32_t base, int agent, int action) {
-    uint32_t x = base + (uint32_t)(32 * agent + action + 1) * 0x9E3779B9u;  // base is already well mixed
-    x *= 0x7feb352du;
-    x ^= x >> 15;
-    x *= 0x846ca68bu;
-    x ^= x >> 16;
-    const float u = fmaf((float)(x >> 9), 1.0f / 8388608.0f, 0.5f / 8388608.0f);  // (0, 1), exact
-    return fmaf(-0.693147182f, lg2_approx(-lg2_approx(u)), logit);
-}
-
-// The arg-max runs on keys that carry their action in the five low mantissa bits (31 - action, so that among
-// positive keys equal in the upper 27 bits the lower action wins): one LOP3 + one FMNMX per candidate and one
-// shuffle + one FMNMX per reduction step instead of compare-and-select pairs on (key, action). The 2^-19
-// relative truncation of the key is far below the noise resolution.
-__device__ __forceinline__ float pack_key(float key, int action) {
-    return __uint_as_float((__float_as_uint(key) & ~31u) | (uint32_t)(31 - action));
 }
 
 constexpr size_t kSmemBytes = sizeof(__nv_bfloat16) * 2 * kKP * kXS + sizeof(uint32_t) * (kW1Words + kW2Words);
@@ -268,7 +223,15 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) pz_policy_mlp_kernel(const
     }
 }
 
+// Which kernel pz_policy_mlp_act launches (process-wide; the two produce the same sample definition)
+static std::atomic<int> g_policy_impl{PZ_POLICY_IMPL_DEFAULT};
+
 }  // namespace pzp
+
+extern "C" int pz_policy_select(int32_t impl) {
+    if (impl != PZ_POLICY_IMPL_TCGEN05 && impl != PZ_POLICY_IMPL_MMA_SYNC) return -1;
+    return pzp::g_policy_impl.exchange(impl);
+}
 
 extern "C" int pz_policy_mlp_act(const void *obs_dev, int64_t n, int64_t ld, int32_t rows, const void *w1_dev,
                                  int32_t hidden_rows, int32_t features, const void *w2_dev, int32_t n_actions,
@@ -299,6 +262,7 @@ extern "C" int pz_policy_mlp_act(const void *obs_dev, int64_t n, int64_t ld, int
     P.act_dtype = action_dtype;
     P.greedy = greedy != 0;
     P.logits = logits_dev;
+    if (g_policy_impl.load(std::memory_order_relaxed) == PZ_POLICY_IMPL_TCGEN05) return launch_tc(P, (cudaStream_t)stream);
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t tiles = (n + kTileEnvs - 1) / kTileEnvs;

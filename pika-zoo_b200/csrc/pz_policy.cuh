@@ -1,0 +1,64 @@
+// Shared by the two implementations of pz_policy_mlp_act (pz_policy.cu: warp-level mma.sync; pz_policy_tc.cu:
+// tcgen05 + TMEM): the launch parameters and the counter-based Gumbel noise / packed-key arg-max, which are the
+// definition of the sample and therefore identical in both.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/pikazoo_b200.h"
+
+namespace pzp {
+
+struct Params {
+    const __nv_bfloat16 *obs;  // [2][rows][ld], element (a, k, env)
+    int64_t n, ld;
+    int rows;
+    const __nv_bfloat16 *w1;  // [2][h1][k1]
+    const __nv_bfloat16 *w2;  // [2][n_actions][k2]
+    int h1, k1, n_actions, k2;
+    uint64_t seed, step, first_env;
+    void *actions;
+    int act_dtype, greedy;
+    float *logits;  // optional [n][2][n_actions]
+};
+
+__device__ __forceinline__ float lg2_approx(float x) {  // MUFU.LG2; the arguments here are normal numbers
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Counter-based noise, restated in pika-zoo_b200/policy.py (gumbel_noise_reference) for the tests: one 64-bit
+// mix per (seed, step, global env), one 32-bit mix per (agent, action). The key added to a logit is
+//   key = fma(-ln2, log2(-log2(u)), logit) = logit + Gumbel(u) + ln(ln 2): the constant does not move the arg-max.
+__device__ __forceinline__ uint32_t noise_base(uint64_t seed, uint64_t step, uint64_t genv) {
+    uint64_t z = (seed + 0x9E3779B97F4A7C15ULL * (genv + 1ULL)) ^ (step * 0xD1B54A32D192ED03ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return (uint32_t)z;
+}
+__device__ __forceinline__ float gumbel_key(float logit, uint32_t base, int agent, int action) {
+    uint32_t x = base + (uint32_t)(32 * agent + action + 1) * 0x9E3779B9u;  // base is already well mixed
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    const float u = fmaf((float)(x >> 9), 1.0f / 8388608.0f, 0.5f / 8388608.0f);  // (0, 1), exact
+    return fmaf(-0.693147182f, lg2_approx(-lg2_approx(u)), logit);
+}
+
+// The arg-max runs on keys that carry their action in the five low mantissa bits (31 - action, so that among
+// positive keys equal in the upper 27 bits the lower action wins): one LOP3 + one FMNMX per candidate and one
+// shuffle + one FMNMX per reduction step instead of compare-and-select pairs on (key, action). The 2^-19
+// relative truncation of the key is far below the noise resolution.
+__device__ __forceinline__ float pack_key(float key, int action) {
+    return __uint_as_float((__float_as_uint(key) & ~31u) | (uint32_t)(31 - action));
+}
+
+// pz_policy_tc.cu
+int launch_tc(const Params &P, cudaStream_t stream);
+
+}  // namespace pzp

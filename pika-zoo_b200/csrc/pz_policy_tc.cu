@@ -1,0 +1,341 @@
+// pz_policy_mlp_act on the 5th-generation tensor cores (tcgen05 + TMEM), the default implementation.
+//
+// A CTA of 128 threads owns a tile of 128 envs: thread t IS env t of the tile from the first epilogue on, which
+// is what makes this form cheap — in the warp-level mma.sync kernel (pz_policy.cu) a warp's 16 envs are spread
+// over accumulator fragments, so every hidden activation is rectified / packed and every Gumbel key is built in
+// fragment order (24 candidate slots per quad for 18 actions, quad shuffles for the arg-max), ~1,180 warp
+// instructions per 16 envs. Here, per agent:
+//
+//   layer 1   D1[128 envs][80 hidden]  = X^T[128][48] . W1^T      one thread issues 3 tcgen05.mma (K = 16 each);
+//             (TMEM, fp32, 80 columns)                            A = the observation tile as it lies in the
+//                                                                 feature-major tensor (MN-major, no swizzle),
+//                                                                 B = W1 (K-major), both in shared memory
+//   epilogue  thread t reads row t of D1 (tcgen05.ld 32x32b), rectifies, rounds to bf16 and stores the 40 packed
+//             pairs back to TMEM (tcgen05.st) as row t of H
+//   layer 2   D2[128][32]              = H[128][80] . W2^T        5 tcgen05.mma with A taken from TMEM
+//   sample    thread t reads its env's logits (one row of D2) and takes argmax(logit + Gumbel) over exactly
+//             n_actions candidates in registers: no shuffles, no padded slots
+//
+// TMEM: 128 columns per CTA (D1 0..79, H 80..119, D2 reuses 0..31), four CTAs per SM fill the 512 columns.
+// Shared memory: 24 KB of observation tile (both agents) + 25 KB of weights, staged once per persistent CTA.
+// The tensor-core work of a CTA is strictly serial (MMA -> epilogue -> MMA -> sample, twice per tile); the four
+// resident CTAs of an SM overlap each other's loads, MMAs and epilogues.
+//
+// Canonical shared-memory layouts (no swizzle; 8 x 16-byte "core matrices" of 128 contiguous bytes):
+//   X  (MN-major A): element (env m, feature k) at (k / 8) * 2048 + (m / 8) * 128 + (k % 8) * 16 + (m % 8) * 2
+//                    -> a 16-byte piece of 8 consecutive envs of one feature row lands as one 16-byte row of a
+//                       core matrix, so the tile is filled by plain 16-byte cp.async from the feature-major rows
+//   W1 (K-major B):  element (hidden n, feature k) at (k / 8) * 1280 + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2
+//   W2 (K-major B):  element (action n, hidden k)  at (k / 8) *  512 + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <mutex>
+
+#include "pz_policy.cuh"
+
+namespace pzp {
+namespace tc {
+
+constexpr int kThreads = 128;
+constexpr int kTileEnvs = 128;
+constexpr int kKP = PZ_POLICY_MAX_FEATURES;  // 48 = 3 k-steps of 16
+constexpr int kHP = PZ_POLICY_MAX_HIDDEN;    // 80: N of layer 1 (multiple of 16), 5 k-steps of layer 2
+constexpr int kAP = 32;                      // N of layer 2: PZ_POLICY_MAX_ACTIONS (24) padded to a multiple of 16
+constexpr int kCtasPerSm = 4;
+constexpr uint32_t kTmemCols = 128;          // per CTA; 4 CTAs x 128 = the SM's 512 columns
+constexpr uint32_t kColD1 = 0, kColH = kHP, kColD2 = 0;
+static_assert(kHP + kHP / 2 <= (int)kTmemCols && kAP <= kHP, "TMEM columns");
+static_assert(PZ_POLICY_MAX_ACTIONS <= kAP && kKP % 16 == 0 && kHP % 16 == 0, "tile shapes");
+
+constexpr int kXKGroup = (kTileEnvs / 8) * 128;    // 2048 B: one group of 8 features, 16 env atoms
+constexpr int kXAgent = (kKP / 8) * kXKGroup;      // 12288 B
+constexpr int kW1KGroup = (kHP / 8) * 128;         // 1280 B
+constexpr int kW1Agent = (kKP / 8) * kW1KGroup;    // 7680 B
+constexpr int kW2KGroup = (kAP / 8) * 128;         // 512 B
+constexpr int kW2Agent = (kHP / 8) * kW2KGroup;    // 5120 B
+constexpr int kOffX = 0, kOffW1 = 2 * kXAgent, kOffW2 = kOffW1 + 2 * kW1Agent, kOffBar = kOffW2 + 2 * kW2Agent;
+constexpr size_t kSmemBytes = kOffBar + 16;        // + mbarrier (8 B) + TMEM base address (4 B)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Shared-memory matrix descriptor (tcgen05, no swizzle): start address, leading / stride byte offsets in 16-byte
+// units, descriptor version 1 (sm_100), layout type 0.
+//   K-major operand : LBO = distance between the two 8-element K halves of one MMA, SBO = between 8-row groups
+//   MN-major operand: LBO = distance between groups of 8 along K,                   SBO = between 8-element MN atoms
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ULL << 46);
+}
+// Instruction descriptor, kind::f16: D fp32, A and B bf16, M = 128.
+__host__ __device__ constexpr uint32_t instr_desc(int n, bool a_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// mbarrier arrive once every tcgen05.mma issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Bounded: a wrong descriptor must end in a launch failure, not in a hung device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; spins++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && spins > (1u << 22)) __trap();
+    }
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// relu commutes with the rounding: convert the pair first, then one packed max against zero
+__device__ __forceinline__ uint32_t relu_pack(uint32_t lo_bits, uint32_t hi_bits) {
+    const __nv_bfloat162 v =
+        __hmax2(__floats2bfloat162_rn(__uint_as_float(lo_bits), __uint_as_float(hi_bits)), __floats2bfloat162_rn(0.0f, 0.0f));
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+
+template <int NA>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) pz_policy_mlp_tc_kernel(const __grid_constant__ Params P) {
+    const int n_actions = NA ? NA : P.n_actions;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t bar = s_base + kOffBar;
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kOffBar + 8);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- once per CTA: TMEM columns, the barrier, zeroed operands, the weights in canonical K-major order ----
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + kOffBar + 8),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < kOffBar / 16; i += kThreads) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    {
+        __nv_bfloat16 *w1s = reinterpret_cast<__nv_bfloat16 *>(smem + kOffW1);
+        for (int i = tid; i < 2 * P.h1 * P.k1; i += kThreads) {
+            const int a = i / (P.h1 * P.k1), rem = i - a * (P.h1 * P.k1), n = rem / P.k1, k = rem - n * P.k1;
+            w1s[(a * kW1Agent + (k >> 3) * kW1KGroup + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) >> 1] = P.w1[i];
+        }
+        __nv_bfloat16 *w2s = reinterpret_cast<__nv_bfloat16 *>(smem + kOffW2);
+        for (int i = tid; i < 2 * n_actions * P.k2; i += kThreads) {
+            const int a = i / (n_actions * P.k2), rem = i - a * (n_actions * P.k2), n = rem / P.k2, k = rem - n * P.k2;
+            w2s[(a * kW2Agent + (k >> 3) * kW2KGroup + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) >> 1] = P.w2[i];
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA's reads
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 lanes (rows) of the tile
+    uint32_t phase = 0;
+
+    constexpr uint32_t kIdesc1 = instr_desc(kHP, true), kIdesc2 = instr_desc(kAP, false);
+    const bool vec_ok = (P.ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(P.obs) & 15u) == 0);
+    const int k_groups = (P.k1 + 7) >> 3;
+    const int64_t n_tiles = (P.n + kTileEnvs - 1) / kTileEnvs;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t env0 = tile * kTileEnvs;
+        // ---- observation tile, both agents. The MMAs that read the previous tile have completed (their
+        //      mbarrier was waited on), so the buffer is free.
+        if (vec_ok && env0 + kTileEnvs <= P.n) {
+            // one (agent, group of 8 features) per pass: lane = (feature % 8) + 8 * (env atom % 4), warp = env atom / 4:
+            // a warp writes 512 contiguous bytes of shared memory and reads 8 rows x 64 contiguous bytes
+            const int kr = lane & 7, m8 = warp * 4 + (lane >> 3);
+            const __nv_bfloat16 *src0 = P.obs + env0 + m8 * 8;
+            const uint32_t dst0 = s_base + kOffX + m8 * 128 + kr * 16;
+            for (int a = 0; a < 2; a++)
+                for (int kg = 0; kg < k_groups; kg++) {
+                    const int k = kg * 8 + kr;
+                    if (k < P.k1)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + a * kXAgent + kg * kXKGroup),
+                                     "l"(src0 + ((int64_t)a * P.rows + k) * P.ld)
+                                     : "memory");
+                }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else {  // ragged last tile or unaligned rows
+            __nv_bfloat16 *xs = reinterpret_cast<__nv_bfloat16 *>(smem + kOffX);
+            const __nv_bfloat16 zero = __float2bfloat16(0.0f);
+            for (int i = tid; i < 2 * P.k1 * kTileEnvs; i += kThreads) {
+                const int a = i / (P.k1 * kTileEnvs), rem = i - a * (P.k1 * kTileEnvs), k = rem / kTileEnvs,
+                          m = rem % kTileEnvs;
+                xs[(a * kXAgent + (k >> 3) * kXKGroup + (m >> 3) * 128 + (k & 7) * 16 + (m & 7) * 2) >> 1] =
+                    env0 + m < P.n ? P.obs[((int64_t)a * P.rows + k) * P.ld + env0 + m] : zero;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();  // the previous tile's TMEM reads are ordered before the MMAs issued after this barrier
+        __syncthreads();
+
+        const int64_t env = env0 + tid;
+        const uint32_t nbase = P.greedy ? 0u : noise_base(P.seed, P.step, P.first_env + (uint64_t)env);
+        int act[2];
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+            // ---- layer 1 -> D1
+            if (tid == 0) {
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < kKP / 16; ks++)
+                    mma_ss(tmem + kColD1, smem_desc(s_base + kOffX + a * kXAgent + ks * 2 * kXKGroup, kXKGroup, 128),
+                           smem_desc(s_base + kOffW1 + a * kW1Agent + ks * 2 * kW1KGroup, kW1KGroup, 128), kIdesc1, ks > 0);
+                mma_commit(bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            tc_fence_after();
+            // ---- relu, round to bf16, back to TMEM as the A operand of layer 2 (thread = env row)
+#pragma unroll
+            for (int c = 0; c < kHP / 16; c++) {
+                uint32_t v[16], h[8];
+                tmem_ld16(t_row + kColD1 + 16 * c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; j++) h[j] = relu_pack(v[2 * j], v[2 * j + 1]);
+                tmem_st8(t_row + kColH + 8 * c, h);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncthreads();
+            // ---- layer 2 -> D2 (over D1's columns: every thread has read its row)
+            if (tid == 0) {
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < kHP / 16; j++)
+                    mma_ts(tmem + kColD2, tmem + kColH + 8 * j,
+                           smem_desc(s_base + kOffW2 + a * kW2Agent + j * 2 * kW2KGroup, kW2KGroup, 128), kIdesc2, j > 0);
+                mma_commit(bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            tc_fence_after();
+            // ---- this env's logits, the sample
+            uint32_t lg[24];
+            {
+                uint32_t v16[16], v8[8];
+                tmem_ld16(t_row + kColD2, v16);
+                if (NA == 0 || NA > 16) tmem_ld8(t_row + kColD2 + 16, v8);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j++) lg[j] = v16[j];
+#pragma unroll
+                for (int j = 0; j < 8; j++) lg[16 + j] = (NA == 0 || NA > 16) ? v8[j] : 0u;
+            }
+            if (P.logits != nullptr && env < P.n) {  // launch-uniform pointer
+#pragma unroll
+                for (int j = 0; j < (NA ? NA : PZ_POLICY_MAX_ACTIONS); j++)
+                    if (j < n_actions) P.logits[(env * 2 + a) * n_actions + j] = __uint_as_float(lg[j]);
+            }
+            float best = pack_key(-INFINITY, 31);
+#pragma unroll
+            for (int j = 0; j < (NA ? NA : PZ_POLICY_MAX_ACTIONS); j++) {
+                const float logit = __uint_as_float(lg[j]);
+                if (j < n_actions) best = fmaxf(best, pack_key(P.greedy ? logit : gumbel_key(logit, nbase, a, j), j));
+            }
+            const int chosen = 31 - (int)(__float_as_uint(best) & 31u);
+            act[a] = chosen < n_actions ? chosen : 0;  // every key NaN: action 0
+            if (a == 0) {  // D2 / D1 are overwritten by the next agent's layer 1
+                tc_fence_before();
+                __syncthreads();
+            }
+        }
+        if (env < P.n) {
+            if (P.act_dtype == PZ_ACT_U8)
+                reinterpret_cast<uchar2 *>(P.actions)[env] = make_uchar2((unsigned char)act[0], (unsigned char)act[1]);
+            else if (P.act_dtype == PZ_ACT_I32)
+                reinterpret_cast<int2 *>(P.actions)[env] = make_int2(act[0], act[1]);
+            else
+                reinterpret_cast<longlong2 *>(P.actions)[env] = make_longlong2(act[0], act[1]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
+template <int NA>
+static cudaError_t launch_one(const Params &P, unsigned grid, cudaStream_t stream, int dev) {
+    static std::mutex mu;
+    static bool attr_set[64] = {};
+    {  // more than 48 KB of dynamic shared memory needs the opt-in, once per device
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(pz_policy_mlp_tc_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)kSmemBytes);
+            if (e != cudaSuccess) return e;
+            attr_set[dev] = true;
+        }
+    }
+    pz_policy_mlp_tc_kernel<NA><<<grid, kThreads, kSmemBytes, stream>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace tc
+
+int launch_tc(const Params &P, cudaStream_t stream) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t tiles = (P.n + tc::kTileEnvs - 1) / tc::kTileEnvs;
+    const int64_t resident = (int64_t)sms * tc::kCtasPerSm;  // persistent over tiles: weights and TMEM once per CTA
+    const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
+    cudaError_t err;
+    if (P.n_actions == 18)
+        err = tc::launch_one<18>(P, grid, stream, dev);
+    else if (P.n_actions == 13)
+        err = tc::launch_one<13>(P, grid, stream, dev);
+    else
+        err = tc::launch_one<0>(P, grid, stream, dev);
+    return err == cudaSuccess ? 0 : (int)err;
+}
+
+}  // namespace pzp
