@@ -40,14 +40,23 @@ __device__ __forceinline__ uint32_t noise_base(uint64_t seed, uint64_t step, uin
     z = z ^ (z >> 31);
     return (uint32_t)z;
 }
-__device__ __forceinline__ float gumbel_key(float logit, uint32_t base, int agent, int action) {
-    uint32_t x = base + (uint32_t)(32 * agent + action + 1) * 0x9E3779B9u;  // base is already well mixed
+// u = ((x >> 9) + 0.5) / 2^23 in (0, 1), exact: the 23 bits are placed as the mantissa of a float in [1, 2) and
+// 1 - 2^-24 is subtracted (both steps exact) — one logic and one add instruction instead of a conversion on the
+// special-function pipe, which the two logarithms already load
+__device__ __forceinline__ float gumbel_from_bits(float logit, uint32_t x) {
     x *= 0x7feb352du;
     x ^= x >> 15;
     x *= 0x846ca68bu;
     x ^= x >> 16;
-    const float u = fmaf((float)(x >> 9), 1.0f / 8388608.0f, 0.5f / 8388608.0f);  // (0, 1), exact
+    const float u = __uint_as_float(0x3F800000u | (x >> 9)) + (-1.0f + 5.9604644775390625e-08f);
     return fmaf(-0.693147182f, lg2_approx(-lg2_approx(u)), logit);
+}
+__device__ __forceinline__ float gumbel_key(float logit, uint32_t base, int agent, int action) {
+    return gumbel_from_bits(logit, base + (uint32_t)(32 * agent + action + 1) * 0x9E3779B9u);  // base is already well mixed
+}
+// the same with `agent_base` = base + 32 * agent * 0x9E3779B9 hoisted by the caller
+__device__ __forceinline__ float gumbel_key_from(float logit, uint32_t agent_base, int action) {
+    return gumbel_from_bits(logit, agent_base + (uint32_t)(action + 1) * 0x9E3779B9u);
 }
 
 // The arg-max runs on keys that carry their action in the five low mantissa bits (31 - action, so that among

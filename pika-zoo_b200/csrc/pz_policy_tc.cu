@@ -1,25 +1,27 @@
-// pz_policy_mlp_act on the 5th-generation tensor cores (tcgen05 + TMEM), the default implementation.
+// pz_policy_mlp_act on the 5th-generation tensor cores (tcgen05 + TMEM).
 //
-// A CTA of 128 threads owns a tile of 128 envs: thread t IS env t of the tile from the first epilogue on, which
-// is what makes this form cheap — in the warp-level mma.sync kernel (pz_policy.cu) a warp's 16 envs are spread
-// over accumulator fragments, so every hidden activation is rectified / packed and every Gumbel key is built in
-// fragment order (24 candidate slots per quad for 18 actions, quad shuffles for the arg-max), ~1,180 warp
-// instructions per 16 envs. Here, per agent:
+// Thread t of a 128-env tile IS env t from the first epilogue on, which is what makes this form cheap: in the
+// warp-level mma.sync kernel (pz_policy.cu) a warp's 16 envs are spread over accumulator fragments, so every
+// hidden activation is rectified / packed and every Gumbel key is built in fragment order (24 candidate slots
+// per quad for 18 actions, quad shuffles for the arg-max), ~1,180 warp instructions per 16 envs. Here, per
+// (tile, agent):
 //
-//   layer 1   D1[128 envs][80 hidden]  = X^T[128][48] . W1^T      one thread issues 3 tcgen05.mma (K = 16 each);
+//   layer 1   D1[128 envs][80 hidden]  = X^T[128][48] . W1^T      3 tcgen05.mma (K = 16 each), one issuing thread;
 //             (TMEM, fp32, 80 columns)                            A = the observation tile as it lies in the
 //                                                                 feature-major tensor (MN-major, no swizzle),
 //                                                                 B = W1 (K-major), both in shared memory
 //   epilogue  thread t reads row t of D1 (tcgen05.ld 32x32b), rectifies, rounds to bf16 and stores the 40 packed
-//             pairs back to TMEM (tcgen05.st) as row t of H
+//             pairs back over the columns it has read (tcgen05.st) as row t of H
 //   layer 2   D2[128][32]              = H[128][80] . W2^T        5 tcgen05.mma with A taken from TMEM
 //   sample    thread t reads its env's logits (one row of D2) and takes argmax(logit + Gumbel) over exactly
 //             n_actions candidates in registers: no shuffles, no padded slots
 //
-// TMEM: 128 columns per CTA (D1 0..79, H 80..119, D2 reuses 0..31), four CTAs per SM fill the 512 columns.
-// Shared memory: 24 KB of observation tile (both agents) + 25 KB of weights, staged once per persistent CTA.
-// The tensor-core work of a CTA is strictly serial (MMA -> epilogue -> MMA -> sample, twice per tile); the four
-// resident CTAs of an SM overlap each other's loads, MMAs and epilogues.
+// The tensor-core work of one tile is a serial chain (MMA -> epilogue -> MMA -> sample) of latencies, so the SM
+// is filled with independent chains: ONE persistent CTA per SM holds the weights once and runs three chains of
+// 256 threads (warps 0-3: agent 0, warps 4-7: agent 1 of the same tile, so both agents' layers go out in one
+// batch of MMAs and their epilogues run side by side), each with its own named barrier, mbarrier, 160 TMEM
+// columns (per agent: D1 0..79, H in place 0..39, D2 40..71) and a double-buffered observation tile whose next
+// instance is fetched with cp.async while the current one is computed.
 //
 // Canonical shared-memory layouts (no swizzle; 8 x 16-byte "core matrices" of 128 contiguous bytes):
 //   X  (MN-major A): element (env m, feature k) at (k / 8) * 2048 + (m / 8) * 128 + (k % 8) * 16 + (m % 8) * 2
@@ -38,25 +40,29 @@
 namespace pzp {
 namespace tc {
 
-constexpr int kThreads = 128;
+constexpr int kChains = 3;          // per CTA = per SM
+constexpr int kChainThreads = 256;  // 8 warps: agent = warp / 4 within the chain, env row = 32 * (warp % 4) + lane
+constexpr int kThreads = kChains * kChainThreads;
 constexpr int kTileEnvs = 128;
 constexpr int kKP = PZ_POLICY_MAX_FEATURES;  // 48 = 3 k-steps of 16
 constexpr int kHP = PZ_POLICY_MAX_HIDDEN;    // 80: N of layer 1 (multiple of 16), 5 k-steps of layer 2
 constexpr int kAP = 32;                      // N of layer 2: PZ_POLICY_MAX_ACTIONS (24) padded to a multiple of 16
-constexpr int kCtasPerSm = 4;
-constexpr uint32_t kTmemCols = 128;          // per CTA; 4 CTAs x 128 = the SM's 512 columns
-constexpr uint32_t kColD1 = 0, kColH = kHP, kColD2 = 0;
-static_assert(kHP + kHP / 2 <= (int)kTmemCols && kAP <= kHP, "TMEM columns");
+constexpr uint32_t kTmemCols = 512;          // the whole SM
+constexpr uint32_t kAgentCols = kHP, kChainCols = 2 * kAgentCols;
+constexpr uint32_t kColD1 = 0, kColH = 0, kColD2 = kHP / 2;  // H overwrites the columns of D1 its thread has read
+static_assert(kChains * kChainCols <= kTmemCols && kHP / 2 + kAP <= kHP, "TMEM columns");
 static_assert(PZ_POLICY_MAX_ACTIONS <= kAP && kKP % 16 == 0 && kHP % 16 == 0, "tile shapes");
 
 constexpr int kXKGroup = (kTileEnvs / 8) * 128;    // 2048 B: one group of 8 features, 16 env atoms
 constexpr int kXAgent = (kKP / 8) * kXKGroup;      // 12288 B
+constexpr int kXTile = 2 * kXAgent;                // both agents
 constexpr int kW1KGroup = (kHP / 8) * 128;         // 1280 B
 constexpr int kW1Agent = (kKP / 8) * kW1KGroup;    // 7680 B
 constexpr int kW2KGroup = (kAP / 8) * 128;         // 512 B
 constexpr int kW2Agent = (kHP / 8) * kW2KGroup;    // 5120 B
-constexpr int kOffX = 0, kOffW1 = 2 * kXAgent, kOffW2 = kOffW1 + 2 * kW1Agent, kOffBar = kOffW2 + 2 * kW2Agent;
-constexpr size_t kSmemBytes = kOffBar + 16;        // + mbarrier (8 B) + TMEM base address (4 B)
+constexpr int kOffW1 = 0, kOffW2 = 2 * kW1Agent, kOffX = kOffW2 + 2 * kW2Agent;  // X: [chain][buffer][agent]
+constexpr int kOffBar = kOffX + kChains * 2 * kXTile;
+constexpr size_t kSmemBytes = kOffBar + 32;        // + one mbarrier per chain (8 B each) + TMEM base address (4 B)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -98,13 +104,13 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // Bounded: a wrong descriptor must end in a launch failure, not in a hung device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    for (uint32_t spins = 0; !done; spins++) {
+    for (uint32_t spins = 0; !done; spins++) {  // try_wait suspends the thread up to the hinted time before it returns
         asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(0x989680u)
             : "memory");
-        if (!done && spins > (1u << 22)) __trap();
+        if (!done && spins > (1u << 20)) __trap();
     }
 }
 
@@ -137,26 +143,29 @@ __device__ __forceinline__ uint32_t relu_pack(uint32_t lo_bits, uint32_t hi_bits
     return *reinterpret_cast<const uint32_t *>(&v);
 }
 
+__device__ __forceinline__ void chain_sync(int chain) {
+    asm volatile("bar.sync %0, %1;" ::"r"(chain + 1), "r"(kChainThreads) : "memory");
+}
+
 template <int NA>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) pz_policy_mlp_tc_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __grid_constant__ Params P) {
     const int n_actions = NA ? NA : P.n_actions;
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
-    const uint32_t bar = s_base + kOffBar;
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kOffBar + 8);
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kOffBar + 24);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chain = warp >> 3, wic = warp & 7, agent = wic >> 2, ctid = tid - chain * kChainThreads;
+    const uint32_t bar = s_base + kOffBar + 8 * chain;
 
-    // ---- once per CTA: TMEM columns, the barrier, zeroed operands, the weights in canonical K-major order ----
+    // ---- once per CTA: TMEM, the barriers, zeroed operands, the weights in canonical K-major order ----
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + kOffBar + 8),
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + kOffBar + 24),
                      "r"(kTmemCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1u) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    if (ctid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1u) : "memory");
+    if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int i = tid; i < kOffBar / 16; i += kThreads) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     {
@@ -176,128 +185,166 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) pz_policy_mlp_tc_kernel(
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 lanes (rows) of the tile
-    uint32_t phase = 0;
+    const uint32_t t_chain = tmem + chain * kChainCols;                                       // lane 0: MMA operands
+    const uint32_t t_row = t_chain + agent * kAgentCols + ((uint32_t)((wic & 3) * 32) << 16);  // this thread's row
+    const uint32_t s_x = s_base + kOffX + chain * 2 * kXTile;
 
     constexpr uint32_t kIdesc1 = instr_desc(kHP, true), kIdesc2 = instr_desc(kAP, false);
     const bool vec_ok = (P.ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(P.obs) & 15u) == 0);
-    const int k_groups = (P.k1 + 7) >> 3;
     const int64_t n_tiles = (P.n + kTileEnvs - 1) / kTileEnvs;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t env0 = tile * kTileEnvs;
-        // ---- observation tile, both agents. The MMAs that read the previous tile have completed (their
-        //      mbarrier was waited on), so the buffer is free.
+    const int64_t t_stride = (int64_t)gridDim.x * kChains;
+
+    // The chain's 256 threads fill one tile (both agents): warps 0-3 agent 0, warps 4-7 agent 1; per pass one group
+    // of 8 features, lane = (feature % 8) + 8 * (env atom % 4), warp % 4 = env atom / 4 — a warp writes 512
+    // contiguous bytes of shared memory and reads 8 rows x 64 contiguous bytes.
+    auto load_tile = [&](int64_t t, uint32_t b) {
+        const int64_t env0 = t * kTileEnvs;
         if (vec_ok && env0 + kTileEnvs <= P.n) {
-            // one (agent, group of 8 features) per pass: lane = (feature % 8) + 8 * (env atom % 4), warp = env atom / 4:
-            // a warp writes 512 contiguous bytes of shared memory and reads 8 rows x 64 contiguous bytes
-            const int kr = lane & 7, m8 = warp * 4 + (lane >> 3);
-            const __nv_bfloat16 *src0 = P.obs + env0 + m8 * 8;
-            const uint32_t dst0 = s_base + kOffX + m8 * 128 + kr * 16;
-            for (int a = 0; a < 2; a++)
-                for (int kg = 0; kg < k_groups; kg++) {
-                    const int k = kg * 8 + kr;
-                    if (k < P.k1)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + a * kXAgent + kg * kXKGroup),
-                                     "l"(src0 + ((int64_t)a * P.rows + k) * P.ld)
-                                     : "memory");
-                }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const int kr = lane & 7, m8 = (wic & 3) * 4 + (lane >> 3);
+            const __nv_bfloat16 *src = P.obs + ((int64_t)agent * P.rows + kr) * P.ld + env0 + m8 * 8;
+            uint32_t dst = s_x + b * kXTile + agent * kXAgent + m8 * 128 + kr * 16;
+            for (int k = kr; k < P.k1; k += 8, src += 8 * P.ld, dst += kXKGroup)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
         } else {  // ragged last tile or unaligned rows
-            __nv_bfloat16 *xs = reinterpret_cast<__nv_bfloat16 *>(smem + kOffX);
+            __nv_bfloat16 *xs = reinterpret_cast<__nv_bfloat16 *>(smem + kOffX + (chain * 2 + b) * kXTile);
             const __nv_bfloat16 zero = __float2bfloat16(0.0f);
-            for (int i = tid; i < 2 * P.k1 * kTileEnvs; i += kThreads) {
+            for (int i = ctid; i < 2 * P.k1 * kTileEnvs; i += kChainThreads) {
                 const int a = i / (P.k1 * kTileEnvs), rem = i - a * (P.k1 * kTileEnvs), k = rem / kTileEnvs,
                           m = rem % kTileEnvs;
                 xs[(a * kXAgent + (k >> 3) * kXKGroup + (m >> 3) * 128 + (k & 7) * 16 + (m & 7) * 2) >> 1] =
                     env0 + m < P.n ? P.obs[((int64_t)a * P.rows + k) * P.ld + env0 + m] : zero;
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tc_fence_before();  // the previous tile's TMEM reads are ordered before the MMAs issued after this barrier
-        __syncthreads();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
 
-        const int64_t env = env0 + tid;
+    // layer 1 of both agents of the tile in buffer b -> D1 (one thread)
+    auto issue_layer1 = [&](uint32_t b) {
+        tc_fence_after();
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int ks = 0; ks < kKP / 16; ks++)
+                mma_ss(t_chain + a * kAgentCols + kColD1,
+                       smem_desc(s_x + b * kXTile + a * kXAgent + ks * 2 * kXKGroup, kXKGroup, 128),
+                       smem_desc(s_base + kOffW1 + a * kW1Agent + ks * 2 * kW1KGroup, kW1KGroup, 128), kIdesc1, ks > 0);
+        mma_commit(bar);
+    };
+    // cp.async data of every group but the newest has landed -> visible to the tensor core after the chain's barrier
+    auto tile_ready = [&]() {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();  // and this thread's TMEM reads are ordered before the MMAs issued after the barrier
+        chain_sync(chain);
+    };
+
+    // Software pipeline over the chain's tiles t0, t1 = t0 + stride, ...: the tile after next is fetched while a
+    // tile is computed, and layer 1 of the NEXT tile is issued as soon as every thread holds this tile's logits in
+    // registers, so its round trip through the tensor core hides behind the sampling arithmetic.
+    int64_t tile = blockIdx.x + (int64_t)gridDim.x * chain;
+    uint32_t buf = 0, phase = 0;
+    if (tile < n_tiles) {
+        load_tile(tile, 0);
+        if (tile + t_stride < n_tiles)
+            load_tile(tile + t_stride, 1);
+        else
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        tile_ready();
+        if (ctid == 0) issue_layer1(0);
+    }
+    for (; tile < n_tiles; tile += t_stride, buf ^= 1u) {
+        const int64_t env = tile * kTileEnvs + (wic & 3) * 32 + lane;
         const uint32_t nbase = P.greedy ? 0u : noise_base(P.seed, P.step, P.first_env + (uint64_t)env);
-        int act[2];
+        mbar_wait(bar, phase);  // layer 1 of this tile
+        phase ^= 1u;
+        tc_fence_after();
+        // its buffer is free: the tile after next travels while this one and the next are computed
+        if (tile + 2 * t_stride < n_tiles)
+            load_tile(tile + 2 * t_stride, buf);
+        else
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        // ---- relu, round to bf16, back to TMEM as the A operand of layer 2 (thread = env row of its agent).
+        //      H column j holds hidden units 2j, 2j+1: it overwrites D1 columns this thread has already read.
+        {
+            uint32_t v[2][16], h[8];
 #pragma unroll
-        for (int a = 0; a < 2; a++) {
-            // ---- layer 1 -> D1
-            if (tid == 0) {
-                tc_fence_after();
-#pragma unroll
-                for (int ks = 0; ks < kKP / 16; ks++)
-                    mma_ss(tmem + kColD1, smem_desc(s_base + kOffX + a * kXAgent + ks * 2 * kXKGroup, kXKGroup, 128),
-                           smem_desc(s_base + kOffW1 + a * kW1Agent + ks * 2 * kW1KGroup, kW1KGroup, 128), kIdesc1, ks > 0);
-                mma_commit(bar);
-            }
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-            tc_fence_after();
-            // ---- relu, round to bf16, back to TMEM as the A operand of layer 2 (thread = env row)
-#pragma unroll
-            for (int c = 0; c < kHP / 16; c++) {
-                uint32_t v[16], h[8];
-                tmem_ld16(t_row + kColD1 + 16 * c, v);
+            for (int c = 0; c < kHP / 16; c += 2) {
+                tmem_ld16(t_row + kColD1 + 16 * c, v[0]);
+                if (c + 1 < kHP / 16) tmem_ld16(t_row + kColD1 + 16 * (c + 1), v[1]);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 8; j++) h[j] = relu_pack(v[2 * j], v[2 * j + 1]);
-                tmem_st8(t_row + kColH + 8 * c, h);
+                for (int q = 0; q < 2; q++)
+                    if (c + q < kHP / 16) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) h[j] = relu_pack(v[q][2 * j], v[q][2 * j + 1]);
+                        tmem_st8(t_row + kColH + 8 * (c + q), h);
+                    }
             }
-            tmem_st_wait();
-            tc_fence_before();
-            __syncthreads();
-            // ---- layer 2 -> D2 (over D1's columns: every thread has read its row)
-            if (tid == 0) {
-                tc_fence_after();
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        chain_sync(chain);
+        // ---- layer 2 of both agents -> D2
+        if (ctid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int a = 0; a < 2; a++)
 #pragma unroll
                 for (int j = 0; j < kHP / 16; j++)
-                    mma_ts(tmem + kColD2, tmem + kColH + 8 * j,
+                    mma_ts(t_chain + a * kAgentCols + kColD2, t_chain + a * kAgentCols + kColH + 8 * j,
                            smem_desc(s_base + kOffW2 + a * kW2Agent + j * 2 * kW2KGroup, kW2KGroup, 128), kIdesc2, j > 0);
-                mma_commit(bar);
-            }
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-            tc_fence_after();
-            // ---- this env's logits, the sample
-            uint32_t lg[24];
-            {
-                uint32_t v16[16], v8[8];
-                tmem_ld16(t_row + kColD2, v16);
-                if (NA == 0 || NA > 16) tmem_ld8(t_row + kColD2 + 16, v8);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; j++) lg[j] = v16[j];
-#pragma unroll
-                for (int j = 0; j < 8; j++) lg[16 + j] = (NA == 0 || NA > 16) ? v8[j] : 0u;
-            }
-            if (P.logits != nullptr && env < P.n) {  // launch-uniform pointer
-#pragma unroll
-                for (int j = 0; j < (NA ? NA : PZ_POLICY_MAX_ACTIONS); j++)
-                    if (j < n_actions) P.logits[(env * 2 + a) * n_actions + j] = __uint_as_float(lg[j]);
-            }
-            float best = pack_key(-INFINITY, 31);
-#pragma unroll
-            for (int j = 0; j < (NA ? NA : PZ_POLICY_MAX_ACTIONS); j++) {
-                const float logit = __uint_as_float(lg[j]);
-                if (j < n_actions) best = fmaxf(best, pack_key(P.greedy ? logit : gumbel_key(logit, nbase, a, j), j));
-            }
-            const int chosen = 31 - (int)(__float_as_uint(best) & 31u);
-            act[a] = chosen < n_actions ? chosen : 0;  // every key NaN: action 0
-            if (a == 0) {  // D2 / D1 are overwritten by the next agent's layer 1
-                tc_fence_before();
-                __syncthreads();
-            }
+            mma_commit(bar);
         }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+        // ---- this (env, agent)'s logits into registers; then the tensor core can have the columns back
+        uint32_t lg[24];
+        {
+            uint32_t v16[16], v8[8];
+            tmem_ld16(t_row + kColD2, v16);
+            if (NA == 0 || NA > 16) tmem_ld8(t_row + kColD2 + 16, v8);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; j++) lg[j] = v16[j];
+#pragma unroll
+            for (int j = 0; j < 8; j++) lg[16 + j] = (NA == 0 || NA > 16) ? v8[j] : 0u;
+        }
+        if (tile + t_stride < n_tiles) {  // chain-uniform
+            tile_ready();
+            if (ctid == 0) issue_layer1(buf ^ 1u);
+        }
+        // ---- the sample
+        if (P.logits != nullptr && env < P.n) {  // launch-uniform pointer
+#pragma unroll
+            for (int j = 0; j < (NA ? NA : PZ_POLICY_MAX_ACTIONS); j++)
+                if (j < n_actions) P.logits[(env * 2 + agent) * n_actions + j] = __uint_as_float(lg[j]);
+        }
+        // branch-free over the candidates (the greedy test is hoisted), so that the keys' dependent chains
+        // (two multiplies, two logarithms each) interleave
+        float best = pack_key(-INFINITY, 31);
+        if (P.greedy) {
+#pragma unroll
+            for (int j = 0; j < (NA ? NA : PZ_POLICY_MAX_ACTIONS); j++)
+                if (j < n_actions) best = fmaxf(best, pack_key(__uint_as_float(lg[j]), j));
+        } else {
+            const uint32_t agent_base = nbase + (uint32_t)(32 * agent) * 0x9E3779B9u;
+#pragma unroll
+            for (int j = 0; j < (NA ? NA : PZ_POLICY_MAX_ACTIONS); j++)
+                if (j < n_actions) best = fmaxf(best, pack_key(gumbel_key_from(__uint_as_float(lg[j]), agent_base, j), j));
+        }
+        int act = 31 - (int)(__float_as_uint(best) & 31u);
+        if (act >= n_actions) act = 0;  // every key NaN: action 0
         if (env < P.n) {
             if (P.act_dtype == PZ_ACT_U8)
-                reinterpret_cast<uchar2 *>(P.actions)[env] = make_uchar2((unsigned char)act[0], (unsigned char)act[1]);
+                reinterpret_cast<unsigned char *>(P.actions)[env * 2 + agent] = (unsigned char)act;
             else if (P.act_dtype == PZ_ACT_I32)
-                reinterpret_cast<int2 *>(P.actions)[env] = make_int2(act[0], act[1]);
+                reinterpret_cast<int *>(P.actions)[env * 2 + agent] = act;
             else
-                reinterpret_cast<longlong2 *>(P.actions)[env] = make_longlong2(act[0], act[1]);
+                reinterpret_cast<long long *>(P.actions)[env * 2 + agent] = act;
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
@@ -325,9 +372,10 @@ static cudaError_t launch_one(const Params &P, unsigned grid, cudaStream_t strea
 int launch_tc(const Params &P, cudaStream_t stream) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // one persistent CTA per SM (it owns the SM's TMEM); chain c of CTA b walks tiles b + grid * (c + 3 i), so a
+    // batch of fewer tiles than SMs still spreads one tile per SM
     const int64_t tiles = (P.n + tc::kTileEnvs - 1) / tc::kTileEnvs;
-    const int64_t resident = (int64_t)sms * tc::kCtasPerSm;  // persistent over tiles: weights and TMEM once per CTA
-    const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
     cudaError_t err;
     if (P.n_actions == 18)
         err = tc::launch_one<18>(P, grid, stream, dev);
