@@ -473,15 +473,29 @@ def run_b200_arm(args):
         tf = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-        a.record()
-        for _ in range(200):
-            actor(v.obs)
-        b.record()
-        torch.cuda.synchronize()
+        lib = pikazoo_b200.load_library()
+
+        def policy_kernel_us():
+            a.record()
+            for _ in range(200):
+                actor(v.obs)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) * 1e3 / 200
+
+        tc_us = policy_kernel_us()
+        prev = lib.pz_policy_select(1)  # A/B: the warp-level mma.sync implementation of the same definition
+        try:
+            for _ in range(5):
+                actor(v.obs)
+            mma_us = policy_kernel_us()
+        finally:
+            lib.pz_policy_select(prev)
         variants["configs[4]_fused_policy_kernel_loop_2M_envs_per_gpu"] = {
             "ms_per_step": float(tf.item()) / 200, "env_steps_per_sec": n5 * world * 200 / (float(tf.item()) * 1e-3),
-            "of_which_policy_kernel_us": a.elapsed_time(b) * 1e3 / 200,
-            "note": "policy = pz_policy_mlp_act (mma.sync bf16, one pass over the 160 B of observations per env)"}
+            "of_which_policy_kernel_us": tc_us, "policy_kernel_us_mma_sync_implementation": mma_us,
+            "note": "policy = pz_policy_mlp_act (tcgen05.mma, accumulators and hidden activations in TMEM, one pass "
+                    "over the 160 B of observations per env)"}
         del v, pol, actor
         return variants
 

@@ -235,7 +235,7 @@ void pz_host_destroy(pz_host_ctx *ctx);
  * switches process-wide and returns the previous choice, or -1 for an unknown code. */
 #define PZ_POLICY_IMPL_TCGEN05 0
 #define PZ_POLICY_IMPL_MMA_SYNC 1
-#define PZ_POLICY_IMPL_DEFAULT PZ_POLICY_IMPL_MMA_SYNC
+#define PZ_POLICY_IMPL_DEFAULT PZ_POLICY_IMPL_TCGEN05
 int pz_policy_select(int32_t impl);
 #define PZ_POLICY_MAX_FEATURES 48
 #define PZ_POLICY_MAX_HIDDEN 80

@@ -59,11 +59,7 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// relu commutes with the rounding: convert the pair first, then one packed max against zero
-__device__ __forceinline__ uint32_t relu_pack(float lo, float hi) {
-    const __nv_bfloat162 v = __hmax2(__floats2bfloat162_rn(lo, hi), __floats2bfloat162_rn(0.0f, 0.0f));
-    return *reinterpret_cast<const uint32_t *>(&v);
-}
+__device__ __forceinline__ uint32_t relu_pack(float lo, float hi) { return relu_pack_bf16x2(lo, hi); }
 
 constexpr size_t kSmemBytes = sizeof(__nv_bfloat16) * 2 * kKP * kXS + sizeof(uint32_t) * (kW1Words + kW2Words);
 

@@ -64,7 +64,14 @@ __device__ __forceinline__ float gumbel_key_from(float logit, uint32_t agent_bas
 // shuffle + one FMNMX per reduction step instead of compare-and-select pairs on (key, action). The 2^-19
 // relative truncation of the key is far below the noise resolution.
 __device__ __forceinline__ float pack_key(float key, int action) {
-    return __uint_as_float((__float_as_uint(key) & ~31u) | (uint32_t)(31 - action));
+    return __uint_as_float((__float_as_uint(key) | 31u) ^ (uint32_t)action);  // low five bits = 31 - action: one LOP3
+}
+
+// Two fp32 values rectified and rounded to a packed bf16 pair (low half = lo) in one conversion instruction
+__device__ __forceinline__ uint32_t relu_pack_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
 }
 
 // pz_policy_tc.cu

@@ -101,6 +101,9 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+#ifndef PZ_TC_WAIT_HINT
+#define PZ_TC_WAIT_HINT 0x989680u
+#endif
 // Bounded: a wrong descriptor must end in a launch failure, not in a hung device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
@@ -108,7 +111,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity), "r"(0x989680u)
+            : "r"(bar), "r"(parity), "r"(PZ_TC_WAIT_HINT)
             : "memory");
         if (!done && spins > (1u << 20)) __trap();
     }
@@ -136,11 +139,8 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// relu commutes with the rounding: convert the pair first, then one packed max against zero
 __device__ __forceinline__ uint32_t relu_pack(uint32_t lo_bits, uint32_t hi_bits) {
-    const __nv_bfloat162 v =
-        __hmax2(__floats2bfloat162_rn(__uint_as_float(lo_bits), __uint_as_float(hi_bits)), __floats2bfloat162_rn(0.0f, 0.0f));
-    return *reinterpret_cast<const uint32_t *>(&v);
+    return relu_pack_bf16x2(__uint_as_float(lo_bits), __uint_as_float(hi_bits));
 }
 
 __device__ __forceinline__ void chain_sync(int chain) {

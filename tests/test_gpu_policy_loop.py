@@ -116,7 +116,19 @@ def test_step_loop_is_cuda_graph_capturable(cuda_lib):
     assert torch.equal(graphed.obs, eager.obs) and torch.equal(graphed.stats, eager.stats)
 
 
-# ---- the fused policy kernel (csrc/pz_policy.cu) -------------------------------------------------------
+# ---- the fused policy kernel (csrc/pz_policy_tc.cu: tcgen05 + TMEM, the default; csrc/pz_policy.cu: mma.sync) ----
+IMPLS = {"tcgen05": 0, "mma_sync": 1}
+
+
+@pytest.fixture(params=sorted(IMPLS))
+def fused_impl(request, cuda_lib):
+    """Every test of the fused kernel runs on both implementations of pz_policy_mlp_act."""
+    prev = cuda_lib.pz_policy_select(IMPLS[request.param])
+    assert prev in (0, 1)
+    yield request.param
+    cuda_lib.pz_policy_select(prev)
+
+
 def _reference_logits(policy, obs):
     """[N, 2, A] float32 from plain PyTorch fp32 arithmetic on the same bf16 values, hidden activations rounded
     to bf16 where the kernel rounds them."""
@@ -138,7 +150,7 @@ def _played_env(n, **kw):
 
 
 @pytest.mark.parametrize("n", [64, 1000, 4096 + 8, 100_003])
-def test_fused_policy_logits_and_greedy_actions(cuda_lib, n):
+def test_fused_policy_logits_and_greedy_actions(cuda_lib, fused_impl, n):
     """Floating point: the fused kernel's logits against a PyTorch fp32 reference of the same network.
     Tolerance 2e-3 absolute (fp32 sums in another order can round a hidden activation to the neighbouring
     bf16, 2^-8 relative, which reaches a logit through one weight of magnitude ~0.1). Greedy actions are the
@@ -167,7 +179,7 @@ def test_fused_policy_logits_and_greedy_actions(cuda_lib, n):
 
 
 @pytest.mark.parametrize("n_actions", [13, 7, 24])
-def test_fused_policy_other_action_counts(cuda_lib, n_actions):
+def test_fused_policy_other_action_counts(cuda_lib, fused_impl, n_actions):
     """13 actions (SimplifyAction) has its own instantiation, other counts take the generic one."""
     from pikazoo_b200.policy import MLPPolicy, gumbel_noise_reference, sample_reference
 
@@ -184,7 +196,7 @@ def test_fused_policy_other_action_counts(cuda_lib, n_actions):
     assert np.array_equal(g.cpu().numpy().astype(np.int64), sample_reference(logits.cpu().numpy(), None))
 
 
-def test_fused_policy_sampling_is_the_documented_argmax(cuda_lib):
+def test_fused_policy_sampling_is_the_documented_argmax(cuda_lib, fused_impl):
     """actions == argmax(logits + Gumbel noise) with the noise restated in numpy from the counters. The kernel
     takes its logarithms from the hardware approximation, so keys differ by a few float32 ulp: every mismatch
     must be a near-tie, and there must be next to none."""
@@ -210,7 +222,7 @@ def test_fused_policy_sampling_is_the_documented_argmax(cuda_lib):
     assert torch.equal(a0, policy.act_fused(env.obs, step=1))
 
 
-def test_fused_policy_samples_follow_softmax(cuda_lib):
+def test_fused_policy_samples_follow_softmax(cuda_lib, fused_impl):
     """Statistics: after reset every env shows the same observation, so N envs are N independent samples of
     one categorical distribution; the frequencies must match softmax(logits) within five standard errors."""
     import pikazoo_b200
@@ -233,7 +245,7 @@ def test_fused_policy_samples_follow_softmax(cuda_lib):
         assert np.all(np.abs(freq - p[agent]) < 5 * se + 1e-6), (agent, freq, p[agent])
 
 
-def test_fused_actor_rollout_loop_matches_oracle(cuda_lib):
+def test_fused_actor_rollout_loop_matches_oracle(cuda_lib, fused_impl):
     """configs[4] with the fused actor: uint8 actions straight from the policy kernel into the step kernel; the
     oracle replays them."""
     import pikazoo_b200
@@ -261,7 +273,7 @@ def test_fused_actor_rollout_loop_matches_oracle(cuda_lib):
     assert seen["done"] > n // 4 and len(seen["distinct"]) == 18
 
 
-def test_fused_policy_rejects_bad_arguments(cuda_lib):
+def test_fused_policy_rejects_bad_arguments(cuda_lib, fused_impl):
     from pikazoo_b200 import _lib
     from pikazoo_b200.policy import MLPPolicy
 
@@ -278,3 +290,33 @@ def test_fused_policy_rejects_bad_arguments(cuda_lib):
         b = list(args)
         b[pos] = bad
         assert L.pz_policy_mlp_act(*b) < 0, pos
+
+
+@pytest.mark.parametrize("n,n_actions", [(128, 18), (1000, 18), (4096 + 8, 13), (1 << 17, 18), (300_001, 7)])
+def test_fused_policy_implementations_agree(cuda_lib, n, n_actions):
+    """The tcgen05 kernel and the warp-level mma.sync kernel are two implementations of ONE definition: same
+    logits (both accumulate the same bf16 products in fp32, sixteen features at a time) and therefore the same
+    greedy and sampled actions, including ragged last tiles and batches smaller than one tile per SM."""
+    from pikazoo_b200.policy import MLPPolicy
+
+    env = _played_env(n)
+    policy = MLPPolicy(n_actions=n_actions, device=env.device, seed=8)
+    with torch.no_grad():  # non-zero biases
+        policy.w1[:, : policy.hidden, policy.ONES_ROW] = 0.25
+        policy.w2[:, :, policy.hidden] = -0.5
+    got = {}
+    prev = cuda_lib.pz_policy_select(0)
+    try:
+        for name, code in IMPLS.items():
+            assert cuda_lib.pz_policy_select(code) in (0, 1)
+            logits = torch.full((n, 2, n_actions), float("nan"), device="cuda")
+            sampled = policy.act_fused(env.obs, step=6, seed=2, first_env=5, logits_out=logits).clone()
+            greedy = policy.act_fused(env.obs, step=6, greedy=True, action_dtype=torch.int64).clone()
+            got[name] = (logits, sampled, greedy)
+    finally:
+        cuda_lib.pz_policy_select(prev)
+    (l0, s0, g0), (l1, s1, g1) = got["tcgen05"], got["mma_sync"]
+    assert not torch.isnan(l0).any() and not torch.isnan(l1).any()
+    assert float((l0 - l1).abs().max()) <= 1e-5  # measured: bit-identical
+    assert float((s0 != s1).float().mean()) <= 1e-4 and float((g0 != g1).float().mean()) <= 1e-4
+    assert cuda_lib.pz_policy_select(7) == -1  # unknown code: refused, selection unchanged
