@@ -16,12 +16,15 @@
 //   sample    thread t reads its env's logits (one row of D2) and takes argmax(logit + Gumbel) over exactly
 //             n_actions candidates in registers: no shuffles, no padded slots
 //
-// The tensor-core work of one tile is a serial chain (MMA -> epilogue -> MMA -> sample) of latencies, so the SM
-// is filled with independent chains: ONE persistent CTA per SM holds the weights once and runs three chains of
-// 256 threads (warps 0-3: agent 0, warps 4-7: agent 1 of the same tile, so both agents' layers go out in one
-// batch of MMAs and their epilogues run side by side), each with its own named barrier, mbarrier, 160 TMEM
-// columns (per agent: D1 0..79, H in place 0..39, D2 40..71) and a double-buffered observation tile whose next
-// instance is fetched with cp.async while the current one is computed.
+// The tensor-core work of one (tile, agent) is a serial chain (MMA -> epilogue -> MMA -> sample) of latencies, and
+// a chain holds 80 TMEM columns while it runs (D1 0..79, H in place 0..39, D2 40..71), so the SM's 512 columns
+// carry six of them: ONE persistent CTA per SM stages the weights once and runs six chains of 128 threads, two per
+// tile (one per agent), each with its own named barrier, mbarrier, TMEM columns and a double-buffered observation
+// tile: the tile after next is fetched with cp.async while a tile is computed, and layer 1 of the NEXT tile is
+// issued as soon as every thread holds its logits in registers, so that its round trip through the tensor core
+// hides behind the sampling arithmetic. Measured on B200, 2 M envs: 0.150 ms (four independent 128-thread CTAs per
+// SM without the pipeline 0.181; three 256-thread chains that batch both agents' MMAs 0.157; the mma.sync kernel
+// 0.219). PZ_TC_AGENTS_PER_CHAIN=2 builds the three-chain form.
 //
 // Canonical shared-memory layouts (no swizzle; 8 x 16-byte "core matrices" of 128 contiguous bytes):
 //   X  (MN-major A): element (env m, feature k) at (k / 8) * 2048 + (m / 8) * 128 + (k % 8) * 16 + (m % 8) * 2
@@ -40,29 +43,35 @@
 namespace pzp {
 namespace tc {
 
-constexpr int kChains = 3;          // per CTA = per SM
-constexpr int kChainThreads = 256;  // 8 warps: agent = warp / 4 within the chain, env row = 32 * (warp % 4) + lane
+#ifndef PZ_TC_AGENTS_PER_CHAIN
+#define PZ_TC_AGENTS_PER_CHAIN 1
+#endif
+constexpr int kAPC = PZ_TC_AGENTS_PER_CHAIN;   // 1: a chain of 4 warps owns one agent of a tile;
+                                               // 2: a chain of 8 warps owns a tile (warps 0-3 agent 0, 4-7 agent 1)
+constexpr int kChains = 6 / kAPC;              // per CTA = per SM
+constexpr int kChainThreads = 128 * kAPC;      // env row = 32 * (warp % 4) + lane
 constexpr int kThreads = kChains * kChainThreads;
 constexpr int kTileEnvs = 128;
 constexpr int kKP = PZ_POLICY_MAX_FEATURES;  // 48 = 3 k-steps of 16
 constexpr int kHP = PZ_POLICY_MAX_HIDDEN;    // 80: N of layer 1 (multiple of 16), 5 k-steps of layer 2
 constexpr int kAP = 32;                      // N of layer 2: PZ_POLICY_MAX_ACTIONS (24) padded to a multiple of 16
 constexpr uint32_t kTmemCols = 512;          // the whole SM
-constexpr uint32_t kAgentCols = kHP, kChainCols = 2 * kAgentCols;
+constexpr uint32_t kAgentCols = kHP, kChainCols = kAPC * kAgentCols;
 constexpr uint32_t kColD1 = 0, kColH = 0, kColD2 = kHP / 2;  // H overwrites the columns of D1 its thread has read
 static_assert(kChains * kChainCols <= kTmemCols && kHP / 2 + kAP <= kHP, "TMEM columns");
 static_assert(PZ_POLICY_MAX_ACTIONS <= kAP && kKP % 16 == 0 && kHP % 16 == 0, "tile shapes");
 
 constexpr int kXKGroup = (kTileEnvs / 8) * 128;    // 2048 B: one group of 8 features, 16 env atoms
 constexpr int kXAgent = (kKP / 8) * kXKGroup;      // 12288 B
-constexpr int kXTile = 2 * kXAgent;                // both agents
+constexpr int kXTile = kAPC * kXAgent;             // what one chain stages: both agents, or its own
 constexpr int kW1KGroup = (kHP / 8) * 128;         // 1280 B
 constexpr int kW1Agent = (kKP / 8) * kW1KGroup;    // 7680 B
 constexpr int kW2KGroup = (kAP / 8) * 128;         // 512 B
 constexpr int kW2Agent = (kHP / 8) * kW2KGroup;    // 5120 B
 constexpr int kOffW1 = 0, kOffW2 = 2 * kW1Agent, kOffX = kOffW2 + 2 * kW2Agent;  // X: [chain][buffer][agent]
 constexpr int kOffBar = kOffX + kChains * 2 * kXTile;
-constexpr size_t kSmemBytes = kOffBar + 32;        // + one mbarrier per chain (8 B each) + TMEM base address (4 B)
+constexpr int kOffTmemSlot = kOffBar + 8 * kChains;
+constexpr size_t kSmemBytes = kOffTmemSlot + 16;   // one mbarrier per chain (8 B each), the TMEM base address (4 B)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -152,14 +161,17 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
     const int n_actions = NA ? NA : P.n_actions;
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kOffBar + 24);
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kOffTmemSlot);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int chain = warp >> 3, wic = warp & 7, agent = wic >> 2, ctid = tid - chain * kChainThreads;
+    const int chain = warp / (4 * kAPC), wic = warp % (4 * kAPC), ctid = tid - chain * kChainThreads;
+    const int agent = kAPC == 2 ? wic >> 2 : chain & 1;   // the agent this thread samples for
+    const int slot = kAPC == 2 ? agent : 0;               // its place in the chain's TMEM columns and tile buffers
+    const int seq = kAPC == 2 ? chain : chain >> 1;       // which of the CTA's three tile sequences the chain walks
     const uint32_t bar = s_base + kOffBar + 8 * chain;
 
     // ---- once per CTA: TMEM, the barriers, zeroed operands, the weights in canonical K-major order ----
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + kOffBar + 24),
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + kOffTmemSlot),
                      "r"(kTmemCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -186,15 +198,15 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t t_chain = tmem + chain * kChainCols;                                       // lane 0: MMA operands
-    const uint32_t t_row = t_chain + agent * kAgentCols + ((uint32_t)((wic & 3) * 32) << 16);  // this thread's row
+    const uint32_t t_row = t_chain + slot * kAgentCols + ((uint32_t)((wic & 3) * 32) << 16);  // this thread's row
     const uint32_t s_x = s_base + kOffX + chain * 2 * kXTile;
 
     constexpr uint32_t kIdesc1 = instr_desc(kHP, true), kIdesc2 = instr_desc(kAP, false);
     const bool vec_ok = (P.ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(P.obs) & 15u) == 0);
     const int64_t n_tiles = (P.n + kTileEnvs - 1) / kTileEnvs;
-    const int64_t t_stride = (int64_t)gridDim.x * kChains;
+    const int64_t t_stride = (int64_t)gridDim.x * 3;
 
-    // The chain's 256 threads fill one tile (both agents): warps 0-3 agent 0, warps 4-7 agent 1; per pass one group
+    // The chain's threads fill what it computes on (its agent's half of the tile, or both): per pass one group
     // of 8 features, lane = (feature % 8) + 8 * (env atom % 4), warp % 4 = env atom / 4 — a warp writes 512
     // contiguous bytes of shared memory and reads 8 rows x 64 contiguous bytes.
     auto load_tile = [&](int64_t t, uint32_t b) {
@@ -202,16 +214,16 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
         if (vec_ok && env0 + kTileEnvs <= P.n) {
             const int kr = lane & 7, m8 = (wic & 3) * 4 + (lane >> 3);
             const __nv_bfloat16 *src = P.obs + ((int64_t)agent * P.rows + kr) * P.ld + env0 + m8 * 8;
-            uint32_t dst = s_x + b * kXTile + agent * kXAgent + m8 * 128 + kr * 16;
+            uint32_t dst = s_x + b * kXTile + slot * kXAgent + m8 * 128 + kr * 16;
             for (int k = kr; k < P.k1; k += 8, src += 8 * P.ld, dst += kXKGroup)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
         } else {  // ragged last tile or unaligned rows
             __nv_bfloat16 *xs = reinterpret_cast<__nv_bfloat16 *>(smem + kOffX + (chain * 2 + b) * kXTile);
             const __nv_bfloat16 zero = __float2bfloat16(0.0f);
-            for (int i = ctid; i < 2 * P.k1 * kTileEnvs; i += kChainThreads) {
-                const int a = i / (P.k1 * kTileEnvs), rem = i - a * (P.k1 * kTileEnvs), k = rem / kTileEnvs,
-                          m = rem % kTileEnvs;
-                xs[(a * kXAgent + (k >> 3) * kXKGroup + (m >> 3) * 128 + (k & 7) * 16 + (m & 7) * 2) >> 1] =
+            for (int i = ctid; i < kAPC * P.k1 * kTileEnvs; i += kChainThreads) {
+                const int sl = i / (P.k1 * kTileEnvs), rem = i - sl * (P.k1 * kTileEnvs), k = rem / kTileEnvs,
+                          m = rem % kTileEnvs, a = kAPC == 2 ? sl : agent;
+                xs[(sl * kXAgent + (k >> 3) * kXKGroup + (m >> 3) * 128 + (k & 7) * 16 + (m & 7) * 2) >> 1] =
                     env0 + m < P.n ? P.obs[((int64_t)a * P.rows + k) * P.ld + env0 + m] : zero;
             }
         }
@@ -222,12 +234,13 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
     auto issue_layer1 = [&](uint32_t b) {
         tc_fence_after();
 #pragma unroll
-        for (int a = 0; a < 2; a++)
+        for (int sl = 0; sl < kAPC; sl++)
 #pragma unroll
             for (int ks = 0; ks < kKP / 16; ks++)
-                mma_ss(t_chain + a * kAgentCols + kColD1,
-                       smem_desc(s_x + b * kXTile + a * kXAgent + ks * 2 * kXKGroup, kXKGroup, 128),
-                       smem_desc(s_base + kOffW1 + a * kW1Agent + ks * 2 * kW1KGroup, kW1KGroup, 128), kIdesc1, ks > 0);
+                mma_ss(t_chain + sl * kAgentCols + kColD1,
+                       smem_desc(s_x + b * kXTile + sl * kXAgent + ks * 2 * kXKGroup, kXKGroup, 128),
+                       smem_desc(s_base + kOffW1 + (kAPC == 2 ? sl : agent) * kW1Agent + ks * 2 * kW1KGroup, kW1KGroup, 128),
+                       kIdesc1, ks > 0);
         mma_commit(bar);
     };
     // cp.async data of every group but the newest has landed -> visible to the tensor core after the chain's barrier
@@ -241,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
     // Software pipeline over the chain's tiles t0, t1 = t0 + stride, ...: the tile after next is fetched while a
     // tile is computed, and layer 1 of the NEXT tile is issued as soon as every thread holds this tile's logits in
     // registers, so its round trip through the tensor core hides behind the sampling arithmetic.
-    int64_t tile = blockIdx.x + (int64_t)gridDim.x * chain;
+    int64_t tile = blockIdx.x + (int64_t)gridDim.x * seq;
     uint32_t buf = 0, phase = 0;
     if (tile < n_tiles) {
         load_tile(tile, 0);
@@ -288,11 +301,12 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
         if (ctid == 0) {
             tc_fence_after();
 #pragma unroll
-            for (int a = 0; a < 2; a++)
+            for (int sl = 0; sl < kAPC; sl++)
 #pragma unroll
                 for (int j = 0; j < kHP / 16; j++)
-                    mma_ts(t_chain + a * kAgentCols + kColD2, t_chain + a * kAgentCols + kColH + 8 * j,
-                           smem_desc(s_base + kOffW2 + a * kW2Agent + j * 2 * kW2KGroup, kW2KGroup, 128), kIdesc2, j > 0);
+                    mma_ts(t_chain + sl * kAgentCols + kColD2, t_chain + sl * kAgentCols + kColH + 8 * j,
+                           smem_desc(s_base + kOffW2 + (kAPC == 2 ? sl : agent) * kW2Agent + j * 2 * kW2KGroup, kW2KGroup, 128),
+                           kIdesc2, j > 0);
             mma_commit(bar);
         }
         mbar_wait(bar, phase);
