@@ -152,6 +152,13 @@ __device__ __forceinline__ uint32_t relu_pack(uint32_t lo_bits, uint32_t hi_bits
     return relu_pack_bf16x2(__uint_as_float(lo_bits), __uint_as_float(hi_bits));
 }
 
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void chain_sync(int chain) {
     asm volatile("bar.sync %0, %1;" ::"r"(chain + 1), "r"(kChainThreads) : "memory");
 }
@@ -162,7 +169,10 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kOffTmemSlot);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // warp-uniform by construction: everything derived from it (chain, agent, TMEM and shared-memory addresses, the
+    // MMA descriptors) can live in uniform registers, which is where the tensor-core instructions take them from
+    const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
     const int chain = warp / (4 * kAPC), wic = warp % (4 * kAPC), ctid = tid - chain * kChainThreads;
     const int agent = kAPC == 2 ? wic >> 2 : chain & 1;   // the agent this thread samples for
     const int slot = kAPC == 2 ? agent : 0;               // its place in the chain's TMEM columns and tile buffers
@@ -263,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
         else
             asm volatile("cp.async.commit_group;" ::: "memory");
         tile_ready();
-        if (ctid == 0) issue_layer1(0);
+        if (wic == 0 && elect_one()) issue_layer1(0);
     }
     for (; tile < n_tiles; tile += t_stride, buf ^= 1u) {
         const int64_t env = tile * kTileEnvs + (wic & 3) * 32 + lane;
@@ -298,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
         tc_fence_before();
         chain_sync(chain);
         // ---- layer 2 of both agents -> D2
-        if (ctid == 0) {
+        if (wic == 0 && elect_one()) {
             tc_fence_after();
 #pragma unroll
             for (int sl = 0; sl < kAPC; sl++)
@@ -326,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
         }
         if (tile + t_stride < n_tiles) {  // chain-uniform
             tile_ready();
-            if (ctid == 0) issue_layer1(buf ^ 1u);
+            if (wic == 0 && elect_one()) issue_layer1(buf ^ 1u);
         }
         // ---- the sample
         if (P.logits != nullptr && env < P.n) {  // launch-uniform pointer
