@@ -43,13 +43,16 @@ __device__ __forceinline__ uint32_t noise_base(uint64_t seed, uint64_t step, uin
 // u = ((x >> 9) + 0.5) / 2^23 in (0, 1), exact: the 23 bits are placed as the mantissa of a float in [1, 2) and
 // 1 - 2^-24 is subtracted (both steps exact) — one logic and one add instruction instead of a conversion on the
 // special-function pipe, which the two logarithms already load
-__device__ __forceinline__ float gumbel_from_bits(float logit, uint32_t x) {
+__device__ __forceinline__ float gumbel_log_term(uint32_t x) {  // log2(-log2(u)): everything but the logit
     x *= 0x7feb352du;
     x ^= x >> 15;
     x *= 0x846ca68bu;
     x ^= x >> 16;
     const float u = __uint_as_float(0x3F800000u | (x >> 9)) + (-1.0f + 5.9604644775390625e-08f);
-    return fmaf(-0.693147182f, lg2_approx(-lg2_approx(u)), logit);
+    return lg2_approx(-lg2_approx(u));
+}
+__device__ __forceinline__ float gumbel_from_bits(float logit, uint32_t x) {
+    return fmaf(-0.693147182f, gumbel_log_term(x), logit);
 }
 __device__ __forceinline__ float gumbel_key(float logit, uint32_t base, int agent, int action) {
     return gumbel_from_bits(logit, base + (uint32_t)(32 * agent + action + 1) * 0x9E3779B9u);  // base is already well mixed

@@ -110,6 +110,12 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+#ifndef PZ_TC_EPI_BATCH
+#define PZ_TC_EPI_BATCH 2
+#endif
+#ifndef PZ_TC_NOISE_EARLY
+#define PZ_TC_NOISE_EARLY 9
+#endif
 #ifndef PZ_TC_WAIT_HINT
 #define PZ_TC_WAIT_HINT 0x989680u
 #endif
@@ -117,11 +123,19 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spins = 0; !done; spins++) {  // try_wait suspends the thread up to the hinted time before it returns
+#ifdef PZ_TC_SPIN
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+#else
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(bar), "r"(parity), "r"(PZ_TC_WAIT_HINT)
             : "memory");
+#endif
         if (!done && spins > (1u << 20)) __trap();
     }
 }
@@ -281,23 +295,20 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
         mbar_wait(bar, phase);  // layer 1 of this tile
         phase ^= 1u;
         tc_fence_after();
-        // its buffer is free: the tile after next travels while this one and the next are computed
-        if (tile + 2 * t_stride < n_tiles)
-            load_tile(tile + 2 * t_stride, buf);
-        else
-            asm volatile("cp.async.commit_group;" ::: "memory");
         // ---- relu, round to bf16, back to TMEM as the A operand of layer 2 (thread = env row of its agent).
         //      H column j holds hidden units 2j, 2j+1: it overwrites D1 columns this thread has already read.
         {
-            uint32_t v[2][16], h[8];
+            constexpr int kChunks = kHP / 16, kBatch = PZ_TC_EPI_BATCH;  // chunks of 16 columns read per wait
+            uint32_t v[kBatch][16], h[8];
 #pragma unroll
-            for (int c = 0; c < kHP / 16; c += 2) {
-                tmem_ld16(t_row + kColD1 + 16 * c, v[0]);
-                if (c + 1 < kHP / 16) tmem_ld16(t_row + kColD1 + 16 * (c + 1), v[1]);
+            for (int c = 0; c < kChunks; c += kBatch) {
+#pragma unroll
+                for (int q = 0; q < kBatch; q++)
+                    if (c + q < kChunks) tmem_ld16(t_row + kColD1 + 16 * (c + q), v[q]);
                 tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 2; q++)
-                    if (c + q < kHP / 16) {
+                for (int q = 0; q < kBatch; q++)
+                    if (c + q < kChunks) {
 #pragma unroll
                         for (int j = 0; j < 8; j++) h[j] = relu_pack(v[q][2 * j], v[q][2 * j + 1]);
                         tmem_st8(t_row + kColH + 8 * (c + q), h);
@@ -318,6 +329,23 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
                            smem_desc(s_base + kOffW2 + (kAPC == 2 ? sl : agent) * kW2Agent + j * 2 * kW2KGroup, kW2KGroup, 128),
                            kIdesc2, j > 0);
             mma_commit(bar);
+        }
+        // layer 1 has read this tile's buffer: the tile after next can travel into it (issued here, off the
+        // critical path between the two layers)
+        if (tile + 2 * t_stride < n_tiles)
+            load_tile(tile + 2 * t_stride, buf);
+        else
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        // The noise does not depend on the logits: the terms of the first kNoiseEarly candidates are computed while
+        // layer 2 is in the tensor core, the others behind the issue of the next tile's layer 1 — both round trips
+        // have arithmetic to hide behind. key_j = fma(-ln 2, term_j, logit_j) is assembled when the logits are there.
+        constexpr int kCand = NA ? NA : PZ_POLICY_MAX_ACTIONS;
+        constexpr int kNoiseEarly = PZ_TC_NOISE_EARLY < kCand ? PZ_TC_NOISE_EARLY : kCand;
+        const uint32_t agent_base = nbase + (uint32_t)(32 * agent) * 0x9E3779B9u;
+        float term[kCand];
+        if (!P.greedy) {
+#pragma unroll
+            for (int j = 0; j < kNoiseEarly; j++) term[j] = gumbel_log_term(agent_base + (uint32_t)(j + 1) * 0x9E3779B9u);
         }
         mbar_wait(bar, phase);
         phase ^= 1u;
@@ -349,13 +377,15 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
         float best = pack_key(-INFINITY, 31);
         if (P.greedy) {
 #pragma unroll
-            for (int j = 0; j < (NA ? NA : PZ_POLICY_MAX_ACTIONS); j++)
+            for (int j = 0; j < kCand; j++)
                 if (j < n_actions) best = fmaxf(best, pack_key(__uint_as_float(lg[j]), j));
         } else {
-            const uint32_t agent_base = nbase + (uint32_t)(32 * agent) * 0x9E3779B9u;
 #pragma unroll
-            for (int j = 0; j < (NA ? NA : PZ_POLICY_MAX_ACTIONS); j++)
-                if (j < n_actions) best = fmaxf(best, pack_key(gumbel_key_from(__uint_as_float(lg[j]), agent_base, j), j));
+            for (int j = kNoiseEarly; j < kCand; j++) term[j] = gumbel_log_term(agent_base + (uint32_t)(j + 1) * 0x9E3779B9u);
+#pragma unroll
+            for (int j = 0; j < kCand; j++)
+                if (j < n_actions)
+                    best = fmaxf(best, pack_key(fmaf(-0.693147182f, term[j], __uint_as_float(lg[j])), j));
         }
         int act = 31 - (int)(__float_as_uint(best) & 31u);
         if (act >= n_actions) act = 0;  // every key NaN: action 0
