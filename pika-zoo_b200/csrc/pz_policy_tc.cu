@@ -32,10 +32,12 @@
 //                       core matrix, so the tile is filled by plain 16-byte cp.async from the feature-major rows
 //   W1 (K-major B):  element (hidden n, feature k) at (k / 8) * 1280 + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2
 //   W2 (K-major B):  element (action n, hidden k)  at (k / 8) *  512 + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2
+#include <cuda.h>  // CUtensorMap; the driver entry point is looked up at run time, libcuda is not linked
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstring>
 #include <mutex>
 
 #include "pz_policy.cuh"
@@ -70,8 +72,9 @@ constexpr int kW2KGroup = (kAP / 8) * 128;         // 512 B
 constexpr int kW2Agent = (kHP / 8) * kW2KGroup;    // 5120 B
 constexpr int kOffW1 = 0, kOffW2 = 2 * kW1Agent, kOffX = kOffW2 + 2 * kW2Agent;  // X: [chain][buffer][agent]
 constexpr int kOffBar = kOffX + kChains * 2 * kXTile;
-constexpr int kOffTmemSlot = kOffBar + 8 * kChains;
-constexpr size_t kSmemBytes = kOffTmemSlot + 16;   // one mbarrier per chain (8 B each), the TMEM base address (4 B)
+constexpr int kOffTmemSlot = kOffBar + 24 * kChains;
+constexpr size_t kSmemBytes = kOffTmemSlot + 16;   // per chain: MMA mbarrier + one "tile landed" mbarrier per buffer
+                                                    // (8 B each); the TMEM base address (4 B)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -177,8 +180,19 @@ __device__ __forceinline__ void chain_sync(int chain) {
     asm volatile("bar.sync %0, %1;" ::"r"(chain + 1), "r"(kChainThreads) : "memory");
 }
 
+#ifdef PZ_TC_TIMING  // debug build: chain 0 of CTA 0 stamps its phases into the logits buffer (as uint64)
+#define PZ_STAMP(slot)                                                                                     \
+    do {                                                                                                   \
+        if (blockIdx.x == 0 && tid == 0 && iter >= 4 && iter < 12)                                         \
+            reinterpret_cast<long long *>(P.logits)[(iter - 4) * 12 + (slot)] = clock64();                 \
+    } while (0)
+#else
+#define PZ_STAMP(slot) do { } while (0)
+#endif
+
 template <int NA>
-__global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(kThreads, 1)
+    pz_policy_mlp_tc_kernel(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap tmap, const int use_tma) {
     const int n_actions = NA ? NA : P.n_actions;
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
@@ -191,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
     const int agent = kAPC == 2 ? wic >> 2 : chain & 1;   // the agent this thread samples for
     const int slot = kAPC == 2 ? agent : 0;               // its place in the chain's TMEM columns and tile buffers
     const int seq = kAPC == 2 ? chain : chain >> 1;       // which of the CTA's three tile sequences the chain walks
-    const uint32_t bar = s_base + kOffBar + 8 * chain;
+    const uint32_t bar = s_base + kOffBar + 24 * chain;  // +8, +16: the tile buffers' barriers
 
     // ---- once per CTA: TMEM, the barriers, zeroed operands, the weights in canonical K-major order ----
     if (warp == 0) {
@@ -200,7 +214,11 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (ctid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1u) : "memory");
+    if (ctid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar + 8), "r"(1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar + 16), "r"(1u) : "memory");
+    }
     if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int i = tid; i < kOffBar / 16; i += kThreads) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
@@ -235,6 +253,25 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
     // contiguous bytes of shared memory and reads 8 rows x 64 contiguous bytes.
     auto load_tile = [&](int64_t t, uint32_t b) {
         const int64_t env0 = t * kTileEnvs;
+        if (use_tma) {
+            // One bulk tensor copy per group of 8 features: the tensor map views the observations as
+            // [env / 8][feature row][env % 8] with an (8, 8, 16) box, whose dense shared-memory image (8 envs, then
+            // 8 features, then 16 env atoms) IS the canonical layout of the group. Envs past the end read as zero.
+            if (wic == 0 && elect_one()) {
+                const uint32_t full = bar + 8 + 8 * b;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full),
+                             "r"((uint32_t)(kAPC * ((P.k1 + 7) >> 3) * kXKGroup))
+                             : "memory");
+                for (int sl = 0; sl < kAPC; sl++)
+                    for (int kg = 0; kg < ((P.k1 + 7) >> 3); kg++)
+                        asm volatile(
+                            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                            ::"r"(s_x + b * kXTile + sl * kXAgent + kg * kXKGroup), "l"(&tmap), "r"(0),
+                            "r"((kAPC == 2 ? sl : agent) * P.rows + kg * 8), "r"((int)(env0 >> 3)), "r"(full)
+                            : "memory");
+            }
+            return;
+        }
         if (vec_ok && env0 + kTileEnvs <= P.n) {
             const int kr = lane & 7, m8 = (wic & 3) * 4 + (lane >> 3);
             const __nv_bfloat16 *src = P.obs + ((int64_t)agent * P.rows + kr) * P.ld + env0 + m8 * 8;
@@ -255,7 +292,9 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
     };
 
     // layer 1 of both agents of the tile in buffer b -> D1 (one thread)
+    uint32_t full_phase = 0;  // bit b: parity the next wait on buffer b's barrier uses (tracked by every thread)
     auto issue_layer1 = [&](uint32_t b) {
+        if (use_tma) mbar_wait(bar + 8 + 8 * b, (full_phase >> b) & 1u);  // the bulk copies of this tile have landed
         tc_fence_after();
 #pragma unroll
         for (int sl = 0; sl < kAPC; sl++)
@@ -269,8 +308,10 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
     };
     // cp.async data of every group but the newest has landed -> visible to the tensor core after the chain's barrier
     auto tile_ready = [&]() {
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (!use_tma) {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
         tc_fence_before();  // and this thread's TMEM reads are ordered before the MMAs issued after the barrier
         chain_sync(chain);
     };
@@ -288,13 +329,17 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
             asm volatile("cp.async.commit_group;" ::: "memory");
         tile_ready();
         if (wic == 0 && elect_one()) issue_layer1(0);
+        full_phase ^= 1u;
     }
-    for (; tile < n_tiles; tile += t_stride, buf ^= 1u) {
+    int iter = 0;
+    for (; tile < n_tiles; tile += t_stride, buf ^= 1u, iter++) {
+        PZ_STAMP(0);
         const int64_t env = tile * kTileEnvs + (wic & 3) * 32 + lane;
         const uint32_t nbase = P.greedy ? 0u : noise_base(P.seed, P.step, P.first_env + (uint64_t)env);
         mbar_wait(bar, phase);  // layer 1 of this tile
         phase ^= 1u;
         tc_fence_after();
+        PZ_STAMP(1);
         // ---- relu, round to bf16, back to TMEM as the A operand of layer 2 (thread = env row of its agent).
         //      H column j holds hidden units 2j, 2j+1: it overwrites D1 columns this thread has already read.
         {
@@ -316,8 +361,10 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
             }
         }
         tmem_st_wait();
+        PZ_STAMP(2);
         tc_fence_before();
         chain_sync(chain);
+        PZ_STAMP(3);
         // ---- layer 2 of both agents -> D2
         if (wic == 0 && elect_one()) {
             tc_fence_after();
@@ -330,6 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
                            kIdesc2, j > 0);
             mma_commit(bar);
         }
+        PZ_STAMP(4);
         // layer 1 has read this tile's buffer: the tile after next can travel into it (issued here, off the
         // critical path between the two layers)
         if (tile + 2 * t_stride < n_tiles)
@@ -347,9 +395,11 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
 #pragma unroll
             for (int j = 0; j < kNoiseEarly; j++) term[j] = gumbel_log_term(agent_base + (uint32_t)(j + 1) * 0x9E3779B9u);
         }
+        PZ_STAMP(5);
         mbar_wait(bar, phase);
         phase ^= 1u;
         tc_fence_after();
+        PZ_STAMP(6);
         // ---- this (env, agent)'s logits into registers; then the tensor core can have the columns back
         uint32_t lg[24];
         {
@@ -362,16 +412,22 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
 #pragma unroll
             for (int j = 0; j < 8; j++) lg[16 + j] = (NA == 0 || NA > 16) ? v8[j] : 0u;
         }
+        PZ_STAMP(7);
         if (tile + t_stride < n_tiles) {  // chain-uniform
             tile_ready();
+            PZ_STAMP(8);
             if (wic == 0 && elect_one()) issue_layer1(buf ^ 1u);
+            full_phase ^= 1u << (buf ^ 1u);
         }
+        PZ_STAMP(9);
         // ---- the sample
+#ifndef PZ_TC_TIMING
         if (P.logits != nullptr && env < P.n) {  // launch-uniform pointer
 #pragma unroll
             for (int j = 0; j < (NA ? NA : PZ_POLICY_MAX_ACTIONS); j++)
                 if (j < n_actions) P.logits[(env * 2 + agent) * n_actions + j] = __uint_as_float(lg[j]);
         }
+#endif
         // branch-free over the candidates (the greedy test is hoisted), so that the keys' dependent chains
         // (two multiplies, two logarithms each) interleave
         float best = pack_key(-INFINITY, 31);
@@ -397,11 +453,44 @@ __global__ void __launch_bounds__(kThreads, 1) pz_policy_mlp_tc_kernel(const __g
             else
                 reinterpret_cast<long long *>(P.actions)[env * 2 + agent] = act;
         }
+        PZ_STAMP(10);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// The feature-major observations [2 * rows][ld] bf16 as a rank-3 tensor (env % 8, feature row, env / 8) with an
+// (8, 8, 16) box: see load_tile. False when the shape does not allow it (the kernel then fills its tiles with
+// cp.async / plain loads).
+static bool make_obs_map(const Params &P, CUtensorMap *map) {
+    if (P.ld % 8 != 0 || (reinterpret_cast<uintptr_t>(P.obs) & 15u) != 0 || P.k1 % 8 != 0 || P.rows < P.k1 || P.n < 8)
+        return false;
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {8, (cuuint64_t)(2 * (int64_t)P.rows), (cuuint64_t)(P.n / 8)};  // whole groups of 8 envs
+    const cuuint64_t strides[2] = {(cuuint64_t)P.ld * 2, 16};                                    // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {8, 8, (cuuint32_t)(kTileEnvs / 8)}, estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16 *>(P.obs), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int NA>
@@ -417,7 +506,11 @@ static cudaError_t launch_one(const Params &P, unsigned grid, cudaStream_t strea
             attr_set[dev] = true;
         }
     }
-    pz_policy_mlp_tc_kernel<NA><<<grid, kThreads, kSmemBytes, stream>>>(P);
+    alignas(64) CUtensorMap map;
+    // whole groups of 8 envs only travel by bulk copy: a ragged tail (n % 8 != 0) keeps the element-wise path
+    const int use_tma = (P.n % 8 == 0 && make_obs_map(P, &map)) ? 1 : 0;
+    if (!use_tma) memset(&map, 0, sizeof(map));
+    pz_policy_mlp_tc_kernel<NA><<<grid, kThreads, kSmemBytes, stream>>>(P, map, use_tma);
     return cudaGetLastError();
 }
 
