@@ -224,14 +224,16 @@ void pz_host_destroy(pz_host_ctx *ctx);
  *                0 .. features-1 enter the contraction (policy.py folds the biases in through a row of ones)
  *   w1_dev       bf16 [2][hidden_rows][features], w2_dev bf16 [2][n_actions][w2_cols] (row-major, per agent)
  *   logits       = W2 . relu(W1 . x), fp32 accumulation, hidden activations rounded to bf16
- *   actions_dev  [n][2] of action_dtype (PZ_ACT_*): argmax_a(logits[a] + Gumbel(seed, step, first_env + env,
- *                agent, a)) — a categorical sample from softmax(logits), reproducible from the counters
- *                (restated in policy.py gumbel_noise_reference); greedy != 0: plain argmax
+ *   actions_dev  [n][2] of action_dtype (PZ_ACT_*): a categorical sample from softmax(logits), reproducible from
+ *                the counters (seed, step, first_env + env, agent[, action]) that key its uniforms
+ *                (csrc/pz_policy.cuh, restated in policy.py); greedy != 0: plain argmax
  *   logits_dev   optional fp32 [n][2][n_actions]
  *
- * Two implementations of the same definition: PZ_POLICY_IMPL_TCGEN05 (csrc/pz_policy_tc.cu: tcgen05.mma with the
- * accumulators and the hidden activations in TMEM, one thread per env in the epilogues) and
- * PZ_POLICY_IMPL_MMA_SYNC (csrc/pz_policy.cu: warp-level mma.sync, kept for A/B measurements). pz_policy_select
+ * Two implementations of the same network — logits bit-identical, same greedy actions: PZ_POLICY_IMPL_TCGEN05
+ * (csrc/pz_policy_tc.cu: tcgen05.mma with the accumulators and the hidden activations in TMEM, tiles by TMA, one
+ * thread per env in the epilogues; samples by inversion of the cumulative distribution with one uniform per env and
+ * agent, policy.py inverse_cdf_reference) and PZ_POLICY_IMPL_MMA_SYNC (csrc/pz_policy.cu: warp-level mma.sync, kept
+ * for A/B measurements; samples by argmax(logits + Gumbel noise), policy.py gumbel_noise_reference). pz_policy_select
  * switches process-wide and returns the previous choice, or -1 for an unknown code. */
 #define PZ_POLICY_IMPL_TCGEN05 0
 #define PZ_POLICY_IMPL_MMA_SYNC 1

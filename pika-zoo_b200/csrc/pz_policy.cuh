@@ -43,13 +43,16 @@ __device__ __forceinline__ uint32_t noise_base(uint64_t seed, uint64_t step, uin
 // u = ((x >> 9) + 0.5) / 2^23 in (0, 1), exact: the 23 bits are placed as the mantissa of a float in [1, 2) and
 // 1 - 2^-24 is subtracted (both steps exact) — one logic and one add instruction instead of a conversion on the
 // special-function pipe, which the two logarithms already load
-__device__ __forceinline__ float gumbel_log_term(uint32_t x) {  // log2(-log2(u)): everything but the logit
+// 32 mixed bits -> u = ((x >> 9) + 0.5) / 2^23 in (0, 1)
+__device__ __forceinline__ float uniform_from_counter(uint32_t x) {
     x *= 0x7feb352du;
     x ^= x >> 15;
     x *= 0x846ca68bu;
     x ^= x >> 16;
-    const float u = __uint_as_float(0x3F800000u | (x >> 9)) + (-1.0f + 5.9604644775390625e-08f);
-    return lg2_approx(-lg2_approx(u));
+    return __uint_as_float(0x3F800000u | (x >> 9)) + (-1.0f + 5.9604644775390625e-08f);
+}
+__device__ __forceinline__ float gumbel_log_term(uint32_t x) {  // log2(-log2(u)): everything but the logit
+    return lg2_approx(-lg2_approx(uniform_from_counter(x)));
 }
 __device__ __forceinline__ float gumbel_from_bits(float logit, uint32_t x) {
     return fmaf(-0.693147182f, gumbel_log_term(x), logit);
@@ -75,6 +78,40 @@ __device__ __forceinline__ uint32_t relu_pack_bf16x2(float lo, float hi) {
     uint32_t d;
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// The tcgen05 kernel's categorical sample (one thread holds all the logits of its env and agent): inversion of the
+// cumulative distribution with ONE uniform per (env, agent) — the first uniform of the Gumbel stream above, counter
+// (seed, step, global env, agent, action 0):
+//   w_j = 2^((logit_j - max) * log2 e),  c_j = w_0 + ... + w_j (fp32, in action order),
+//   action = #{ j < n_actions - 1 : c_j <= u * c_last }
+// i.e. P(action = j) = softmax(logits)_j up to the 2^-23 resolution of u. Restated in pika-zoo_b200/policy.py
+// (inverse_cdf_reference). A third of the Gumbel arg-max's instructions and half of its special-function work.
+template <int N>
+__device__ __forceinline__ int sample_inverse_cdf(const float (&logit)[N], int n_actions, uint32_t agent_base) {
+    float m = logit[0];
+#pragma unroll
+    for (int j = 1; j < N; j++)
+        if (j < n_actions) m = fmaxf(m, logit[j]);
+    const float shift = -m * 1.44269504f;
+    float c[N], acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        if (j < n_actions) acc += ex2_approx(fmaf(logit[j], 1.44269504f, shift));
+        c[j] = acc;
+    }
+    const float target = uniform_from_counter(agent_base + 0x9E3779B9u) * acc;
+    int action = 0;
+#pragma unroll
+    for (int j = 0; j < N - 1; j++)
+        if (j < n_actions - 1) action += (c[j] <= target) ? 1 : 0;
+    return action;  // NaN logits: every comparison is false, action 0
 }
 
 // pz_policy_tc.cu

@@ -116,9 +116,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 #ifndef PZ_TC_EPI_BATCH
 #define PZ_TC_EPI_BATCH 2
 #endif
-#ifndef PZ_TC_NOISE_EARLY
-#define PZ_TC_NOISE_EARLY 9
-#endif
 #ifndef PZ_TC_WAIT_HINT
 #define PZ_TC_WAIT_HINT 0x989680u
 #endif
@@ -384,17 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             load_tile(tile + 2 * t_stride, buf);
         else
             asm volatile("cp.async.commit_group;" ::: "memory");
-        // The noise does not depend on the logits: the terms of the first kNoiseEarly candidates are computed while
-        // layer 2 is in the tensor core, the others behind the issue of the next tile's layer 1 — both round trips
-        // have arithmetic to hide behind. key_j = fma(-ln 2, term_j, logit_j) is assembled when the logits are there.
         constexpr int kCand = NA ? NA : PZ_POLICY_MAX_ACTIONS;
-        constexpr int kNoiseEarly = PZ_TC_NOISE_EARLY < kCand ? PZ_TC_NOISE_EARLY : kCand;
-        const uint32_t agent_base = nbase + (uint32_t)(32 * agent) * 0x9E3779B9u;
-        float term[kCand];
-        if (!P.greedy) {
-#pragma unroll
-            for (int j = 0; j < kNoiseEarly; j++) term[j] = gumbel_log_term(agent_base + (uint32_t)(j + 1) * 0x9E3779B9u);
-        }
         PZ_STAMP(5);
         mbar_wait(bar, phase);
         phase ^= 1u;
@@ -428,23 +415,20 @@ __global__ void __launch_bounds__(kThreads, 1)
                 if (j < n_actions) P.logits[(env * 2 + agent) * n_actions + j] = __uint_as_float(lg[j]);
         }
 #endif
-        // branch-free over the candidates (the greedy test is hoisted), so that the keys' dependent chains
-        // (two multiplies, two logarithms each) interleave
-        float best = pack_key(-INFINITY, 31);
-        if (P.greedy) {
+        int act;
+        if (P.greedy) {  // the packed-key arg-max both implementations share
+            float best = pack_key(-INFINITY, 31);
 #pragma unroll
             for (int j = 0; j < kCand; j++)
                 if (j < n_actions) best = fmaxf(best, pack_key(__uint_as_float(lg[j]), j));
+            act = 31 - (int)(__float_as_uint(best) & 31u);
+            if (act >= n_actions) act = 0;  // every key NaN: action 0
         } else {
+            float logit[kCand];
 #pragma unroll
-            for (int j = kNoiseEarly; j < kCand; j++) term[j] = gumbel_log_term(agent_base + (uint32_t)(j + 1) * 0x9E3779B9u);
-#pragma unroll
-            for (int j = 0; j < kCand; j++)
-                if (j < n_actions)
-                    best = fmaxf(best, pack_key(fmaf(-0.693147182f, term[j], __uint_as_float(lg[j])), j));
+            for (int j = 0; j < kCand; j++) logit[j] = __uint_as_float(lg[j]);
+            act = sample_inverse_cdf<kCand>(logit, n_actions, nbase + (uint32_t)(32 * agent) * 0x9E3779B9u);
         }
-        int act = 31 - (int)(__float_as_uint(best) & 31u);
-        if (act >= n_actions) act = 0;  // every key NaN: action 0
         if (env < P.n) {
             if (P.act_dtype == PZ_ACT_U8)
                 reinterpret_cast<unsigned char *>(P.actions)[env * 2 + agent] = (unsigned char)act;

@@ -22,11 +22,9 @@ from .vec_env import PikaVecEnv
 _ACT_CODES = {torch.int32: _lib.ACT_I32, torch.int64: _lib.ACT_I64, torch.uint8: _lib.ACT_U8}
 
 
-def gumbel_noise_reference(seed: int, step: int, first_env: int, n: int, n_actions: int) -> np.ndarray:
-    """float32 [n, 2, n_actions]: the noise pz_policy_mlp_act adds to the logits before its arg-max, restated
-    in numpy from csrc/pz_policy.cu (noise_base / gumbel_key): -ln2 * log2(-log2(u)), i.e. Gumbel noise plus
-    the constant ln(ln 2). Integer part exact; the two logarithms are numpy's float32 ones where the kernel uses
-    the hardware approximation (a few ulp apart)."""
+def _counter_uniform(seed: int, step: int, first_env: int, n: int, n_slots: int) -> np.ndarray:
+    """float32 [n, 2, n_slots]: the uniforms of csrc/pz_policy.cuh (noise_base / uniform_from_counter) for counters
+    (seed, step, first_env + env, agent, slot): ((mixed bits >> 9) + 0.5) / 2^23, exact."""
     m64 = (1 << 64) - 1
     env = np.arange(first_env, first_env + n, dtype=np.uint64)
     with np.errstate(over="ignore"):
@@ -37,14 +35,39 @@ def gumbel_noise_reference(seed: int, step: int, first_env: int, n: int, n_actio
         z = z ^ (z >> np.uint64(31))
         base = (z & np.uint64(0xFFFFFFFF)).astype(np.uint32)[:, None, None]
         k = (np.uint32(32) * np.arange(2, dtype=np.uint32)[None, :, None]
-             + np.arange(n_actions, dtype=np.uint32)[None, None, :] + np.uint32(1))
+             + np.arange(n_slots, dtype=np.uint32)[None, None, :] + np.uint32(1))
         x = base + k * np.uint32(0x9E3779B9)
         x *= np.uint32(0x7FEB352D)
         x ^= x >> np.uint32(15)
         x *= np.uint32(0x846CA68B)
         x ^= x >> np.uint32(16)
-    u = (x >> np.uint32(9)).astype(np.float32) * np.float32(1.0 / 8388608.0) + np.float32(0.5 / 8388608.0)  # exact
+    return (x >> np.uint32(9)).astype(np.float32) * np.float32(1.0 / 8388608.0) + np.float32(0.5 / 8388608.0)
+
+
+def gumbel_noise_reference(seed: int, step: int, first_env: int, n: int, n_actions: int) -> np.ndarray:
+    """float32 [n, 2, n_actions]: the noise the mma.sync implementation of pz_policy_mlp_act adds to the logits
+    before its arg-max, restated in numpy from csrc/pz_policy.cuh (noise_base / gumbel_key):
+    -ln2 * log2(-log2(u)), i.e. Gumbel noise plus the constant ln(ln 2). Integer part exact; the two logarithms are
+    numpy's float32 ones where the kernel uses the hardware approximation (a few ulp apart)."""
+    u = _counter_uniform(seed, step, first_env, n, n_actions)
     return np.float32(-0.693147182) * np.log2(-np.log2(u))
+
+
+def inverse_cdf_reference(logits: np.ndarray, seed: int, step: int, first_env: int) -> np.ndarray:
+    """int64 [n, 2]: the categorical sample the tcgen05 implementation of pz_policy_mlp_act takes
+    (csrc/pz_policy.cuh sample_inverse_cdf), restated in numpy: weights 2^((logit - max) * log2 e), their running
+    sums in action order (float32, sequential), ONE uniform per (env, agent) — slot 0 of the counter stream —, and
+    action = #{j < n_actions - 1 : c_j <= u * c_last}. numpy's exp2 stands where the kernel uses the hardware
+    approximation: samples within a few ulp of a boundary may differ."""
+    lg = np.asarray(logits, dtype=np.float32)
+    n = lg.shape[0]
+    log2e = np.float32(1.44269504)
+    shift = -lg.max(axis=-1, keepdims=True) * log2e
+    w = np.exp2(lg * log2e + shift).astype(np.float32)
+    c = np.cumsum(w, axis=-1, dtype=np.float32)
+    u = _counter_uniform(seed, step, first_env, n, 1)[..., 0]
+    target = (u * c[..., -1]).astype(np.float32)
+    return (c[..., :-1] <= target[..., None]).sum(axis=-1).astype(np.int64)
 
 
 def sample_reference(logits: np.ndarray, noise: Optional[np.ndarray]) -> np.ndarray:
@@ -126,9 +149,11 @@ class MLPPolicy(nn.Module):
                   out: Optional[torch.Tensor] = None, logits_out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Actions [N, 2] of `action_dtype` for feature-major bf16 observations [2, rows, N] (what
         PikaVecEnv(obs_layout="feature_major", obs_dtype=torch.bfloat16, obs_feature_rows=40) emits), by the
-        library's fused kernel: same network as `logits_t`, the categorical sample taken as
-        argmax(logits + Gumbel noise) with counter-based noise keyed by (seed, step, first_env + env, agent,
-        action) — pass a different `step` every call. `logits_out`: optional float32 [N, 2, n_actions]."""
+        library's fused kernel: same network as `logits_t`, the categorical sample driven by
+        counter-based uniforms keyed by (seed, step, first_env + env, agent[, action]) — pass a different `step`
+        every call. The tcgen05 kernel inverts the cumulative distribution with one uniform per (env, agent)
+        (`inverse_cdf_reference`); the mma.sync kernel takes argmax(logits + Gumbel noise) (`gumbel_noise_reference`,
+        `sample_reference`). `logits_out`: optional float32 [N, 2, n_actions]."""
         if not (obs.dim() == 3 and obs.shape[0] == 2 and obs.dtype == torch.bfloat16 and obs.is_cuda
                 and obs.is_contiguous() and obs.shape[1] >= self.K_PAD):
             raise ValueError("act_fused needs contiguous feature-major bf16 observations [2, rows >= 40, N] on a CUDA device")

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from pikazoo_b200 import _lib  # noqa: E402
-from pikazoo_b200.policy import MLPPolicy  # noqa: E402
+from pikazoo_b200.policy import MLPPolicy, inverse_cdf_reference  # noqa: E402
 
 TC, MMA = 0, 1
 L = _lib.load()
@@ -56,7 +56,8 @@ for n_actions in (18, 13, 7):
             "logits_tc_vs_ref": float((l_t - ref).abs().max()),
             "logits_mma_vs_ref": float((l_m - ref).abs().max()),
             "logits_tc_vs_mma": float((l_t - l_m).abs().max()),
-            "sampled_mismatch": float((a_t != a_m).float().mean()),
+            "sampled_mismatch": float((a_t.cpu().numpy().astype("int64")
+                                       != inverse_cdf_reference(l_t.cpu().numpy(), 3, 5, 11)).mean()),
             "greedy_mismatch": float((g_t != g_m).float().mean()),
             "nan_logits_tc": int(torch.isnan(l_t).sum()),
         }

@@ -1,3 +1,4 @@
+"""ms per launch of pz_policy_mlp_act at 2 M envs, both implementations, sampled and greedy (what the sampler costs)."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

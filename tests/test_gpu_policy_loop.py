@@ -137,6 +137,17 @@ def _reference_logits(policy, obs):
     return torch.bmm(policy.w2.float(), h).permute(2, 0, 1).contiguous()
 
 
+def _expected_samples(impl, logits, seed, step, first_env):
+    """What the implementation's categorical sampler must return for these logits and counters (numpy restatements
+    in pikazoo_b200/policy.py): inversion of the cumulative distribution (tcgen05), Gumbel arg-max (mma.sync)."""
+    from pikazoo_b200.policy import gumbel_noise_reference, inverse_cdf_reference, sample_reference
+
+    n, _, n_actions = logits.shape
+    if impl == "tcgen05":
+        return inverse_cdf_reference(logits, seed, step, first_env)
+    return sample_reference(logits, gumbel_noise_reference(seed, step, first_env, n, n_actions))
+
+
 def _played_env(n, **kw):
     import pikazoo_b200
 
@@ -181,7 +192,7 @@ def test_fused_policy_logits_and_greedy_actions(cuda_lib, fused_impl, n):
 @pytest.mark.parametrize("n_actions", [13, 7, 24])
 def test_fused_policy_other_action_counts(cuda_lib, fused_impl, n_actions):
     """13 actions (SimplifyAction) has its own instantiation, other counts take the generic one."""
-    from pikazoo_b200.policy import MLPPolicy, gumbel_noise_reference, sample_reference
+    from pikazoo_b200.policy import MLPPolicy, sample_reference
 
     n = 20_000
     env = _played_env(n)
@@ -190,17 +201,19 @@ def test_fused_policy_other_action_counts(cuda_lib, fused_impl, n_actions):
     a = policy.act_fused(env.obs, step=3, seed=9, logits_out=logits)
     ref = _reference_logits(policy, env.obs)
     assert (logits - ref).abs().max().item() < 2e-3
-    expect = sample_reference(logits.cpu().numpy(), gumbel_noise_reference(9, 3, 0, n, n_actions))
+    expect = _expected_samples(fused_impl, logits.cpu().numpy(), 9, 3, 0)
     assert int((a.cpu().numpy() != expect).sum()) <= 8 and int(a.max()) < n_actions
     g = policy.act_fused(env.obs, step=3, greedy=True, logits_out=logits)
     assert np.array_equal(g.cpu().numpy().astype(np.int64), sample_reference(logits.cpu().numpy(), None))
 
 
-def test_fused_policy_sampling_is_the_documented_argmax(cuda_lib, fused_impl):
-    """actions == argmax(logits + Gumbel noise) with the noise restated in numpy from the counters. The kernel
-    takes its logarithms from the hardware approximation, so keys differ by a few float32 ulp: every mismatch
-    must be a near-tie, and there must be next to none."""
-    from pikazoo_b200.policy import MLPPolicy, gumbel_noise_reference, sample_reference
+def test_fused_policy_sampling_is_the_documented_sampler(cuda_lib, fused_impl):
+    """The sampled actions are a pure function of the logits and the counters, restated in numpy: tcgen05 —
+    inversion of the cumulative distribution with one uniform per (env, agent); mma.sync — argmax(logits + Gumbel
+    noise). The kernels take exp2 / log2 from the hardware approximations, so weights and keys differ from numpy's
+    by a few float32 ulp: every mismatch must be a near-tie (a target within 1e-4 of a boundary of the cumulative
+    distribution, two keys within 1e-4), and there must be next to none."""
+    from pikazoo_b200.policy import MLPPolicy, _counter_uniform, gumbel_noise_reference
 
     n = 50_000
     env = _played_env(n)
@@ -208,14 +221,21 @@ def test_fused_policy_sampling_is_the_documented_argmax(cuda_lib, fused_impl):
     logits = torch.empty((n, 2, 18), device="cuda")
     for step, seed, first in ((0, 0, 0), (7, 123456789, 10**6), (2**40, 2**63 + 5, 3)):
         a = policy.act_fused(env.obs, step=step, seed=seed, first_env=first, logits_out=logits).cpu().numpy()
-        noise = gumbel_noise_reference(seed, step, first, n, 18)
-        keys = logits.cpu().numpy() + noise
-        expect = sample_reference(logits.cpu().numpy(), noise)
+        lg = logits.cpu().numpy()
+        expect = _expected_samples(fused_impl, lg, seed, step, first)
         bad = np.argwhere(a != expect)
         assert len(bad) <= 2 * n * 2e-4, len(bad)
-        for e, ag in bad:
-            top = np.sort(keys[e, ag])[-2:]
-            assert top[1] - top[0] < 1e-4
+        if fused_impl == "tcgen05":
+            p = np.exp(lg.astype(np.float64) - lg.max(axis=-1, keepdims=True))
+            cdf = np.cumsum(p, axis=-1) / p.sum(axis=-1, keepdims=True)
+            u = _counter_uniform(seed, step, first, n, 1)[..., 0].astype(np.float64)
+            for e, ag in bad:
+                assert np.abs(cdf[e, ag] - u[e, ag]).min() < 1e-4 and abs(int(a[e, ag]) - int(expect[e, ag])) == 1
+        else:
+            keys = lg + gumbel_noise_reference(seed, step, first, n, 18)
+            for e, ag in bad:
+                top = np.sort(keys[e, ag])[-2:]
+                assert top[1] - top[0] < 1e-4
     # a different step gives different samples; the same counters give the same ones
     a0 = policy.act_fused(env.obs, step=1).clone()
     assert not torch.equal(a0, policy.act_fused(env.obs, step=2))
@@ -294,9 +314,10 @@ def test_fused_policy_rejects_bad_arguments(cuda_lib, fused_impl):
 
 @pytest.mark.parametrize("n,n_actions", [(128, 18), (1000, 18), (4096 + 8, 13), (1 << 17, 18), (300_001, 7)])
 def test_fused_policy_implementations_agree(cuda_lib, n, n_actions):
-    """The tcgen05 kernel and the warp-level mma.sync kernel are two implementations of ONE definition: same
-    logits (both accumulate the same bf16 products in fp32, sixteen features at a time) and therefore the same
-    greedy and sampled actions, including ragged last tiles and batches smaller than one tile per SM."""
+    """The tcgen05 kernel and the warp-level mma.sync kernel evaluate the same network: same logits (both accumulate
+    the same bf16 products in fp32, sixteen features at a time) and therefore the same greedy actions, including
+    ragged last tiles and batches smaller than one tile per SM. Their categorical samplers differ (inversion of the
+    cumulative distribution / Gumbel arg-max); each returns what its numpy restatement returns."""
     from pikazoo_b200.policy import MLPPolicy
 
     env = _played_env(n)
@@ -312,11 +333,13 @@ def test_fused_policy_implementations_agree(cuda_lib, n, n_actions):
             logits = torch.full((n, 2, n_actions), float("nan"), device="cuda")
             sampled = policy.act_fused(env.obs, step=6, seed=2, first_env=5, logits_out=logits).clone()
             greedy = policy.act_fused(env.obs, step=6, greedy=True, action_dtype=torch.int64).clone()
-            got[name] = (logits, sampled, greedy)
+            expect = _expected_samples(name, logits.cpu().numpy(), 2, 6, 5)
+            assert float((sampled.cpu().numpy() != expect).mean()) <= 2e-4, name
+            got[name] = (logits, greedy)
     finally:
         cuda_lib.pz_policy_select(prev)
-    (l0, s0, g0), (l1, s1, g1) = got["tcgen05"], got["mma_sync"]
+    (l0, g0), (l1, g1) = got["tcgen05"], got["mma_sync"]
     assert not torch.isnan(l0).any() and not torch.isnan(l1).any()
     assert float((l0 - l1).abs().max()) <= 1e-5  # measured: bit-identical
-    assert float((s0 != s1).float().mean()) <= 1e-4 and float((g0 != g1).float().mean()) <= 1e-4
+    assert float((g0 != g1).float().mean()) <= 1e-4
     assert cuda_lib.pz_policy_select(7) == -1  # unknown code: refused, selection unchanged

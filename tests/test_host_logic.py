@@ -136,3 +136,19 @@ def test_policy_noise_and_sampling_restatements():
     tie = np.zeros((1, 2, 18), np.float32)
     tie[0, :, 5] = tie[0, :, 11] = 2.0
     assert sample_reference(tie, None).tolist() == [[5, 5]]
+    # the tcgen05 kernel's sampler: inversion of the cumulative distribution with the stream's first uniform
+    from pikazoo_b200.policy import _counter_uniform, inverse_cdf_reference
+
+    u = _counter_uniform(7, 3, 100, 4096, 1)
+    assert u.shape == (4096, 2, 1) and u.min() > 0 and u.max() < 1 and abs(u.mean() - 0.5) < 0.02
+    assert np.array_equal(u[..., 0], _counter_uniform(7, 3, 100, 4096, 18)[..., 0])  # slot 0 of the Gumbel stream
+    lg = np.random.default_rng(1).normal(size=(100_000, 2, 18)).astype(np.float32)
+    s = inverse_cdf_reference(lg, 7, 3, 100)
+    assert s.shape == (100_000, 2) and s.min() == 0 and s.max() == 17
+    assert np.array_equal(s[50:60], inverse_cdf_reference(lg[50:60], 7, 3, 150))  # keyed by the GLOBAL env index
+    p = np.exp(lg.astype(np.float64)); p /= p.sum(axis=-1, keepdims=True)
+    freq, want = np.bincount(s.ravel(), minlength=18) / s.size, p.mean(axis=(0, 1))
+    assert np.abs(freq - want).max() < 5 * np.sqrt(want.max() / s.size)
+    one_hot = np.full((4, 2, 18), -np.inf, np.float32)
+    one_hot[:, :, 13] = 0.0
+    assert (inverse_cdf_reference(one_hot, 1, 2, 3) == 13).all()  # zero-width intervals are never chosen
