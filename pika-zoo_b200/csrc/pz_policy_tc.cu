@@ -1,35 +1,36 @@
-// pz_policy_mlp_act on the 5th-generation tensor cores (tcgen05 + TMEM).
+// pz_policy_mlp_act on the 5th-generation tensor cores (tcgen05 + TMEM), tiles by TMA.
 //
 // Thread t of a 128-env tile IS env t from the first epilogue on, which is what makes this form cheap: in the
 // warp-level mma.sync kernel (pz_policy.cu) a warp's 16 envs are spread over accumulator fragments, so every
-// hidden activation is rectified / packed and every Gumbel key is built in fragment order (24 candidate slots
-// per quad for 18 actions, quad shuffles for the arg-max), ~1,180 warp instructions per 16 envs. Here, per
-// (tile, agent):
+// hidden activation is rectified / packed and the sample is taken in fragment order (24 candidate slots per quad
+// for 18 actions, quad shuffles), ~1,180 warp instructions per 16 envs. Here, per (tile, agent):
 //
+//   tile      five cp.async.bulk.tensor.3d (one per group of 8 features) bring the observation tile from the
+//             feature-major tensor into the canonical layout below; completion on an mbarrier
 //   layer 1   D1[128 envs][80 hidden]  = X^T[128][48] . W1^T      3 tcgen05.mma (K = 16 each), one issuing thread;
-//             (TMEM, fp32, 80 columns)                            A = the observation tile as it lies in the
-//                                                                 feature-major tensor (MN-major, no swizzle),
-//                                                                 B = W1 (K-major), both in shared memory
+//             (TMEM, fp32, 80 columns)                            A = the tile (MN-major, no swizzle), B = W1
+//                                                                 (K-major), both in shared memory
 //   epilogue  thread t reads row t of D1 (tcgen05.ld 32x32b), rectifies, rounds to bf16 and stores the 40 packed
 //             pairs back over the columns it has read (tcgen05.st) as row t of H
 //   layer 2   D2[128][32]              = H[128][80] . W2^T        5 tcgen05.mma with A taken from TMEM
-//   sample    thread t reads its env's logits (one row of D2) and takes argmax(logit + Gumbel) over exactly
-//             n_actions candidates in registers: no shuffles, no padded slots
+//   sample    thread t reads its env's logits (one row of D2) and inverts the cumulative distribution in registers
+//             (sample_inverse_cdf, pz_policy.cuh): no shuffles, no padded slots
 //
 // The tensor-core work of one (tile, agent) is a serial chain (MMA -> epilogue -> MMA -> sample) of latencies, and
 // a chain holds 80 TMEM columns while it runs (D1 0..79, H in place 0..39, D2 40..71), so the SM's 512 columns
 // carry six of them: ONE persistent CTA per SM stages the weights once and runs six chains of 128 threads, two per
-// tile (one per agent), each with its own named barrier, mbarrier, TMEM columns and a double-buffered observation
-// tile: the tile after next is fetched with cp.async while a tile is computed, and layer 1 of the NEXT tile is
-// issued as soon as every thread holds its logits in registers, so that its round trip through the tensor core
-// hides behind the sampling arithmetic. Measured on B200, 2 M envs: 0.150 ms (four independent 128-thread CTAs per
-// SM without the pipeline 0.181; three 256-thread chains that batch both agents' MMAs 0.157; the mma.sync kernel
-// 0.219). PZ_TC_AGENTS_PER_CHAIN=2 builds the three-chain form.
+// tile (one per agent), each with its own named barrier, mbarriers, TMEM columns and a double-buffered observation
+// tile: the tile after next is fetched while a tile is computed (its bulk copies are issued while layer 2 is in the
+// tensor core), and layer 1 of the NEXT tile is issued as soon as every thread holds its logits in registers, so
+// that its round trip through the tensor core hides behind the sampling arithmetic. Measured on B200, 2 M envs:
+// 0.094 ms (the mma.sync kernel 0.219; the steps in between are in DESIGN.md section 4a).
+// PZ_TC_AGENTS_PER_CHAIN=2 builds three chains of 256 threads that batch both agents' MMAs; PZ_TC_TIMING a debug
+// build that stamps a chain's phases (profiles/policy_chain_phases.py).
 //
 // Canonical shared-memory layouts (no swizzle; 8 x 16-byte "core matrices" of 128 contiguous bytes):
 //   X  (MN-major A): element (env m, feature k) at (k / 8) * 2048 + (m / 8) * 128 + (k % 8) * 16 + (m % 8) * 2
 //                    -> a 16-byte piece of 8 consecutive envs of one feature row lands as one 16-byte row of a
-//                       core matrix, so the tile is filled by plain 16-byte cp.async from the feature-major rows
+//                       core matrix: an (8 envs, 8 features, 16 env atoms) TMA box is one group of 8 features
 //   W1 (K-major B):  element (hidden n, feature k) at (k / 8) * 1280 + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2
 //   W2 (K-major B):  element (action n, hidden k)  at (k / 8) *  512 + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2
 #include <cuda.h>  // CUtensorMap; the driver entry point is looked up at run time, libcuda is not linked
