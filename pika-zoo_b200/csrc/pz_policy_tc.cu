@@ -205,6 +205,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int seq = kAPC == 2 ? chain : chain >> 1;       // which of the CTA's three tile sequences the chain walks
     const uint32_t bar = s_base + kOffBar + 24 * chain;  // +8, +16: the tile buffers' barriers
 
+    // Programmatic dependent launch (both calls are no-ops for an ordinary launch): the next kernel in the stream
+    // — the step kernel, which parks in its own cudaGridDependencySynchronize — may be scheduled as this grid's CTAs
+    // leave; and this kernel's set-up below (TMEM, barriers, 173 KB of zeroed shared memory) runs while the previous
+    // kernel's last CTAs drain. Nothing that a predecessor may have written (weights, observations) is read before
+    // cudaGridDependencySynchronize.
+    cudaTriggerProgrammaticLaunchCompletion();
     // ---- once per CTA: TMEM, the barriers, zeroed operands, the weights in canonical K-major order ----
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + kOffTmemSlot),
@@ -220,6 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int i = tid; i < kOffBar / 16; i += kThreads) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
+    cudaGridDependencySynchronize();
     {
         __nv_bfloat16 *w1s = reinterpret_cast<__nv_bfloat16 *>(smem + kOffW1);
         for (int i = tid; i < 2 * P.h1 * P.k1; i += kThreads) {
@@ -495,8 +502,18 @@ static cudaError_t launch_one(const Params &P, unsigned grid, cudaStream_t strea
     // whole groups of 8 envs only travel by bulk copy: a ragged tail (n % 8 != 0) keeps the element-wise path
     const int use_tma = (P.n % 8 == 0 && make_obs_map(P, &map)) ? 1 : 0;
     if (!use_tma) memset(&map, 0, sizeof(map));
-    pz_policy_mlp_tc_kernel<NA><<<grid, kThreads, kSmemBytes, stream>>>(P, map, use_tma);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, pz_policy_mlp_tc_kernel<NA>, P, map, use_tma);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace tc
