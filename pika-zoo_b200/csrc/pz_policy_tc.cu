@@ -117,26 +117,16 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 #ifndef PZ_TC_EPI_BATCH
 #define PZ_TC_EPI_BATCH 2
 #endif
-#ifndef PZ_TC_WAIT_HINT
-#define PZ_TC_WAIT_HINT 0x989680u
-#endif
-// Bounded: a wrong descriptor must end in a launch failure, not in a hung device.
+// Bounded: a wrong descriptor must end in a launch failure, not in a hung device. try_wait suspends the thread up to
+// the hinted time before it returns (shorter hints and plain test_wait polling measured the same).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    for (uint32_t spins = 0; !done; spins++) {  // try_wait suspends the thread up to the hinted time before it returns
-#ifdef PZ_TC_SPIN
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-#else
+    for (uint32_t spins = 0; !done; spins++) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity), "r"(PZ_TC_WAIT_HINT)
+            : "r"(bar), "r"(parity), "r"(0x989680u)
             : "memory");
-#endif
         if (!done && spins > (1u << 20)) __trap();
     }
 }
@@ -192,6 +182,7 @@ template <int NA>
 __global__ void __launch_bounds__(kThreads, 1)
     pz_policy_mlp_tc_kernel(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap tmap, const int use_tma) {
     const int n_actions = NA ? NA : P.n_actions;
+    constexpr int kCand = NA ? NA : PZ_POLICY_MAX_ACTIONS;  // candidates the unrolled loops run over
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kOffTmemSlot);
@@ -296,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    // layer 1 of both agents of the tile in buffer b -> D1 (one thread)
+    // layer 1 of the chain's agent(s) of the tile in buffer b -> D1 (one thread)
     uint32_t full_phase = 0;  // bit b: parity the next wait on buffer b's barrier uses (tracked by every thread)
     auto issue_layer1 = [&](uint32_t b) {
         if (use_tma) mbar_wait(bar + 8 + 8 * b, (full_phase >> b) & 1u);  // the bulk copies of this tile have landed
@@ -311,7 +302,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                        kIdesc1, ks > 0);
         mma_commit(bar);
     };
-    // cp.async data of every group but the newest has landed -> visible to the tensor core after the chain's barrier
+    // The chain's barrier before layer 1 of a tile is issued: every thread's TMEM reads of the previous tile are
+    // done; without TMA, also: the cp.async data of every group but the newest has landed and is made visible to the
+    // tensor core (with TMA the issuing thread waits on the tile's own mbarrier instead)
     auto tile_ready = [&]() {
         if (!use_tma) {
             asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -370,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         tc_fence_before();
         chain_sync(chain);
         PZ_STAMP(3);
-        // ---- layer 2 of both agents -> D2
+        // ---- layer 2 -> D2
         if (wic == 0 && elect_one()) {
             tc_fence_after();
 #pragma unroll
@@ -389,7 +382,6 @@ __global__ void __launch_bounds__(kThreads, 1)
             load_tile(tile + 2 * t_stride, buf);
         else
             asm volatile("cp.async.commit_group;" ::: "memory");
-        constexpr int kCand = NA ? NA : PZ_POLICY_MAX_ACTIONS;
         PZ_STAMP(5);
         mbar_wait(bar, phase);
         phase ^= 1u;
@@ -419,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #ifndef PZ_TC_TIMING
         if (P.logits != nullptr && env < P.n) {  // launch-uniform pointer
 #pragma unroll
-            for (int j = 0; j < (NA ? NA : PZ_POLICY_MAX_ACTIONS); j++)
+            for (int j = 0; j < kCand; j++)
                 if (j < n_actions) P.logits[(env * 2 + agent) * n_actions + j] = __uint_as_float(lg[j]);
         }
 #endif
