@@ -494,8 +494,8 @@ def run_b200_arm(args):
         variants["configs[4]_fused_policy_kernel_loop_2M_envs_per_gpu"] = {
             "ms_per_step": float(tf.item()) / 200, "env_steps_per_sec": n5 * world * 200 / (float(tf.item()) * 1e-3),
             "of_which_policy_kernel_us": tc_us, "policy_kernel_us_mma_sync_implementation": mma_us,
-            "note": "policy = pz_policy_mlp_act (tcgen05.mma, accumulators and hidden activations in TMEM, one pass "
-                    "over the 160 B of observations per env)"}
+            "note": "policy = pz_policy_mlp_act (tcgen05.mma, tiles by TMA, accumulators and hidden activations in "
+                    "TMEM, one pass over the 160 B of observations per env)"}
         del v, pol, actor
         return variants
 
