@@ -24,11 +24,27 @@ struct Params {
     float *logits;  // optional [n][2][n_actions]
 };
 
+#ifdef PZ_HOST_EMULATION  // tests/emul: this header compiled for the host; libm stands in for the MUFU approximations
+__device__ __forceinline__ float lg2_approx(float x) { return log2f(x); }
+__device__ __forceinline__ float ex2_approx(float x) { return exp2f(x); }
+#else
 __device__ __forceinline__ float lg2_approx(float x) {  // MUFU.LG2; the arguments here are normal numbers
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// Two fp32 values rectified and rounded to a packed bf16 pair (low half = lo) in one conversion instruction
+__device__ __forceinline__ uint32_t relu_pack_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+#endif
 
 // Counter-based noise, restated in pika-zoo_b200/policy.py (gumbel_noise_reference) for the tests: one 64-bit
 // mix per (seed, step, global env), one 32-bit mix per (agent, action). The key added to a logit is
@@ -71,19 +87,6 @@ __device__ __forceinline__ float gumbel_key_from(float logit, uint32_t agent_bas
 // relative truncation of the key is far below the noise resolution.
 __device__ __forceinline__ float pack_key(float key, int action) {
     return __uint_as_float((__float_as_uint(key) | 31u) ^ (uint32_t)action);  // low five bits = 31 - action: one LOP3
-}
-
-// Two fp32 values rectified and rounded to a packed bf16 pair (low half = lo) in one conversion instruction
-__device__ __forceinline__ uint32_t relu_pack_bf16x2(float lo, float hi) {
-    uint32_t d;
-    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    return d;
-}
-
-__device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
 }
 
 // The tcgen05 kernel's categorical sample (one thread holds all the logits of its env and agent): inversion of the

@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "_build", "libpz_emul.so")
 DEPS = [os.path.join(HERE, "pz_emul.cpp")] + [
-    os.path.join(ROOT, "pika-zoo_b200", "csrc", f) for f in ("pz_state.cuh", "pz_rng.cuh", "pz_physics.cuh")]
+    os.path.join(ROOT, "pika-zoo_b200", "csrc", f) for f in ("pz_state.cuh", "pz_rng.cuh", "pz_physics.cuh", "pz_policy.cuh")]
 
 
 def cuda_include():
@@ -22,5 +22,5 @@ def build():
         return None
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in DEPS):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", inc, "-o", LIB, DEPS[0]], check=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", inc, "-I", os.path.join(ROOT, "include"), "-o", LIB, DEPS[0]], check=True)
     return LIB

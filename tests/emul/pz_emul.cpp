@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE — the DEVICE code of pika-zoo_b200/csrc (pz_state.cuh, pz_rng.cuh,
-// pz_physics.cuh) compiled for the host with g++, one lane per "warp", so that the packing,
+// pz_physics.cuh, and the samplers of pz_policy.cuh) compiled for the host with g++, one lane per "warp", so that the packing,
 // the PCG64 restatement, the fast-forwarded trajectory simulations and the computer player can be
 // fuzzed against the oracle in the `-m "not gpu"` suite (tests/test_device_code_on_host.py).
 // It is never linked into the product: libpikazoo_b200.so is built by nvcc from the .cu files only,
@@ -38,7 +38,11 @@ template <typename T>
 static inline T __shfl_sync(unsigned, T v, int) { return v; }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 
+static inline float __uint_as_float(uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t v; std::memcpy(&v, &f, 4); return v; }
+
 #include "../../pika-zoo_b200/csrc/pz_physics.cuh"
+#include "../../pika-zoo_b200/csrc/pz_policy.cuh"
 
 using namespace pz;
 
@@ -196,6 +200,42 @@ void emul_normalize(int64_t n, const int32_t *u, float *f32, double *f64, int no
 
 int emul_synth_action(uint64_t seed, uint64_t env, uint64_t frame, int agent, uint32_t n_actions) {
     return synth_action(seed, env, frame, agent, n_actions);
+}
+
+// The policy kernels' samplers (pz_policy.cuh) on host logits float32 [n][2][n_actions]:
+//   emul_policy_inverse_cdf: what the tcgen05 kernel's threads compute (NA = 18 instantiation when n_actions == 18,
+//                            the generic 24-candidate one otherwise), actions int32 [n][2]
+//   emul_policy_gumbel_keys: the mma.sync kernel's keys logit + noise (before packing), float32 [n][2][n_actions]
+void emul_policy_inverse_cdf(int64_t n, int n_actions, const float *logits, uint64_t seed, uint64_t step,
+                             uint64_t first_env, int generic, int32_t *actions) {
+    for (int64_t e = 0; e < n; e++) {
+        const uint32_t nbase = pzp::noise_base(seed, step, first_env + (uint64_t)e);
+        for (int a = 0; a < 2; a++) {
+            const float *l = logits + (e * 2 + a) * n_actions;
+            const uint32_t agent_base = nbase + (uint32_t)(32 * a) * 0x9E3779B9u;
+            if (n_actions == 18 && !generic) {
+                float v[18];
+                for (int j = 0; j < 18; j++) v[j] = l[j];
+                actions[e * 2 + a] = pzp::sample_inverse_cdf<18>(v, 18, agent_base);
+            } else {
+                float v[PZ_POLICY_MAX_ACTIONS];
+                for (int j = 0; j < PZ_POLICY_MAX_ACTIONS; j++) v[j] = j < n_actions ? l[j] : 0.0f;
+                actions[e * 2 + a] = pzp::sample_inverse_cdf<PZ_POLICY_MAX_ACTIONS>(v, n_actions, agent_base);
+            }
+        }
+    }
+}
+
+void emul_policy_gumbel_keys(int64_t n, int n_actions, const float *logits, uint64_t seed, uint64_t step,
+                             uint64_t first_env, float *keys) {
+    for (int64_t e = 0; e < n; e++) {
+        const uint32_t nbase = pzp::noise_base(seed, step, first_env + (uint64_t)e);
+        for (int a = 0; a < 2; a++)
+            for (int j = 0; j < n_actions; j++) {
+                const int64_t i = (e * 2 + a) * n_actions + j;
+                keys[i] = pzp::gumbel_key(logits[i], nbase, a, j);
+            }
+    }
 }
 
 }  // extern "C"

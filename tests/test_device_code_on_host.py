@@ -264,3 +264,56 @@ def test_synth_actions_match(emul):
         for n_actions in (13, 18):
             assert emul.emul_synth_action(91, env, frame, agent, n_actions) == po.synth_action(91, env, frame, agent,
                                                                                                n_actions)
+
+
+# ---- the policy kernels' samplers (csrc/pz_policy.cuh) -------------------------------------------------------
+@pytest.mark.parametrize("n_actions,generic", [(18, 0), (18, 1), (13, 1), (7, 1), (24, 1), (1, 1)])
+def test_policy_inverse_cdf_sampler_matches_numpy_restatement(emul, n_actions, generic):
+    """sample_inverse_cdf — the code the tcgen05 policy kernel's threads run — on random logits against
+    policy.inverse_cdf_reference: counters (incl. 64-bit seeds / steps and the global env offset), both template
+    forms (18 candidates; 24 with a run-time count), peaked and flat distributions, -inf logits. libm's exp2f stands
+    in for MUFU.EX2 here and numpy's exp2 there, so a sample may differ where the target falls within rounding of a
+    boundary of the cumulative sums: next to never, and then by one action."""
+    from pikazoo_b200.policy import inverse_cdf_reference
+
+    emul.emul_policy_inverse_cdf.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64,
+                                             ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p]
+    n = 60_000
+    rng = np.random.default_rng(n_actions + generic)
+    logits = (rng.normal(size=(n, 2, n_actions)) * rng.choice([0.1, 1.0, 6.0], size=(n, 1, 1))).astype(np.float32)
+    logits[rng.random(logits.shape) < 0.02] = -np.inf
+    logits[:, :, 0] = np.where(np.isinf(logits).all(axis=-1), 0.0, logits[:, :, 0])  # at least one finite logit
+    for seed, step, first in ((0, 0, 0), (2**63 + 11, 2**40 + 3, 10**9)):
+        got = np.zeros((n, 2), dtype=np.int32)
+        emul.emul_policy_inverse_cdf(n, n_actions, _p(logits), seed, step, first, generic, _p(got))
+        want = inverse_cdf_reference(logits, seed, step, first)
+        assert got.min() >= 0 and got.max() < n_actions
+        bad = np.argwhere(got != want)
+        assert len(bad) <= 4, len(bad)
+        for e, a in bad:
+            assert abs(int(got[e, a]) - int(want[e, a])) == 1
+        assert not np.isinf(np.take_along_axis(logits, got[..., None].astype(np.int64), axis=-1)).any()  # p = 0 is never drawn
+    if n_actions > 1:  # and the frequencies are softmax(logits)
+        flat = np.broadcast_to(rng.normal(size=(1, 1, n_actions)).astype(np.float32), (n, 2, n_actions)).copy()
+        got = np.zeros((n, 2), dtype=np.int32)
+        emul.emul_policy_inverse_cdf(n, n_actions, _p(flat), 5, 6, 7, generic, _p(got))
+        p = np.exp(flat[0, 0].astype(np.float64))
+        p /= p.sum()
+        freq = np.bincount(got.ravel(), minlength=n_actions) / got.size
+        assert np.all(np.abs(freq - p) < 5 * np.sqrt(p * (1 - p) / got.size) + 1e-6)
+
+
+def test_policy_gumbel_keys_match_numpy_restatement(emul):
+    """gumbel_key — the mma.sync policy kernel's noise — against policy.gumbel_noise_reference (libm log2f here,
+    numpy's log2 there: a few float32 ulp)."""
+    from pikazoo_b200.policy import gumbel_noise_reference
+
+    emul.emul_policy_gumbel_keys.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64,
+                                             ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
+    n = 20_000
+    logits = np.random.default_rng(3).normal(size=(n, 2, 18)).astype(np.float32)
+    for seed, step, first in ((1, 2, 3), (2**64 - 1, 2**50, 123456)):
+        keys = np.zeros_like(logits)
+        emul.emul_policy_gumbel_keys(n, 18, _p(logits), seed, step, first, _p(keys))
+        want = logits + gumbel_noise_reference(seed, step, first, n, 18)
+        assert np.abs(keys - want).max() < 2e-5
