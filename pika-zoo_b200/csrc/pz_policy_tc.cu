@@ -118,16 +118,25 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 #define PZ_TC_EPI_BATCH 2
 #endif
 // Bounded: a wrong descriptor must end in a launch failure, not in a hung device. try_wait suspends the thread up to
-// the hinted time before it returns (shorter hints and plain test_wait polling measured the same).
+// the hinted time before it returns (shorter hints and plain test_wait polling measured the same); a wait that has
+// polled 64 times starts watching the wall clock and traps after two seconds.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
+    unsigned long long t0 = 0;
     for (uint32_t spins = 0; !done; spins++) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(bar), "r"(parity), "r"(0x989680u)
             : "memory");
-        if (!done && spins > (1u << 20)) __trap();
+        if (!done && spins >= 64) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0)
+                t0 = now;
+            else if (now - t0 > 2000000000ULL)
+                __trap();
+        }
     }
 }
 
