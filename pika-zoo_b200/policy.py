@@ -183,18 +183,20 @@ class FusedActor:
     def __init__(self, policy: MLPPolicy, env: PikaVecEnv, seed: int = 0, greedy: bool = False):
         self.policy, self.env, self.seed, self.greedy, self.step = policy, env, int(seed), greedy, 0
         self.actions = torch.empty((env.num_envs, 2), dtype=env.action_dtype, device=env.device)
-        self._seen, self._w1p, self._w2p = None, 0, 0
+        self._seen, self._w1p, self._w2p, self._knobs = None, 0, 0, None
 
     def __call__(self, obs: torch.Tensor) -> torch.Tensor:
         # The loop is two launches per step of ~0.1 ms each: like PikaVecEnv.step, this path caches every constant
         # argument after it has validated a buffer once (act_fused does that, and sets the ones row), and enters
         # the device guard only when another device is current.
         pol = self.policy
-        if obs is not self._seen or pol.w1.data_ptr() != self._w1p or pol.w2.data_ptr() != self._w2p:
+        if (obs is not self._seen or pol.w1.data_ptr() != self._w1p or pol.w2.data_ptr() != self._w2p
+                or (self.seed, self.greedy) != self._knobs):
             pol.act_fused(obs, self.step, seed=self.seed, first_env=self.env.first_env, greedy=self.greedy,
                           out=self.actions)
             if pol.w1.is_contiguous() and pol.w2.is_contiguous():
                 self._seen, self._w1p, self._w2p = obs, pol.w1.data_ptr(), pol.w2.data_ptr()
+                self._knobs = (self.seed, self.greedy)
                 n = obs.shape[2]
                 self._head = (obs.data_ptr(), n, n, obs.shape[1], self._w1p, pol.w1.shape[1], pol.w1.shape[2], self._w2p,
                               pol.w2.shape[1], pol.w2.shape[2], self.seed & (2**64 - 1))
