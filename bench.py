@@ -484,7 +484,7 @@ def run_b200_arm(args):
             return a.elapsed_time(b) * 1e3 / 200
 
         tc_us = policy_kernel_us()
-        prev = lib.pz_policy_select(1)  # A/B: the warp-level mma.sync implementation of the same definition
+        prev = lib.pz_policy_select(1)  # A/B: the warp-level mma.sync implementation of the same network
         try:
             for _ in range(5):
                 actor(v.obs)

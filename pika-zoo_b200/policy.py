@@ -5,7 +5,7 @@ take its sampled actions without ever leaving the device — observations arrive
 straight from the step kernel (NormalizeObservation fused). `act_fused()` / `FusedActor` run the same
 network for acting through the library's own kernel (csrc/pz_policy_tc.cu: both layers on tcgen05 with the
 accumulators in TMEM and the categorical sample, in one pass over the observations: 0.10 ms instead of 1.45 ms
-per 2 M envs; csrc/pz_policy.cu is the warp-level mma.sync form of the same definition)."""
+per 2 M envs; csrc/pz_policy.cu is the warp-level mma.sync form of the same network, with a Gumbel arg-max sampler)."""
 
 from __future__ import annotations
 
