@@ -1,6 +1,6 @@
 /* The C ABI on its own: no Python, no torch. Builds with
- *     gcc examples/c_abi_demo.c -Iinclude -I/usr/local/cuda/include -Lpika-zoo_b200/csrc -lpikazoo_b200 \
- *         -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,$PWD/pika-zoo_b200/csrc -o c_abi_demo
+ *     gcc examples/c_abi_demo.c -Iinclude -I/usr/local/cuda/include -Lpikazoo_b200/csrc -lpikazoo_b200 \
+ *         -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,$PWD/pikazoo_b200/csrc -o c_abi_demo
  * and prints two lines that tests/test_gpu_c_abi_demo.py compares with the oracle:
  *   device path: n envs, computer vs computer (actions_dev = NULL), T pz_step calls, then the unpacked
  *                state of every env is folded into one 64-bit checksum;

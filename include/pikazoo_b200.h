@@ -219,7 +219,7 @@ void pz_host_destroy(pz_host_ctx *ctx);
 
 /* ---- caller side: the MLP policy of BASELINE.json configs[4], evaluated and sampled in one kernel ----
  * The reference has no policy; this is the product's own helper for the loop `obs -> policy -> step`
- * (pika-zoo_b200/policy.py), fed by the feature-major bf16 observations of pz_step (PZ_LAYOUT_FEATURE_MAJOR).
+ * (pikazoo_b200/policy.py), fed by the feature-major bf16 observations of pz_step (PZ_LAYOUT_FEATURE_MAJOR).
  *   obs_dev      bf16 [2][rows][ld]: element (agent, feature k, env) at (agent * rows + k) * ld + env; rows
  *                0 .. features-1 enter the contraction (policy.py folds the biases in through a row of ones)
  *   w1_dev       bf16 [2][hidden_rows][features], w2_dev bf16 [2][n_actions][w2_cols] (row-major, per agent)

@@ -1,7 +1,7 @@
 /* TEST INFRASTRUCTURE — CPU restatement of the reference hot path (oracle).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
- * legs may load this library; the product (pika-zoo_b200/) never does.
+ * legs may load this library; the product (pikazoo_b200/) never does.
  *
  * Parity status: the reference holds no golden vectors or known-answer tests for this
  * path (SURVEY.md §4, §8(c) — "parity unpinned" at the reference's own test level), so

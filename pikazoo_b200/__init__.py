@@ -1,18 +1,16 @@
-"""Importable alias of the `pika-zoo_b200/` package (a hyphen is not a valid identifier).
+"""pikazoo_b200: B200-native batched Pikachu Volleyball (drop-in for the hot path of
+helpingstar/pika-zoo).
 
     import pikazoo_b200
     from pikazoo_b200 import pikazoo_v0, PikaVecEnv
     from pikazoo_b200.wrappers import SimplifyAction
 """
 
-import importlib as _importlib
-import os as _os
-import sys as _sys
+from . import pikazoo_v0, wrappers  # noqa: F401
+from ._lib import PikaLibraryError, load as load_library  # noqa: F401
+from .dist import allreduce_stats, make_sharded_env, shard_range  # noqa: F401
+from .vec_env import PikaVecEnv, make_config  # noqa: F401
+from .wrappers import (ConvertSingleAgent, NormalizeObservation, RecordEpisodeStatistics,  # noqa: F401
+                       RewardByBallPosition, RewardInNormalState, SimplifyAction)
 
-_root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
-if _root not in _sys.path:
-    _sys.path.insert(0, _root)
-_real = _importlib.import_module("pika-zoo_b200")
-_sys.modules[__name__] = _real
-for _name in ("pikazoo_v0", "wrappers", "vec_env", "dist", "spaces", "_lib"):
-    _sys.modules[f"{__name__}.{_name}"] = _importlib.import_module(f"pika-zoo_b200.{_name}")
+__version__ = "0.1.0"

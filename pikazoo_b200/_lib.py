@@ -80,14 +80,14 @@ _lib = None
 
 
 def load() -> ctypes.CDLL:
-    """Load csrc/libpikazoo_b200.so (build it with `python pika-zoo_b200/build.py`)."""
+    """Load csrc/libpikazoo_b200.so (build it with `python pikazoo_b200/build.py`)."""
     global _lib
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
         raise PikaLibraryError(
             f"{LIB_PATH} is missing: the CUDA extension has not been built "
-            "(run `python pika-zoo_b200/build.py` or __graft_entry__.build()). There is no CPU fallback."
+            "(run `python pikazoo_b200/build.py` or __graft_entry__.build()). There is no CPU fallback."
         )
     L = ctypes.CDLL(LIB_PATH)
     vp, i64, u64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int32

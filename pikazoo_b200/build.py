@@ -1,6 +1,6 @@
 """Build the sm_100a shared library (csrc/libpikazoo_b200.so) in-tree with nvcc.
 
-    python pika-zoo_b200/build.py [--force] [--verbose] [--out variants/NAME.so]
+    python pikazoo_b200/build.py [--force] [--verbose] [--out variants/NAME.so]
 
 --out builds a tuning variant (with PZ_NVCC_FLAGS=-D...) beside the product library instead of replacing it;
 PIKAZOO_B200_LIB=<that path> makes the package load it.

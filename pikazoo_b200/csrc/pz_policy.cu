@@ -1,5 +1,5 @@
 // Caller side of the hot path (BASELINE.json configs[4]: "actions from an on-device MLP policy in a rollout
-// loop"): the two-layer MLP of pika-zoo_b200/policy.py evaluated for both agents and sampled, in ONE kernel,
+// loop"): the two-layer MLP of pikazoo_b200/policy.py evaluated for both agents and sampled, in ONE kernel,
 // straight from the simulator's feature-major bf16 observations.
 //
 //   logits[env][agent][:] = W2[agent] . relu(W1[agent] . x[agent][:, env])         bf16 in, fp32 accumulate

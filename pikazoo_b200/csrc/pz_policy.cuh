@@ -46,7 +46,7 @@ __device__ __forceinline__ uint32_t relu_pack_bf16x2(float lo, float hi) {
 }
 #endif
 
-// Counter-based noise, restated in pika-zoo_b200/policy.py (gumbel_noise_reference) for the tests: one 64-bit
+// Counter-based noise, restated in pikazoo_b200/policy.py (gumbel_noise_reference) for the tests: one 64-bit
 // mix per (seed, step, global env), one 32-bit mix per (agent, action). The key added to a logit is
 //   key = fma(-ln2, log2(-log2(u)), logit) = logit + Gumbel(u) + ln(ln 2): the constant does not move the arg-max.
 __device__ __forceinline__ uint32_t noise_base(uint64_t seed, uint64_t step, uint64_t genv) {
@@ -94,7 +94,7 @@ __device__ __forceinline__ float pack_key(float key, int action) {
 // (seed, step, global env, agent, action 0):
 //   w_j = 2^((logit_j - max) * log2 e),  c_j = w_0 + ... + w_j (fp32, in action order),
 //   action = #{ j < n_actions - 1 : c_j <= u * c_last }
-// i.e. P(action = j) = softmax(logits)_j up to the 2^-23 resolution of u. Restated in pika-zoo_b200/policy.py
+// i.e. P(action = j) = softmax(logits)_j up to the 2^-23 resolution of u. Restated in pikazoo_b200/policy.py
 // (inverse_cdf_reference). A third of the Gumbel arg-max's instructions and half of its special-function work.
 template <int N>
 __device__ __forceinline__ int sample_inverse_cdf(const float (&logit)[N], int n_actions, uint32_t agent_base) {

@@ -1,7 +1,7 @@
 """Cycle stamps of one chain of the tcgen05 policy kernel (clock64 at its phase boundaries, iterations 4..11 of chain
 0 of CTA 0), from a debug build that writes them into the logits buffer:
 
-    PZ_NVCC_FLAGS=-DPZ_TC_TIMING python pika-zoo_b200/build.py --out variants/timing.so
+    PZ_NVCC_FLAGS=-DPZ_TC_TIMING python pikazoo_b200/build.py --out variants/timing.so
     PIKAZOO_B200_LIB=variants/timing.so python profiles/policy_chain_phases.py
 """
 import os, sys, json

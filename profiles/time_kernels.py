@@ -2,7 +2,7 @@
 
     python profiles/time_kernels.py [n_envs] [reps]
 
-Not the bench: no host path, no CPU baseline. Used to compare builds (PZ_NVCC_FLAGS=... python pika-zoo_b200/build.py).
+Not the bench: no host path, no CPU baseline. Used to compare builds (PZ_NVCC_FLAGS=... python pikazoo_b200/build.py).
 """
 import json
 import os

@@ -35,7 +35,7 @@ def cuda_lib():
     """Build (if needed) and load the CUDA library; GPU tests must run the native path."""
     import importlib
 
-    build = importlib.import_module("pika-zoo_b200.build")
+    build = importlib.import_module("pikazoo_b200.build")
     build.build()
     import pikazoo_b200
 

@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "_build", "libpz_emul.so")
 DEPS = [os.path.join(HERE, "pz_emul.cpp")] + [
-    os.path.join(ROOT, "pika-zoo_b200", "csrc", f) for f in ("pz_state.cuh", "pz_rng.cuh", "pz_physics.cuh", "pz_policy.cuh")]
+    os.path.join(ROOT, "pikazoo_b200", "csrc", f) for f in ("pz_state.cuh", "pz_rng.cuh", "pz_physics.cuh", "pz_policy.cuh")]
 
 
 def cuda_include():

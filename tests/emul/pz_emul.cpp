@@ -1,9 +1,9 @@
-// TEST INFRASTRUCTURE — the DEVICE code of pika-zoo_b200/csrc (pz_state.cuh, pz_rng.cuh,
+// TEST INFRASTRUCTURE — the DEVICE code of pikazoo_b200/csrc (pz_state.cuh, pz_rng.cuh,
 // pz_physics.cuh, and the samplers of pz_policy.cuh) compiled for the host with g++, one lane per "warp", so that the packing,
 // the PCG64 restatement, the fast-forwarded trajectory simulations and the computer player can be
 // fuzzed against the oracle in the `-m "not gpu"` suite (tests/test_device_code_on_host.py).
 // It is never linked into the product: libpikazoo_b200.so is built by nvcc from the .cu files only,
-// and nothing under pika-zoo_b200/ can load this. The kernel glue (launch geometry, bulk-copy
+// and nothing under pikazoo_b200/ can load this. The kernel glue (launch geometry, bulk-copy
 // observation output, statistics atomics) is NOT covered here; the -m gpu tests cover it.
 #define PZ_HOST_EMULATION 1
 #include <cuda_runtime.h>  // vector types only; no CUDA call is made
@@ -41,8 +41,8 @@ static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline float __uint_as_float(uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
 static inline uint32_t __float_as_uint(float f) { uint32_t v; std::memcpy(&v, &f, 4); return v; }
 
-#include "../../pika-zoo_b200/csrc/pz_physics.cuh"
-#include "../../pika-zoo_b200/csrc/pz_policy.cuh"
+#include "../../pikazoo_b200/csrc/pz_physics.cuh"
+#include "../../pikazoo_b200/csrc/pz_policy.cuh"
 
 using namespace pz;
 

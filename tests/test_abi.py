@@ -63,7 +63,7 @@ def test_argument_validation_without_gpu(cuda_lib):
 
 def test_product_does_not_import_oracle():
     # the product path must never route through the oracle
-    pkg = os.path.join(ROOT, "pika-zoo_b200")
+    pkg = os.path.join(ROOT, "pikazoo_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
