@@ -48,7 +48,7 @@ int main(int argc, char **argv) {
 
     /* ---- device-pointer entry points: computer vs computer ---- */
     pz_config cfg;
-    pz_default_config(&cfg);
+    if (pz_config_init(&cfg, sizeof cfg)) return 3;
     cfg.is_player1_computer = cfg.is_player2_computer = 1;
     cfg.winning_score = 3;
     cfg.serve = PZ_SERVE_RANDOM;
@@ -73,7 +73,7 @@ int main(int argc, char **argv) {
 
     /* ---- host-buffer entry points: random actions, fused SimplifyAction ---- */
     pz_config hc;
-    pz_default_config(&hc);
+    if (pz_config_init(&hc, sizeof hc)) return 3;
     hc.simplify_action = 1;
     hc.winning_score = 2;
     pz_host_ctx *ctx = NULL;

@@ -18,7 +18,7 @@
  *   pz_step_ex                pz_step + RecordEpisodeStatistics   pikazoo/wrappers/record_episode_statistics.py:17-40
  *                             (per-env running return / length) and optional truncation
  *   pz_rollout                K x raw_env.step with the state held in registers
- *   pz_step_host              raw_env.step for callers holding HOST buffers (numpy users)
+ *   pz_host_step              raw_env.step for callers holding HOST buffers (numpy users)
  *   pz_export_state / pz_import_state   the Python object graph <-> packed device state
  *
  * Conventions: every pointer named *_dev is device memory owned by the caller (the library
@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PZ_VERSION 2
+#define PZ_VERSION 3
 
 /* packed device state: int32 words per env (structure-of-arrays) */
 #define PZ_STATE_WORDS 17
@@ -74,7 +74,9 @@ enum {
     PZ_E_BADARG = -1,    /* null pointer, n < 0, K < 1 ... */
     PZ_E_BADCONFIG = -2, /* winning_score outside [1,1023], unknown serve/dtype code */
     PZ_E_ALIGN = -3,     /* state/obs pointer not 16-byte aligned */
-    PZ_E_NODEVICE = -4   /* no sm_100 device / kernel image unusable */
+    PZ_E_NODEVICE = -4,  /* no sm_100 device / kernel image unusable */
+    PZ_E_ABI = -5        /* pz_config.struct_bytes / abi_version do not match this library: the caller's binding was
+                            written against another revision of this header (see pz_config_init) */
 };
 
 /* indices into the int64 statistics vector (all counters are += over calls) */
@@ -93,7 +95,14 @@ enum {
     PZ_STAT_TRUNCATED = 10   /* episodes cut by max_episode_frames */
 };
 
+/* Passed by pointer to every entry point that takes a configuration. The first two members are the ABI
+ * handshake: pz_config_init() fills them, and every entry point returns PZ_E_ABI — before reading anything
+ * else — unless struct_bytes == pz_config_bytes() and abi_version == pz_version(). A binding in another
+ * language (ctypes, cffi, cgo ...) that declares a stale, shorter or longer struct is therefore refused
+ * instead of being read past its end. New members are only ever appended, with a PZ_VERSION bump. */
 typedef struct pz_config {
+    uint32_t struct_bytes;           /* sizeof(pz_config) as the caller's binding declares it */
+    uint32_t abi_version;            /* PZ_VERSION the caller's binding was written against */
     int32_t winning_score;           /* pikazoo_env.py:81,102; 1..1023 */
     int32_t serve;                   /* PZ_SERVE_*; pikazoo_env.py:82,104-105 */
     int32_t is_player1_computer;     /* pikazoo_env.py:83 */
@@ -133,7 +142,11 @@ int pz_state_words(void);
 int pz_unpacked_words(void);
 size_t pz_state_bytes(int64_t n);
 const char *pz_strerror(int code);
-void pz_default_config(pz_config *cfg); /* reference defaults: ws=15, winner, no computers */
+size_t pz_config_bytes(void); /* sizeof(pz_config) in this library */
+/* Reference defaults (ws=15, serve winner, no computer players, auto-reset on) into *cfg, and the handshake
+ * members. caller_struct_bytes is sizeof() of the CALLER's declaration of pz_config (C: sizeof(pz_config);
+ * ctypes: ctypes.sizeof(Cfg)): if it differs from pz_config_bytes() nothing is written and PZ_E_ABI returned. */
+int pz_config_init(pz_config *cfg, size_t caller_struct_bytes);
 
 /* Fresh env objects, generator of env i = numpy PCG64(SeedSequence(base_seed + first_env + i)).
  * reset() has not been called. */
@@ -185,10 +198,12 @@ int pz_rollout(int32_t *state_dev, int64_t n, const pz_config *cfg, int32_t K, i
  * tables in HBM (pz_tables_bytes() bytes, allocated by the library with cudaMalloc) holding the result
  * of calculate_expected_landing_point_x_for (physics.py:643-686) and
  * expected_landing_point_x_when_power_hit (physics.py:820-884) for every ball state with
- * |y_velocity| <= PZ_TABLE_MAX_YV, built on the device by the same simulation code. They are built
- * implicitly by the first pz_step / pz_rollout with a computer player and without PZ_FLAG_NO_TABLES
- * (this synchronises `stream` once); call pz_tables_prepare beforehand when capturing CUDA graphs.
- * If the allocation fails the kernels silently use the iterative simulations. */
+ * |y_velocity| <= PZ_TABLE_MAX_YV, built on the device by the same simulation code. Build them explicitly
+ * with pz_tables_prepare (allocates pz_tables_bytes() = 1.9 GB on the current device, runs ~0.3 s of kernels
+ * and synchronises `stream`; returns 0 or the cudaError_t that prevented it — pikazoo_b200.PikaVecEnv does this
+ * in its constructor). A pz_step / pz_rollout with a computer player and without PZ_FLAG_NO_TABLES that finds
+ * them missing builds them implicitly the same way (one lock per device), except under stream capture, where
+ * — like after a failed build — the kernels run the iterative simulations instead (results identical). */
 #define PZ_TABLE_MAX_YV 100
 int pz_tables_prepare(void *stream);
 size_t pz_tables_bytes(void);

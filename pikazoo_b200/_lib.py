@@ -27,7 +27,7 @@ ACTIONS_NOOP, ACTIONS_SYNTH = 0, 1
 FLAG_NO_TABLES = 1
 FLAG_NO_L2_HINTS = 2
 FLAG_NO_PDL = 4
-VERSION = 2
+VERSION = 3
 
 STAT_NAMES = (
     "calls", "episodes", "episode_frames", "p1_wins", "p2_wins", "p1_points", "p2_points", "resets",
@@ -39,6 +39,8 @@ class PzConfig(ctypes.Structure):
     """struct pz_config (include/pikazoo_b200.h)."""
 
     _fields_ = [
+        ("struct_bytes", ctypes.c_uint32),   # ABI handshake, filled by pz_config_init
+        ("abi_version", ctypes.c_uint32),
         ("winning_score", ctypes.c_int32),
         ("serve", ctypes.c_int32),
         ("is_player1_computer", ctypes.c_int32),
@@ -60,6 +62,13 @@ class PzConfig(ctypes.Structure):
         ("obs_layout", ctypes.c_int32),
         ("obs_feature_rows", ctypes.c_int32),
     ]
+
+    def __init__(self, *args, **kw):
+        super().__init__(*args, **kw)
+        # the handshake members, so that a PzConfig built field by field is accepted; load() has checked that
+        # this declaration has the library's size
+        self.struct_bytes = ctypes.sizeof(PzConfig)
+        self.abi_version = VERSION
 
 
 class PzEpisodeIo(ctypes.Structure):
@@ -99,8 +108,9 @@ def load() -> ctypes.CDLL:
     L.pz_state_bytes.restype = ctypes.c_size_t
     L.pz_strerror.argtypes = [ctypes.c_int]
     L.pz_strerror.restype = ctypes.c_char_p
-    L.pz_default_config.argtypes = [cfgp]
-    L.pz_default_config.restype = None
+    L.pz_config_bytes.restype = ctypes.c_size_t
+    L.pz_config_init.argtypes = [cfgp, ctypes.c_size_t]
+    L.pz_config_init.restype = ctypes.c_int
     L.pz_seed.argtypes = [vp, i64, u64, u64, vp]
     L.pz_seed_array.argtypes = [vp, i64, vp, vp]
     L.pz_reset.argtypes = [vp, i64, cfgp, vp, vp]
@@ -139,7 +149,8 @@ def load() -> ctypes.CDLL:
     L.pz_policy_mlp_act.restype = ctypes.c_int
     L.pz_policy_select.argtypes = [i32]
     L.pz_policy_select.restype = ctypes.c_int
-    if L.pz_version() != VERSION or L.pz_state_words() != STATE_WORDS or L.pz_unpacked_words() != UNPACKED_WORDS:
+    if (L.pz_version() != VERSION or L.pz_state_words() != STATE_WORDS or L.pz_unpacked_words() != UNPACKED_WORDS
+            or L.pz_config_bytes() != ctypes.sizeof(PzConfig)):
         raise PikaLibraryError("libpikazoo_b200.so does not match this Python package (rebuild it)")
     _lib = L
     return L

@@ -46,7 +46,7 @@ extern "C" {
 int pz_host_create(pz_host_ctx **out, int64_t n, const pz_config *cfg, uint64_t base_seed, uint64_t first_env,
                    int32_t chunks) {
     if (!out || !cfg || n < 1) return PZ_E_BADARG;
-    if (cfg->winning_score < 1 || cfg->winning_score > 1023) return PZ_E_BADCONFIG;
+    if (int rc = pz::check_config(cfg)) return rc;  // the ABI handshake comes first
     pz_host_ctx *c = new (std::nothrow) pz_host_ctx();
     if (!c) return (int)cudaErrorMemoryAllocation;
     c->n = n;

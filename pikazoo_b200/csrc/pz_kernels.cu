@@ -263,46 +263,63 @@ __global__ void __launch_bounds__(256) pz_build_power_table_kernel(uint16_t *tab
 
 struct DeviceTables {
     uint16_t *land = nullptr, *power = nullptr;
-    int state = 0;  // 0 = not built, 1 = ready, -1 = allocation failed (iterate instead)
+    int state = 0;    // 0 = not built, 1 = ready, -1 = failed (the kernels iterate instead)
+    int error = 0;    // why: the cudaError_t of the failed allocation / build
+    std::mutex mu;    // per device: ranks-as-threads on different GPUs build concurrently
 };
 constexpr int kMaxDevices = 64;
 static DeviceTables g_tables[kMaxDevices];
-static std::mutex g_tables_mu;
 
-// Returns the current device's tables, building them on first use (synchronises `stream` once).
-static const DeviceTables *acquire_tables(cudaStream_t stream) {
+// Returns the current device's tables, building them on first use (synchronises `stream` once; under stream
+// capture nothing can be built: call pz_tables_prepare beforehand). *err receives the reason when there are none.
+static const DeviceTables *acquire_tables(cudaStream_t stream, int *err = nullptr) {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
-    std::lock_guard<std::mutex> lock(g_tables_mu);
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        if (err) *err = e0 != cudaSuccess ? (int)e0 : (int)cudaErrorInvalidDevice;
+        return nullptr;
+    }
     DeviceTables &t = g_tables[dev];
+    std::lock_guard<std::mutex> lock(t.mu);
     if (t.state == 0) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) {
+            if (err) *err = (int)cudaErrorStreamCaptureUnsupported;
+            return nullptr;  // not built and cannot be built now: this launch iterates; state stays 0
+        }
         cudaError_t e1 = cudaMalloc(&t.land, kTabLandEntries * sizeof(uint16_t));
         cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&t.power, kTabPowerEntries * sizeof(uint16_t)) : e1;
         if (e1 != cudaSuccess || e2 != cudaSuccess) {
             if (t.land) cudaFree(t.land);
             t.land = t.power = nullptr;
             t.state = -1;
+            t.error = (int)(e1 != cudaSuccess ? e1 : e2);
             cudaGetLastError();  // clear the sticky allocation error: the iterative path needs no table
         } else {
             pz_build_land_table_kernel<<<(unsigned)((kTabLandEntries + 255) / 256), 256, 0, stream>>>(t.land);
             pz_build_power_table_kernel<<<(unsigned)((kTabPowerEntries + 255) / 256), 256, 0, stream>>>(t.power);
             cudaError_t e3 = cudaStreamSynchronize(stream);
-            if (e3 != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+            if (e3 == cudaSuccess) e3 = cudaGetLastError();
+            if (e3 != cudaSuccess) {
                 cudaFree(t.land);
                 cudaFree(t.power);
                 t.land = t.power = nullptr;
                 t.state = -1;
+                t.error = (int)e3;
             } else {
                 t.state = 1;
             }
         }
     }
+    if (t.state != 1 && err) *err = t.error ? t.error : (int)cudaErrorUnknown;
     return t.state == 1 ? &t : nullptr;
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-static int check_config(const pz_config *c) {
+int check_config(const pz_config *c) {
     if (!c) return PZ_E_BADARG;
+    // ABI handshake first: nothing past the two leading words is read from a struct of another revision
+    if (c->struct_bytes != (uint32_t)sizeof(pz_config) || c->abi_version != (uint32_t)PZ_VERSION) return PZ_E_ABI;
     if (c->winning_score < 1 || c->winning_score > 1023) return PZ_E_BADCONFIG;
     if (c->serve < 0 || c->serve > 2) return PZ_E_BADCONFIG;
     if (c->action_dtype < 0 || c->action_dtype > 2) return PZ_E_BADCONFIG;
@@ -453,18 +470,27 @@ const char *pz_strerror(int code) {
         case PZ_E_BADCONFIG: return "pikazoo_b200: bad config (winning_score must be in [1,1023]; serve/dtype codes)";
         case PZ_E_ALIGN: return "pikazoo_b200: state/obs pointers must be 16-byte aligned";
         case PZ_E_NODEVICE: return "pikazoo_b200: no usable sm_100 device";
+        case PZ_E_ABI:
+            return "pikazoo_b200: pz_config.struct_bytes / abi_version do not match this library (the caller's binding "
+                   "declares another revision of struct pz_config; initialise it with pz_config_init)";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "pikazoo_b200: unknown error";
     }
 }
 
-void pz_default_config(pz_config *c) {
-    if (!c) return;
+size_t pz_config_bytes(void) { return sizeof(pz_config); }
+
+int pz_config_init(pz_config *c, size_t caller_struct_bytes) {
+    if (!c) return PZ_E_BADARG;
+    if (caller_struct_bytes != sizeof(pz_config)) return PZ_E_ABI;  // nothing is written to a struct of another size
     memset(c, 0, sizeof(*c));
+    c->struct_bytes = (uint32_t)sizeof(pz_config);
+    c->abi_version = (uint32_t)PZ_VERSION;
     c->winning_score = 15;
     c->serve = PZ_SERVE_WINNER;
     c->x_line = 216;
     c->y_line = 176;
     c->autoreset = 1;
+    return 0;
 }
 
 int pz_seed(int32_t *state_dev, int64_t n, uint64_t base_seed, uint64_t first_env, void *stream) {
@@ -545,22 +571,25 @@ int pz_rollout(int32_t *state_dev, int64_t n, const pz_config *cfg, int32_t K, i
     return launch_status();
 }
 
-int pz_tables_prepare(void *stream) { return acquire_tables((cudaStream_t)stream) ? 0 : (int)cudaErrorMemoryAllocation; }
+int pz_tables_prepare(void *stream) {
+    int err = 0;
+    return acquire_tables((cudaStream_t)stream, &err) ? 0 : err;
+}
 
 size_t pz_tables_bytes(void) { return (size_t)(kTabLandEntries + kTabPowerEntries) * sizeof(uint16_t); }
 
 int pz_tables_ready(void) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
-    std::lock_guard<std::mutex> lock(g_tables_mu);
+    std::lock_guard<std::mutex> lock(g_tables[dev].mu);
     return g_tables[dev].state == 1;
 }
 
 void pz_tables_release(void) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return;
-    std::lock_guard<std::mutex> lock(g_tables_mu);
     DeviceTables &t = g_tables[dev];
+    std::lock_guard<std::mutex> lock(t.mu);
     if (t.state == 1) {
         cudaDeviceSynchronize();
         cudaFree(t.land);
@@ -568,6 +597,7 @@ void pz_tables_release(void) {
     }
     t.land = t.power = nullptr;
     t.state = 0;
+    t.error = 0;
 }
 
 int pz_export_state(const int32_t *state_dev, int64_t n, int32_t *unpacked_dev, void *stream) {

@@ -8,6 +8,9 @@
 
 namespace pz {
 
+// 0, or PZ_E_ABI (handshake members of another revision) / PZ_E_BADCONFIG / PZ_E_BADARG (null)
+int check_config(const pz_config *cfg);
+
 // Step / reset the env range [begin, end) of a state buffer holding n envs (begin % 32 == 0).
 // actions/obs/reward/done are the base pointers of the full [n]-sized arrays.
 int launch_step(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const pz_config *cfg,

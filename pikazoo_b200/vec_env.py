@@ -227,6 +227,19 @@ class PikaVecEnv:
                 self.lib.pz_seed(self.state.data_ptr(), n, self.seed & (2**64 - 1), self.first_env, self._stream()),
                 "pz_seed",
             )
+            # The memoised trajectory tables of the computer players (1.9 GB per device, ~0.3 s to build) are made
+            # here, explicitly, so that no step() pays for them, CUDA-graph capture of step() works, and a failure
+            # is reported with its cause instead of silently falling back to the iterative simulations.
+            self.tables_ready = False
+            if self.landing_tables and (is_player1_computer or is_player2_computer):
+                rc = self.lib.pz_tables_prepare(self._stream())
+                if rc != 0:
+                    import warnings
+
+                    warnings.warn(f"landing tables unavailable ({self.lib.pz_strerror(rc).decode()}, "
+                                  f"{self.lib.pz_tables_bytes() / 1e9:.1f} GB needed): computer players run the "
+                                  "iterative simulations (identical results, slower)", RuntimeWarning, stacklevel=2)
+                self.tables_ready = rc == 0
         self.frame = 0  # calls issued so far (drives the synthetic action stream of rollout())
         self._action_shape = torch.Size((n, 2))
         self._step_args = None
@@ -275,10 +288,12 @@ class PikaVecEnv:
                                 "pass action_dtype= to the constructor")
             if actions.device != self._io_device or actions.shape != self._action_shape:
                 raise ValueError(f"actions must be a [{self.num_envs}, 2] tensor on {self._io_device}")
+            if not actions.is_contiguous():
+                # (a .contiguous() copy here would be a temporary freed while the launch is in flight, and for
+                # host_mapped a pageable one the device cannot address)
+                raise ValueError("actions must be contiguous")
             if self.host_mapped and not actions.is_pinned():
                 raise ValueError("host_mapped: actions must live in pinned host memory (tensor.pin_memory())")
-            if not actions.is_contiguous():
-                actions = actions.contiguous()
             a_ptr = actions.data_ptr()
         else:
             a_ptr = None

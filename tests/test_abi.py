@@ -30,12 +30,13 @@ def test_library_exports_every_declared_symbol(cuda_lib):
 
 
 def test_constants_and_errors(cuda_lib):
-    assert cuda_lib.pz_version() == 2
+    assert cuda_lib.pz_version() == 3
     assert cuda_lib.pz_state_words() == 17
     assert cuda_lib.pz_unpacked_words() == 53
     assert cuda_lib.pz_state_bytes(1000) == 1000 * 17 * 4
     assert b"bad config" in cuda_lib.pz_strerror(-2)
     assert cuda_lib.pz_strerror(0) == b"success"
+    assert b"struct_bytes" in cuda_lib.pz_strerror(-5)
 
 
 def test_argument_validation_without_gpu(cuda_lib):
@@ -73,10 +74,53 @@ def test_product_does_not_import_oracle():
 
 
 def test_config_struct_layout_matches_header(cuda_lib):
-    from pikazoo_b200._lib import PzConfig
+    from pikazoo_b200._lib import VERSION, PzConfig
 
     c = PzConfig()
-    cuda_lib.pz_default_config(ctypes.byref(c))
+    assert cuda_lib.pz_config_init(ctypes.byref(c), ctypes.sizeof(c)) == 0
     assert (c.winning_score, c.serve, c.x_line, c.y_line, c.autoreset) == (15, 0, 216, 176, 1)
-    assert ctypes.sizeof(PzConfig) == 8 * 4 + 8 * 8 + 8 * 4 + 8 + 2 * 4 and PzConfig.flags.offset == 108
-    assert PzConfig.normal_state_reward.offset == 128 and c.obs_dtype == 0 and c.max_episode_frames == 0
+    assert (c.struct_bytes, c.abi_version) == (ctypes.sizeof(PzConfig), VERSION)
+    assert ctypes.sizeof(PzConfig) == cuda_lib.pz_config_bytes() == 2 * 4 + 8 * 4 + 8 * 8 + 8 * 4 + 8 + 2 * 4
+    assert PzConfig.flags.offset == 116 and PzConfig.additional_reward.offset == 40
+    assert PzConfig.normal_state_reward.offset == 136 and c.obs_dtype == 0 and c.max_episode_frames == 0
+
+
+def test_abi_handshake_refuses_a_stale_struct(cuda_lib):
+    """A binding that declares another revision of struct pz_config (the documented stub was 8 bytes
+    short) is refused with PZ_E_ABI before anything else is read, and pz_config_init writes nothing to it."""
+    from pikazoo_b200 import make_config
+
+    buf = (ctypes.c_ubyte * 256)(*([0xAB] * 256))
+    cfgp = ctypes.cast(buf, ctypes.POINTER(type(make_config())))
+    for wrong in (cuda_lib.pz_config_bytes() - 8, cuda_lib.pz_config_bytes() + 8, 0):
+        assert cuda_lib.pz_config_init(cfgp, wrong) == -5
+        assert bytes(buf) == b"\xab" * 256
+    cfg = make_config()
+    for field, bad in (("struct_bytes", cfg.struct_bytes - 8), ("abi_version", cfg.abi_version - 1)):
+        c = make_config()
+        setattr(c, field, bad)
+        assert cuda_lib.pz_reset(ctypes.c_void_p(16), 4, ctypes.byref(c), None, None) == -5
+        assert cuda_lib.pz_step(ctypes.c_void_p(16), 4, ctypes.byref(c), ctypes.c_void_p(16), None, None, None, None,
+                                None) == -5
+        assert cuda_lib.pz_rollout(ctypes.c_void_p(16), 4, ctypes.byref(c), 1, 0, 0, 0, 0, None, None, None) == -5
+        ctx = ctypes.c_void_p()
+        assert cuda_lib.pz_host_create(ctypes.byref(ctx), 4, ctypes.byref(c), 0, 0, 1) == -5 and not ctx.value
+
+
+def integration_stub_source():
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    return re.search(r"```python\n(# pikazoo/env/b200_backend\.py.*?)```", text, flags=re.S).group(1)
+
+
+def test_integration_md_stub_declares_this_librarys_struct(cuda_lib):
+    """The ctypes stub INTEGRATION.md shows is parsed out of the document: its _Cfg must be the library's struct
+    (size and every member's offset = the package's own binding)."""
+    from pikazoo_b200 import _lib
+
+    block = integration_stub_source().replace('ctypes.CDLL("libpikazoo_b200.so")', f'ctypes.CDLL("{_lib.LIB_PATH}")')
+    ns = {}
+    exec(compile(block, "INTEGRATION.md", "exec"), ns)  # noqa: S102 - our own document; no compute at import
+    stub = ns["_Cfg"]
+    assert ctypes.sizeof(stub) == cuda_lib.pz_config_bytes()
+    assert [(n, getattr(stub, n).offset) for n, _ in stub._fields_] == \
+        [(n, getattr(_lib.PzConfig, n).offset) for n, _ in _lib.PzConfig._fields_]

@@ -16,9 +16,10 @@ pytestmark = pytest.mark.gpu
 
 
 def test_integration_md_stub_runs(cuda_lib):
-    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
-    block = re.search(r"```python\n(# pikazoo/env/b200_backend\.py.*?)```", text, flags=re.S).group(1)
     from pikazoo_b200 import _lib
+    from tests.test_abi import integration_stub_source
+
+    block = integration_stub_source()
 
     block = block.replace('ctypes.CDLL("libpikazoo_b200.so")', f'ctypes.CDLL("{_lib.LIB_PATH}")')
     ns = {}
