@@ -32,6 +32,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_ENV_STEP = 425  # 8 actions + 280 obs + 8 reward + 1 done + 72 state R + 56 state W
+MOVED_BYTES_PER_ENV_STEP = 361  # what the kernel moves on a frame that draws nothing: no PCG64 words
+PRE_ADVANCE_FRAMES = 2048       # frames every env is advanced (uniform device-side actions) before the warm-up, so
+                                # that the timed window is steady state: envs desynchronised over rounds and games
 ENVS_PER_GPU = 1 << 20
 WORKLOAD = ("per-step path (configs[1] scaled to 1,048,576 envs/GPU): uniform random Discrete(18) actions for both "
             "agents, winning_score=15, serve=winner, device obs/reward/done, NEXT-STEP auto-reset")
@@ -46,12 +49,21 @@ def parse_args():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--e2e-steps", type=int, default=40)
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="wall time of each CPU baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-rollout", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
     return ap.parse_args()
+
+
+def bench_config(envs_per_gpu: int, world: int) -> dict:
+    """`config` of the JSON line — the same dict, key for key, in both arms."""
+    return {"workload": WORKLOAD, "envs_per_gpu": envs_per_gpu, "total_envs": envs_per_gpu * world,
+            "parallelism": f"env-shard x{world}",
+            "state": f"steady state: every env advanced {PRE_ADVANCE_FRAMES} frames after reset before the warm-up",
+            "l2": f"inputs larger than L2: {ALGO_BYTES_PER_ENV_STEP * envs_per_gpu / 1e6:.0f} MB touched per step vs 126 MB L2",
+            "actions": "ring of 8 device-resident int32 [n,2] tensors (GPU arm) / pre-generated per thread (CPU arm)"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -112,36 +124,73 @@ def cpu_port_throughput(seconds: float):
     return value, port.cores, sample
 
 
+def python_reference(samples: int, seconds: float, warmup_seconds: float = 1.0):
+    """The UNMODIFIED Python reference on this box's host cores: one env process per core stepping the bench
+    workload (oracle/time_reference.py over the sources oracle/stage_ref.py staged under oracle/_ref/, or
+    /root/reference in the build container). Runs in a child interpreter (no CUDA context is forked).
+    Returns the child's JSON dict, or {"unavailable": why}."""
+    import subprocess
+
+    cmd = [sys.executable, "-m", "oracle.time_reference", "--json", "--workload", "bench", "--samples", str(samples),
+           "--seconds", f"{seconds:.3f}", "--warmup-seconds", f"{warmup_seconds:.3f}"]
+    try:
+        r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=samples * seconds + 120)
+        if r.returncode != 0:
+            return {"unavailable": (r.stderr.strip().splitlines() or ["exit %d" % r.returncode])[-1][:300]}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": repr(exc)[:300]}
+
+
+def cpu_baseline_block(seconds: float, py_samples: int = 1, py_seconds: float | None = None):
+    """`cpu_baseline` of the JSON line: the unmodified Python reference (kind "reference") when its sources are
+    staged, with the C port of the same path (oracle/pika_oracle.c, all host threads) beside it; the port alone
+    (kind "port") otherwise. Returns (block, per-sample values of the headline leg)."""
+    py = python_reference(py_samples, py_seconds if py_seconds is not None else seconds)
+    pv, cores, psample = cpu_port_throughput(min(seconds, 8.0))
+    port = {"value": pv, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": psample,
+            "what": "oracle/pika_oracle.c, the C restatement of the reference path (batched, no Python objects)"}
+    if "unavailable" in py:
+        block = dict(port, python_reference={"unavailable": py["unavailable"]})
+        return block, [pv]
+    w = py["bench"]
+    block = {
+        "value": w["env_steps_per_sec_total"], "unit": "env-steps/s", "cores": py["cores"], "kind": "reference",
+        "sample": (f"{py['cores']} processes (one reference env each, one per host core), {py['samples']} window(s) of "
+                   f"{py['seconds_per_sample']:.2f} s wall after warm-up: pikazoo_v0.env(winning_score=15, serve='winner'), "
+                   f"uniform random Discrete(18) actions for both agents, reset() on termination — the unmodified "
+                   f"reference sources ({py.get('reference_root')}, physics.py sha256 {py.get('physics_py_sha256_16', '?')}), "
+                   f"python {py['python']}, numpy {py['numpy']}"),
+        "per_core_mean": w["per_core_mean"],
+        "python_reference": {"value": w["env_steps_per_sec_total"], "per_core_mean": w["per_core_mean"],
+                             "cores": py["cores"]},
+        "port": port,
+    }
+    return block, w["samples_env_steps_per_sec"]
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # each "step" of this arm is a bounded sample: all host cores stepping their env batches for a fixed
-    # wall time, sized so that the K timed steps take about a minute in total; value = env-steps/sec over
-    # the K timed samples.
+    # each "step" of this arm is a bounded sample: every host core stepping its reference env for a fixed wall
+    # time, sized so that the K timed steps take about a minute in total; value = env-steps/sec, mean of the K samples
     steps = max(1, args.steps)
     warmup = max(1, args.warmup)
-    per_step_seconds = min(1.0, max(0.02, 60.0 / steps))
-    port = CpuPort()
-    for _ in range(min(warmup, max(1, int(3.0 / per_step_seconds)))):  # at most ~3 s of warm-up
-        port.sample(per_step_seconds)
-    vals = [port.sample(per_step_seconds) for _ in range(steps)]
+    per_step_seconds = min(1.0, max(0.05, 60.0 / steps))
+    block, vals = cpu_baseline_block(args.cpu_seconds, py_samples=steps, py_seconds=per_step_seconds)
     value = sum(vals) / len(vals)
-    cores = port.cores
-    sample = (f"{steps} timed samples of {per_step_seconds:.2f} s each: {cores} threads x {port.envs_per_thread} envs "
-              f"stepping the C port of the reference path (oracle/pika_oracle.c); the pure-Python reference cannot "
-              f"travel to the GPU box (DESIGN.md)")
     line = {
         "impl": "reference",
         "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": per_step_seconds * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs_per_gpu,
-                   "total_envs": args.envs_per_gpu * args.gpus, "parallelism": f"env-shard x{args.gpus}",
-                   "note": "same workload as the b200 arm; this arm steps it on the host cores of rank 0's box"},
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": bench_config(args.envs_per_gpu, args.gpus),
+        "cpu_baseline": block,
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "this arm steps the same workload on the host cores of rank 0's box; it holds as many envs as it has "
+                "cores (the reference is one env per object), not the GPU arm's batch",
     }
     print(json.dumps(line), flush=True)
 
@@ -258,6 +307,25 @@ def run_b200_arm(args):
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     ring = [torch.randint(0, 18, (n, 2), generator=gen, device=dev, dtype=torch.int32) for _ in range(R)]
 
+    def timed_launches(e, count):
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        for k_ in range(count):
+            e.step(ring[k_ % R])
+        b_.record()
+        torch.cuda.synchronize()
+        return a_.elapsed_time(b_)
+
+    # The first frames after reset() are not representative: every env is in its first serve in lock-step,
+    # nothing draws, nothing scores (5 % faster than steady state). Time that window as a variant,
+    # then advance every env PRE_ADVANCE_FRAMES frames with uniform device-side actions (K-frame rollout
+    # launches, ~60 ms) so that the timed region below runs on desynchronised envs whatever --warmup is.
+    for k in range(3):
+        env.step(ring[k % R])
+    barrier()
+    post_reset_ms = timed_launches(env, 20) / 20
+    for _ in range(PRE_ADVANCE_FRAMES // 256):
+        env.rollout(256, actions="synth", action_seed=77)
     for k in range(W):
         env.step(ring[k % R])
     barrier()
@@ -287,6 +355,69 @@ def run_b200_arm(args):
         ev[k + 1].record()
     torch.cuda.synchronize()
     per_launch_ms = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(P))
+
+    # ---- write-only HBM probe: the ceiling of a kernel that is 87 % stores (280 MB of its 322 MB per launch) ----
+    def write_probe():
+        L = _lib.load()
+        nbytes = 280 << 20
+        bufs = [torch.empty(nbytes // 4, dtype=torch.int32, device=dev) for _ in range(2)]  # 2 x 280 MB >> 126 MB L2
+        out = {"bytes_per_launch": nbytes, "what": "pz_probe_write: 128-bit streaming stores over 280 MB (two buffers "
+               "alternating), CUDA events around 40 launches; torch_zero = tensor.zero_() on the same buffers"}
+        s_ = torch.cuda.current_stream().cuda_stream
+        for name, fn in (("evict_first_gbs", lambda b_: _lib.check(L.pz_probe_write(b_.data_ptr(), nbytes, 1, s_))),
+                         ("evict_normal_gbs", lambda b_: _lib.check(L.pz_probe_write(b_.data_ptr(), nbytes, 0, s_))),
+                         ("torch_zero_gbs", lambda b_: b_.zero_())):
+            for k_ in range(4):
+                fn(bufs[k_ & 1])
+            a_, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for k_ in range(40):
+                fn(bufs[k_ & 1])
+            b2.record()
+            torch.cuda.synchronize()
+            out[name] = nbytes * 40 / (a_.elapsed_time(b2) * 1e-3) / 1e9
+        return out
+
+    try:
+        wprobe = write_probe()
+    except Exception as exc:  # noqa: BLE001
+        wprobe = {"error": repr(exc)}
+
+    # ---- N > 1: a correctness bit for the sharding itself. Every rank steps its shard of a small global batch
+    # (per-step launches with actions sliced from one global tensor, then K-frame rollouts with the counter-based
+    # actions keyed by global env) and ALSO the whole batch alone; its shard of the whole-batch state must equal
+    # its own state bit for bit, and the all-reduced statistics must equal the whole-batch statistics. ----
+    def shard_check():
+        small = 8192 * world
+        kw = dict(winning_score=3, serve="random", is_player2_computer=True)
+        mine = pikazoo_b200.make_sharded_env(small, rank, world, dev, seed=99, **kw)
+        whole = pikazoo_b200.PikaVecEnv(small, device=dev, seed=99, **kw)
+        first, count = pikazoo_b200.shard_range(small, world, rank)
+        g = torch.Generator(device=dev).manual_seed(4242)  # same seed on every rank: the same global tensor
+        mine.reset(), whole.reset()
+        for _ in range(96):
+            acts = torch.randint(0, 18, (small, 2), generator=g, device=dev, dtype=torch.int32)
+            mine.step(acts[first:first + count].contiguous())
+            whole.step(acts)
+        for _ in range(3):
+            mine.rollout(64, actions="synth", action_seed=5)
+            whole.rollout(64, actions="synth", action_seed=5)
+        state_ok = bool(torch.equal(mine.export_state(), whole.export_state()[first:first + count]))
+        summed = mine.stats.clone()
+        pikazoo_b200.allreduce_stats(summed)
+        stats_ok = bool(torch.equal(summed, whole.stats))
+        ok = torch.tensor([int(state_ok and stats_ok)], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return {"ok": bool(ok.item()), "ranks": world, "global_envs": small, "calls_per_env": 96 + 3 * 64,
+                "rank0_state_equal": state_ok, "allreduced_stats_equal_whole_batch": stats_ok,
+                "episodes_checked": int(whole.stats[1].item())}
+
+    shard = None
+    if world > 1:
+        try:
+            shard = shard_check()
+        except Exception as exc:  # noqa: BLE001
+            shard = {"ok": False, "error": repr(exc)}
 
     # episode statistics: the one collective of the design, off the step path
     stats = env.stats.clone()
@@ -379,8 +510,14 @@ def run_b200_arm(args):
                          ("main_workload_pdl_off", dict(pdl=False))):
             v = pikazoo_b200.PikaVecEnv(n, device=dev, seed=2026, first_env=first, **kw, **ENV_KW)
             v.reset()
+            for _ in range(PRE_ADVANCE_FRAMES // 256):
+                v.rollout(256, actions="synth", action_seed=77)
             variants[name] = time_steps(v, ring, steps=1000, warm=50)
             del v
+        variants["main_workload_first_frames_after_reset"] = {
+            "us_per_launch": post_reset_ms * 1e3, "env_steps_per_sec": n * world / (post_reset_ms * 1e-3),
+            "note": "20 launches right after reset() + 3 steps: all envs in their first serve in lock-step — not the "
+                    "headline (that window is steady state)"}
         shaped = ((0.1, 0.2, 0.3, 0.4, -0.1, -0.2, -0.3, -0.4), 216, 176)
         v = pikazoo_b200.PikaVecEnv(65536, device=dev, seed=13, first_env=rank * 65536, simplify_action=True,
                                     reward_by_ball_position=shaped, **ENV_KW)
@@ -539,25 +676,43 @@ def run_b200_arm(args):
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        achieved = ALGO_BYTES_PER_ENV_STEP * n / (launch_ms * 1e-3) / 1e9
+        launch_s = launch_ms * 1e-3
+        achieved = ALGO_BYTES_PER_ENV_STEP * n / launch_s / 1e9
+        traffic = traffic_note = None
+        traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(traffic_path):
+            with open(traffic_path) as f:
+                tj = json.load(f)
+            traffic, traffic_note = tj.get("pz_step_kernel_bytes_per_launch"), tj.get("source")
+        roofline = {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "kernel": "pz_step_kernel<0,I32,ENV_MAJOR>",
+            "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP, "launch_ms_avg": launch_ms,
+            "launch_ms_p50_with_event_per_launch": per_launch_ms[len(per_launch_ms) // 2],
+            # the three readings of the same launch time
+            "frac_algorithmic_425B": achieved / peak,
+            "moved_bytes_per_env_step": MOVED_BYTES_PER_ENV_STEP,
+            "achieved_moved_bytes": MOVED_BYTES_PER_ENV_STEP * n / launch_s / 1e9,
+            "frac_moved_361B": MOVED_BYTES_PER_ENV_STEP * n / launch_s / 1e9 / peak,
+            "achieved_dram_bytes": (traffic / launch_s / 1e9) if traffic else None,
+            "frac_dram_bytes": (traffic / launch_s / 1e9 / peak) if traffic else None,
+            "traffic_source": traffic_note,
+            "write_probe": wprobe,
+            "note": "frac (425 B convention, SURVEY 8(d)) can exceed 1: the convention counts the 64 B of PCG64 words "
+                    "every frame, the kernel touches them only on frames that draw and moves 361 B; of those, the "
+                    "state lines largely stay resident in the 126 MB L2 between launches, so DRAM sees `traffic`. "
+                    "`peak` is a read+write copy; the kernel is 87 % stores: see write_probe for that ceiling",
+            "peak_source": peak_src}
         line = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "total_envs": total, "parallelism": f"env-shard x{world}",
-                       "l2": f"inputs larger than L2: {ALGO_BYTES_PER_ENV_STEP * n / 1e6:.0f} MB touched per step vs 126 MB L2",
-                       "actions": f"ring of {R} device-resident int32 [n,2] tensors"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "pz_step_kernel<0>", "algorithmic_bytes_per_env_step":
-                             ALGO_BYTES_PER_ENV_STEP, "launch_ms_avg": launch_ms,
-                         "launch_ms_p50_with_event_per_launch": per_launch_ms[len(per_launch_ms) // 2],
-                         "moved_bytes_per_env_step": 361,
-                         "achieved_moved_bytes": 361 * n / (launch_ms * 1e-3) / 1e9,
-                         "note": "frac can exceed 1: the 425 B algorithmic figure counts the 64 B of PCG64 words "
-                                 "every frame, the kernel touches them only on frames that draw and moves 361 B",
-                         "peak_source": peak_src},
+            "config": bench_config(n, world),
+            "roofline": roofline,
             "e2e": e2e, "gpu_launches": K, "clocks": clocks.summary(), "episode_stats": stats_dict,
         }
+        if shard is not None:
+            line["shard_check"] = shard
         if e2e_compact:
             line["e2e_compact"] = e2e_compact
         if rollout:
@@ -565,17 +720,7 @@ def run_b200_arm(args):
         if variants:
             line["variants"] = variants
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, sample = cpu_port_throughput(args.cpu_seconds)
-            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                    "sample": sample,
-                                    "python_reference_note": "the unmodified pure-Python reference cannot travel to "
-                                    "the GPU box; measured in the build container (oracle/time_reference.py, one env "
-                                    "process per core, 8 vCPU) it steps 457 k env-steps/s in total, 57 k per core, on "
-                                    "this workload (profiles/r01_python_reference_cpu_container.json)"}
-        traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(traffic_path):
-            with open(traffic_path) as f:
-                line["roofline"]["traffic"] = json.load(f).get("pz_step_kernel_bytes_per_launch")
+            line["cpu_baseline"], _ = cpu_baseline_block(args.cpu_seconds)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

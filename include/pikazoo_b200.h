@@ -210,6 +210,11 @@ size_t pz_tables_bytes(void);
 int pz_tables_ready(void); /* 1 if the current device holds built tables */
 void pz_tables_release(void);
 
+/* Measurement aid (bench.py `roofline.write_probe`): streams 128-bit stores over `bytes` (a multiple of 16) of
+ * device memory, with the evict-first L2 policy of the step kernel's outputs if evict_first != 0 — the bandwidth
+ * ceiling of a write-dominated kernel, which the read+write copy figure of MEASURED_PEAKS.json is not. */
+int pz_probe_write(void *dst_dev, size_t bytes, int32_t evict_first, void *stream);
+
 /* packed <-> unpacked (int32 [n][53]) conversions, for checkpoints, tests and debugging */
 int pz_export_state(const int32_t *state_dev, int64_t n, int32_t *unpacked_dev, void *stream);
 int pz_import_state(int32_t *state_dev, int64_t n, const int32_t *unpacked_dev, void *stream);

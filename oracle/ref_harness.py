@@ -18,8 +18,10 @@ Only what the reference touches with ``render_mode=None`` is provided:
   pettingzoo.utils.env.ParallelEnv          wrappers/*.py
   pygame                                    pikazoo_env.py:21 (import only)
 
-``/root/reference`` does not exist on the GPU box: nothing that runs there may
-import this module (tests that use it are skipped when the path is absent).
+``/root/reference`` does not exist on the GPU box; there the harness falls back to the staged copy of
+the reference's Python sources under ``oracle/_ref/`` (``oracle/stage_ref.py``), which only
+``oracle/time_reference.py`` (bench.py's CPU legs) uses. Tests that need the reference are skipped
+when neither is present.
 
 Seeding protocol S0 (the only way to seed the unmodified reference, whose
 ``reset(seed=...)`` ignores its argument, pikazoo_env.py:149): construct, then
@@ -35,7 +37,19 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("PIKA_REFERENCE_ROOT", "/root/reference")
+def _find_reference_root() -> str:
+    """PIKA_REFERENCE_ROOT, else the read-only mount of the build container, else the byte-for-byte copy of
+    the reference's .py files that oracle/stage_ref.py stages under oracle/_ref/ (git-ignored; it travels to
+    the GPU box with the tree, where /root/reference does not exist)."""
+    env = os.environ.get("PIKA_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/pikazoo"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:

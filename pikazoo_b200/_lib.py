@@ -121,6 +121,8 @@ def load() -> ctypes.CDLL:
     L.pz_obs_elem_bytes.argtypes = [i32]
     L.pz_obs_elem_bytes.restype = ctypes.c_size_t
     L.pz_rollout.argtypes = [vp, i64, cfgp, i32, i32, u64, u64, u64, vp, vp, vp]
+    L.pz_probe_write.argtypes = [vp, ctypes.c_size_t, i32, vp]
+    L.pz_probe_write.restype = ctypes.c_int
     L.pz_export_state.argtypes = [vp, i64, vp, vp]
     L.pz_import_state.argtypes = [vp, i64, vp, vp]
     for name in ("pz_seed", "pz_seed_array", "pz_reset", "pz_reset_ex", "pz_step", "pz_step_ex", "pz_rollout",

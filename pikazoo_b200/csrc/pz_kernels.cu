@@ -225,6 +225,17 @@ __global__ void __launch_bounds__(kThreads) pz_import_kernel(int32_t *state, int
     s.u[i] = (uint32_t)o[51];
 }
 
+// ---- measurement aid: write-only HBM probe ---------------------------------------------------------
+// The per-step kernel is ~87 % stores: the read+write copy bandwidth in MEASURED_PEAKS.json is
+// not the ceiling such a kernel sees. This streams 128-bit stores with the same L2 policy as the kernel's outputs.
+__global__ void __launch_bounds__(256) pz_probe_write_kernel(uint4 *dst, size_t n16, uint64_t policy, uint32_t v) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride)
+        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%1,%1,%1}, %2;" ::"l"(dst + i), "r"(v),
+                     "l"(policy)
+                     : "memory");
+}
+
 // ---- memoised trajectory tables ------------------------------------------------------------------
 // One thread per table entry runs the very simulation the step kernels would run (same code, same
 // warp-collective form; trailing lanes of the last warp recompute the last entry and do not store).
@@ -598,6 +609,17 @@ void pz_tables_release(void) {
     t.land = t.power = nullptr;
     t.state = 0;
     t.error = 0;
+}
+
+int pz_probe_write(void *dst_dev, size_t bytes, int32_t evict_first, void *stream) {
+    if (!dst_dev || (bytes & 15u)) return PZ_E_BADARG;
+    if (!aligned16(dst_dev)) return PZ_E_ALIGN;
+    if (bytes == 0) return 0;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    pz_probe_write_kernel<<<(unsigned)(sms * 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<uint4 *>(dst_dev), bytes / 16, evict_first ? kL2EvictFirst : kL2EvictNormal, 0x5A5A5A5Au);
+    return launch_status();
 }
 
 int pz_export_state(const int32_t *state_dev, int64_t n, int32_t *unpacked_dev, void *stream) {
