@@ -157,6 +157,10 @@ int pz_seed_array(int32_t *state_dev, int64_t n, const uint64_t *seeds_dev, void
 /* reset() on every env. obs_dev: [n][2][35] of cfg->obs_dtype, or NULL. */
 int pz_reset(int32_t *state_dev, int64_t n, const pz_config *cfg, void *obs_dev, void *stream);
 
+/* raw_env._get_obs (pikazoo_env.py:576-624) of every env from the state as it stands (no frame is run):
+ * obs_dev as for pz_reset. */
+int pz_observe(int32_t *state_dev, int64_t n, const pz_config *cfg, void *obs_dev, void *stream);
+
 /* One frame of every env.
  *   actions_dev [n][2] (cfg->action_dtype), obs_dev [n][2][35] of cfg->obs_dtype (may be NULL),
  *   reward_dev [n][2] (cfg->reward_dtype, may be NULL), done_dev uint8 [n] (may be NULL),
@@ -266,6 +270,28 @@ int pz_policy_mlp_act(const void *obs_dev, int64_t n, int64_t ld, int32_t rows, 
                       int32_t hidden_rows, int32_t features, const void *w2_dev, int32_t n_actions,
                       int32_t w2_cols, uint64_t seed, uint64_t step, uint64_t first_env, void *actions_dev,
                       int32_t action_dtype, int32_t greedy, float *logits_dev, void *stream);
+
+/* K frames of `observation -> MLP policy -> sampled actions -> raw_env.step` in ONE launch (csrc/pz_rollout_policy.cu):
+ * pz_rollout with both players' actions sampled on the device from the policy above, evaluated on tcgen05 from
+ * observation tiles that never leave the SM. HBM sees the packed state once per K frames.
+ *   per frame k = 0 .. K-1 and env i:  o = observations of the state (bf16; NormalizeObservation applied iff
+ *   cfg->normalize_observation, bit-identical to pz_step's PZ_OBS_BF16 rows; policy input row 35 = 1.0 — the bias input
+ *   of policy.py's MLPPolicy —, rows 36.. = 0); logits as pz_policy_mlp_act (player_2's W1 is applied to its own
+ *   permuted view of the observation; its accumulation order differs from pz_policy_mlp_act's, so logits agree to
+ *   rounding, not bit for bit); action = pz_policy_mlp_act's tcgen05 sample with counters (seed, step0 + k,
+ *   first_env + i, agent) or the arg-max if greedy; then one pz_rollout call of the env (NEXT-STEP auto-reset: the
+ *   action sampled for a terminated env is ignored, the env is reset).
+ * cfg: no computer players (PZ_E_BADCONFIG otherwise); n_actions must be the env's action space (13 with
+ * cfg->simplify_action, else 18); hidden_rows <= 80, 36 <= features <= 48, w2_cols <= 80.
+ *   actions_out_dev  optional uint8 [K][n][2]: the sampled actions (a trajectory buffer; the parity tests replay them
+ *                    on the oracle)
+ *   logits_out_dev   optional fp32 [K][n][2][n_actions] (tests)
+ *   obs_dev          optional: the observation after the last frame (cfg->obs_dtype / obs_layout, as pz_observe)
+ *   stats_dev        optional int64 [PZ_NUM_STATS] */
+int pz_rollout_policy(int32_t *state_dev, int64_t n, const pz_config *cfg, int32_t K, const void *w1_dev,
+                      int32_t hidden_rows, int32_t features, const void *w2_dev, int32_t n_actions, int32_t w2_cols,
+                      uint64_t seed, uint64_t step0, uint64_t first_env, int32_t greedy, uint8_t *actions_out_dev,
+                      float *logits_out_dev, void *obs_dev, int64_t *stats_dev, void *stream);
 
 #ifdef __cplusplus
 }

@@ -128,7 +128,7 @@ def _p(a: np.ndarray):
 class OracleVecEnv:
     """N independent oracle envs with the product's batched NEXT-STEP auto-reset semantics."""
 
-    def __init__(self, num_envs, seed=0, autoreset=True, **cfg):
+    def __init__(self, num_envs, seed=0, autoreset=True, seeds=None, **cfg):
         self.n = int(num_envs)
         self.cfg = make_config(**cfg)
         self.autoreset = bool(autoreset)
@@ -140,6 +140,10 @@ class OracleVecEnv:
         self.episode_return = np.zeros((self.n, 2), dtype=np.float64)
         self.episode_length = np.zeros((self.n,), dtype=np.int32)
         lib().pk_vec_init(_p(self.state), self.n, int(seed))
+        if seeds is not None:  # explicit per-env seeds (a strided sample of a larger batch)
+            assert len(seeds) == self.n
+            for j, sd in enumerate(seeds):
+                lib().pk_init(_p(self.state[j]), int(sd))
 
     def reset(self):
         lib().pk_vec_reset_ex(_p(self.state), self.n, ctypes.byref(self.cfg), _p(self.obs), _p(self.episode_return),
@@ -167,6 +171,10 @@ class OracleVecEnv:
         it; float32 = astype(float32) of that; float16 = astype(float16) of the float32; "bfloat16" =
         the float32 rounded to nearest-even on its upper 16 bits, returned as uint16 bit patterns."""
         return convert_obs(self.obs, dtype, normalize=True)
+
+    def raw_obs_bf16(self):
+        """(float)value rounded to bfloat16 (PZ_OBS_BF16 without NormalizeObservation), as uint16 bit patterns."""
+        return convert_obs(self.obs, "bfloat16", normalize=False)
 
     def rollout(self, K, action_mode=0, action_seed=0, first_env=0, frame0=0, stats=None):
         if stats is None:

@@ -149,6 +149,10 @@ def load() -> ctypes.CDLL:
     # caller side: fused MLP policy (pz_policy.cu)
     L.pz_policy_mlp_act.argtypes = [vp, i64, i64, i32, vp, i32, i32, vp, i32, i32, u64, u64, u64, vp, i32, i32, vp, vp]
     L.pz_policy_mlp_act.restype = ctypes.c_int
+    L.pz_rollout_policy.argtypes = [vp, i64, cfgp, i32, vp, i32, i32, vp, i32, i32, u64, u64, u64, i32, vp, vp, vp, vp, vp]
+    L.pz_rollout_policy.restype = ctypes.c_int
+    L.pz_observe.argtypes = [vp, i64, cfgp, vp, vp]
+    L.pz_observe.restype = ctypes.c_int
     L.pz_policy_select.argtypes = [i32]
     L.pz_policy_select.restype = ctypes.c_int
     if (L.pz_version() != VERSION or L.pz_state_words() != STATE_WORDS or L.pz_unpacked_words() != UNPACKED_WORDS

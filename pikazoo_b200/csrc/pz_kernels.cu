@@ -178,6 +178,16 @@ __global__ void __launch_bounds__(kThreads) pz_reset_kernel(const __grid_constan
     if (pending) bulk_store_wait_read();
 }
 
+// raw_env._get_obs (pikazoo_env.py:576-624) of every env, from the packed state as it stands
+__global__ void __launch_bounds__(kThreads) pz_observe_kernel(const __grid_constant__ KParams P) {
+    __shared__ __align__(128) int stage[kWarps][32 * kObsRow];
+    const int warp = threadIdx.x >> 5;
+    const int64_t i = P.begin + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool pending = emit_obs_cold(P.state, P.n, i, P.end, P.obs_dtype, P.normalize, P.obs, stage[warp], P.state_policy,
+                                       P.out_policy, P.obs_layout, P.obs_rows);
+    if (pending) bulk_store_wait_read();
+}
+
 __global__ void __launch_bounds__(kThreads)
     pz_seed_kernel(int32_t *state, int64_t n, uint64_t base_seed, uint64_t first_env, const uint64_t *seeds) {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -428,6 +438,18 @@ int launch_reset(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, cons
     return launch_status();
 }
 
+int launch_observe(int32_t *state_dev, int64_t n, const pz_config *cfg, void *obs_dev, cudaStream_t stream) {
+    if (!state_dev || !obs_dev || n < 0) return PZ_E_BADARG;
+    if (int rc = check_config(cfg)) return rc;
+    if (!aligned16(state_dev) || !aligned16(obs_dev)) return PZ_E_ALIGN;
+    if (n == 0) return 0;
+    KParams P;
+    fill_params(P, state_dev, n, cfg);
+    P.obs = obs_dev;
+    pz_observe_kernel<<<grid_for(n), kThreads, 0, stream>>>(P);
+    return launch_status();
+}
+
 int launch_step(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const pz_config *cfg,
                 const void *actions_dev, void *obs_dev, void *reward_dev, uint8_t *done_dev, int64_t *stats_dev,
                 const pz_episode_io *ep, cudaStream_t st) {
@@ -534,6 +556,10 @@ size_t pz_obs_elem_bytes(int32_t obs_dtype) {
 
 int pz_reset(int32_t *state_dev, int64_t n, const pz_config *cfg, void *obs_dev, void *stream) {
     return pz::launch_reset(state_dev, n, 0, n, cfg, obs_dev, nullptr, (cudaStream_t)stream);
+}
+
+int pz_observe(int32_t *state_dev, int64_t n, const pz_config *cfg, void *obs_dev, void *stream) {
+    return pz::launch_observe(state_dev, n, cfg, obs_dev, (cudaStream_t)stream);
 }
 
 int pz_reset_ex(int32_t *state_dev, int64_t n, const pz_config *cfg, void *obs_dev, const pz_episode_io *episode,

@@ -19,4 +19,7 @@ int launch_step(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const
 int launch_reset(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const pz_config *cfg, void *obs_dev,
                  const pz_episode_io *episode, cudaStream_t stream);
 
+// The observations of the state as it stands (obs_dev as pz_reset's).
+int launch_observe(int32_t *state_dev, int64_t n, const pz_config *cfg, void *obs_dev, cudaStream_t stream);
+
 }  // namespace pz

@@ -231,3 +231,44 @@ def policy_rollout(env: PikaVecEnv, policy: Callable[[torch.Tensor], torch.Tenso
         if on_step is not None:
             on_step(t, actions, obs, reward, done)
     return obs
+
+
+@torch.no_grad()
+def rollout_fused(env: PikaVecEnv, policy: MLPPolicy, K: int, seed: int = 0, step0: Optional[int] = None,
+                  greedy: bool = False, actions_out: Optional[torch.Tensor] = None,
+                  logits_out: Optional[torch.Tensor] = None, write_obs: bool = False):
+    """K iterations of obs -> policy -> env.step in ONE launch (csrc/pz_rollout_policy.cu): the env, its random
+    stream, the observation tile, the hidden activations and the logits stay on the SM for all K frames; both
+    layers run on tcgen05 with the accumulators in TMEM. Same sampler and counters as `FusedActor` (frame k of the
+    launch uses step0 + k; step0 defaults to env.frame), auto-reset as `PikaVecEnv.rollout`. The observation the
+    policy sees is the env's bf16 row (normalised iff the env was built with normalize_observation=True), whatever
+    obs_dtype / obs_layout the env's own output buffer has.
+
+    actions_out: optional uint8 [K, N, 2] receiving the sampled actions (a trajectory buffer; the tests replay them
+    on the oracle); logits_out: optional float32 [K, N, 2, n_actions]; write_obs: also write the observation after
+    the last frame into env.obs. Returns env.obs if write_obs else None."""
+    if env.host_mapped:
+        raise ValueError("rollout_fused needs device-resident env buffers")
+    if policy.w1.dtype != torch.bfloat16:
+        raise TypeError("rollout_fused needs bfloat16 parameters")
+    n = env.num_envs
+    K = int(K)
+    if actions_out is not None and not (actions_out.dtype == torch.uint8 and actions_out.is_contiguous()
+                                        and tuple(actions_out.shape) == (K, n, 2) and actions_out.device == env.device):
+        raise ValueError("actions_out must be a contiguous uint8 [K, N, 2] tensor on the env's device")
+    if logits_out is not None and not (logits_out.dtype == torch.float32 and logits_out.is_contiguous()
+                                       and tuple(logits_out.shape) == (K, n, 2, policy.n_actions)
+                                       and logits_out.device == env.device):
+        raise ValueError("logits_out must be a contiguous float32 [K, N, 2, n_actions] tensor on the env's device")
+    w1, w2 = policy.w1.detach().contiguous(), policy.w2.detach().contiguous()
+    step0 = env.frame if step0 is None else int(step0)
+    with torch.cuda.device(env.device):
+        _lib.check(_lib.load().pz_rollout_policy(
+            env.state.data_ptr(), n, env._cfg_ref(), K, w1.data_ptr(), w1.shape[1], w1.shape[2], w2.data_ptr(),
+            w2.shape[1], w2.shape[2], int(seed) & (2**64 - 1), step0 & (2**64 - 1), env.first_env, 1 if greedy else 0,
+            actions_out.data_ptr() if actions_out is not None else None,
+            logits_out.data_ptr() if logits_out is not None else None,
+            env.obs.data_ptr() if write_obs else None, env._stats_ptr(),
+            torch.cuda.current_stream(env.device).cuda_stream), "pz_rollout_policy")
+    env.frame += K
+    return env.obs if write_obs else None
