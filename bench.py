@@ -633,7 +633,41 @@ def run_b200_arm(args):
             "of_which_policy_kernel_us": tc_us, "policy_kernel_us_mma_sync_implementation": mma_us,
             "note": "policy = pz_policy_mlp_act (tcgen05.mma, tiles by TMA, accumulators and hidden activations in "
                     "TMEM, one pass over the 160 B of observations per env)"}
-        del v, pol, actor
+        del v, actor
+        # and the whole loop in ONE launch per K frames (pz_rollout_policy): env, random stream, observation tile,
+        # hidden activations and logits stay on the SM; HBM sees the packed state once per K frames
+        from pikazoo_b200.policy import rollout_fused
+
+        v = pikazoo_b200.PikaVecEnv(n5, device=dev, seed=5, first_env=rank * n5, winning_score=5, serve="random",
+                                    obs_dtype=torch.bfloat16, normalize_observation=True, action_dtype=torch.uint8,
+                                    obs_layout="feature_major", obs_feature_rows=40)
+        v.reset()
+        for _ in range(2):
+            rollout_fused(v, pol, 64, seed=1)
+        barrier()
+        a.record()
+        for _ in range(5):
+            rollout_fused(v, pol, 64, seed=1)
+        b.record()
+        torch.cuda.synchronize()
+        tk = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+        acts = torch.empty((64, n5, 2), dtype=torch.uint8, device=dev)
+        rollout_fused(v, pol, 64, seed=1, actions_out=acts)
+        a.record()
+        for _ in range(3):
+            rollout_fused(v, pol, 64, seed=1, actions_out=acts)
+        b.record()
+        torch.cuda.synchronize()
+        variants["configs[4]_rollout_policy_K64_2M_envs_per_gpu"] = {
+            "ms_per_launch": float(tk.item()) / 5, "us_per_frame": float(tk.item()) / 5 / 64 * 1e3,
+            "env_steps_per_sec": n5 * world * 64 * 5 / (float(tk.item()) * 1e-3),
+            "env_steps_per_sec_with_action_export": n5 * 64 * 3 / (a.elapsed_time(b) * 1e-3) * world,
+            "hbm_bytes_per_env_frame": (2 * 68 + 0) / 64,
+            "note": "pz_rollout_policy: K = 64 frames of obs -> MLP policy (tcgen05, TMEM) -> sample -> step per launch; "
+                    "the per-GPU figure with action export is rank 0's"}
+        del v, pol, acts
         return variants
 
     variants = None

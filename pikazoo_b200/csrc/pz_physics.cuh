@@ -588,15 +588,15 @@ __device__ __forceinline__ bool ball_player(Env &e, Ctx &d, const Input &in) {
 // raw_env.step (pikazoo_env.py:175-240) for an env that has not terminated. keys1/keys2 are the
 // decoded key bits. AI_MASK bit I = player I+1 is a computer. Warp-collective over `mask` when
 // AI_MASK != 0. Returns player_1's base reward (-1, 0, +1).
+// The same with the two players' inputs already decoded (get_input has run: it only touches
+// power_hit_key_is_down_previous, which the new-round block below does not, so the order is immaterial).
 template <int AI_MASK, class Ctx>
-__device__ __forceinline__ int step_frame(unsigned mask, Env &e, Ctx &d, const StepCfg &c, uint32_t keys1,
-                                          uint32_t keys2, int *scratch) {
+__device__ __forceinline__ int step_frame_inputs(unsigned mask, Env &e, Ctx &d, const StepCfg &c, Input in1, Input in2,
+                                                 int *scratch) {
     if (e.round_ended) {  // :176-180 (game_ended is false here)
         new_round(e, d, c);
         e.round_ended = 0;
     }
-    Input in1 = get_input(e.p[0], keys1);  // also runs for computer players (:183-184)
-    Input in2 = get_input(e.p[1], keys2);
 
     // physics_engine, physics.py:280-337
     // The real ball update differs from one iteration of the landing simulation only on the ground
@@ -638,6 +638,29 @@ __device__ __forceinline__ int step_frame(unsigned mask, Env &e, Ctx &d, const S
     }
     e.ep_frames += 1;
     return e.round_ended ? (e.p2serve ? -1 : 1) : 0;  // :217-223
+}
+
+template <int AI_MASK, class Ctx>
+__device__ __forceinline__ int step_frame(unsigned mask, Env &e, Ctx &d, const StepCfg &c, uint32_t keys1,
+                                          uint32_t keys2, int *scratch) {
+    const Input in1 = get_input(e.p[0], keys1);  // also runs for computer players (:183-184)
+    const Input in2 = get_input(e.p[1], keys2);
+    return step_frame_inputs<AI_MASK>(mask, e, d, c, in1, in2, scratch);
+}
+
+// get_input from a pre-decoded action: (x_direction + 1) | (y_direction + 1) << 2 | power key << 4
+__host__ __device__ constexpr uint32_t pack_input(uint32_t keys) {
+    return (uint32_t)(((keys & kL) ? -1 : ((keys & kR) ? 1 : 0)) + 1) |
+           ((uint32_t)(((keys & kU) ? -1 : ((keys & kD) ? 1 : 0)) + 1) << 2) | ((keys & kP) ? 16u : 0u);
+}
+__device__ __forceinline__ Input input_from_packed(Player &p, uint32_t q) {
+    Input in;
+    in.xdir = (int)(q & 3u) - 1;
+    in.ydir = (int)((q >> 2) & 3u) - 1;
+    const int down = (int)(q >> 4);
+    in.power = down & (p.keyprev ^ 1);
+    p.keyprev = down;
+    return in;
 }
 
 // raw_env._get_obs, pikazoo_env.py:576-624: the 35 distinct values (p1 block 13, p2 block 13,

@@ -111,9 +111,21 @@ __device__ __forceinline__ int sample_inverse_cdf(const float (&logit)[N], int n
     }
     const float target = uniform_from_counter(agent_base + 0x9E3779B9u) * acc;
     int action = 0;
+#ifdef PZ_HOST_EMULATION
 #pragma unroll
     for (int j = 0; j < N - 1; j++)
         if (j < n_actions - 1) action += (c[j] <= target) ? 1 : 0;
+#else
+    // one FSET (all-ones when true) per boundary and one three-input add per two of them, instead of a
+    // compare / select / add triple each
+#pragma unroll
+    for (int j = 0; j < N - 1; j++)
+        if (j < n_actions - 1) {
+            int m;
+            asm("set.le.s32.f32 %0, %1, %2;" : "=r"(m) : "f"(c[j]), "f"(target));
+            action -= m;
+        }
+#endif
     return action;  // NaN logits: every comparison is false, action 0
 }
 

@@ -59,22 +59,30 @@ using pzp::tc::tmem_ld_wait;
 using pzp::tc::tmem_st8;
 using pzp::tc::tmem_st_wait;
 
+// Tiles in flight per SM. Measured on B200, configs[4] (2 M envs, K = 64): 3 groups 18.1 G env-steps/s (every group its
+// own slot, 170 registers), 4: 20.8, 5: 21.9 (96 registers, no spills), 6: 20.4 (80 registers, 420 B of spills).
 #ifndef PZ_RP_GROUPS
-#define PZ_RP_GROUPS 6
+#define PZ_RP_GROUPS 5
+#endif
+#ifndef PZ_RP_BACKOFF_NS
+#define PZ_RP_BACKOFF_NS 100  // sleep between polls of the MMA barrier: the kernel is bound by instruction issue
 #endif
 constexpr int kGroups = PZ_RP_GROUPS;  // tiles in flight per SM
 constexpr int kGroupThreads = 128;
 constexpr int kThreads = kGroups * kGroupThreads;
 constexpr int kTileEnvs = 128;
 constexpr int kKP = PZ_POLICY_MAX_FEATURES;  // 48 = 3 k-steps of 16
-constexpr int kHP = PZ_POLICY_MAX_HIDDEN;    // 80 per agent; N of layer 1 = 160, 5 k-steps of layer 2
+#ifndef PZ_RP_HIDDEN_PAD
+#define PZ_RP_HIDDEN_PAD PZ_POLICY_MAX_HIDDEN
+#endif
+constexpr int kHP = PZ_RP_HIDDEN_PAD;        // 80 per agent; N of layer 1 = 160, 5 k-steps of layer 2
 constexpr int kAP = 32;                      // N of layer 2 per agent
-constexpr int kSlots = 3;
+constexpr int kSlots = 512 / (2 * kHP);  // 3
 constexpr uint32_t kSlotCols = 2 * kHP;  // D1 0..159 | H 0..79 (in place) | D2 of agent a at 80 + 32 a
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColD2 = kHP;
 static_assert(kSlots * kSlotCols <= kTmemCols && kHP + 2 * kAP <= 2 * kHP, "TMEM columns");
-static_assert(2 * kGroups + 1 <= 16, "named barriers");
+static_assert(2 * kGroups + 1 <= 16, "named barriers");  // (a timing experiment with 4 slots of 128 columns gained 3 %)
 
 // shared memory (bytes). Canonical no-swizzle K-major layouts, 8 x 16-byte core matrices:
 //   X  (A): element (env m, feature k)       at (k / 8) * 2048 + m * 16 + (k % 8) * 2
@@ -89,8 +97,8 @@ constexpr int kLutPX = 0, kLutPY = kLutPX + 512, kLutPYV = kLutPY + 256, kLutDiv
               kLutBXV = kLutX432 + 512, kLutEntries = kLutBXV + 64;
 constexpr int kOffW1 = 0, kOffW2 = kOffW1 + kW1Bytes, kOffX = kOffW2 + 2 * kW2Agent, kOffLut = kOffX + kGroups * kXTile,
               kOffBar = (kOffLut + 2 * kLutEntries + 15) / 16 * 16, kOffSlot = kOffBar + 8 * kGroups,
-              kOffMask = kOffSlot + 4 * kGroups, kOffTmem = kOffMask + 4;
-constexpr size_t kSmemBytes = kOffTmem + 4;
+              kOffMask = kOffSlot + 4 * kGroups, kOffTmem = kOffMask + 4, kOffAct = kOffTmem + 4;  // [2][32] uint32
+constexpr size_t kSmemBytes = kOffAct + 2 * 32 * 4;
 
 struct Params {
     int32_t *state;
@@ -198,6 +206,16 @@ __global__ void __launch_bounds__(kThreads, 1) pz_rollout_policy_kernel(const __
         fill_table<28>(lut + kLutX432, 512, 0, nz);
         fill_table<32>(lut + kLutBXV, 64, 32, nz);
     }
+    if (tid < 64) {  // action -> pre-decoded input of player tid / 32 (action_key_map, SimplifyAction folded in)
+        const int a = tid & 31;
+        bool bad;
+        uint32_t keys;
+        if (NA == 13)
+            keys = tid < 32 ? decode_keys<0, true>(a, bad) : decode_keys<1, true>(a, bad);
+        else
+            keys = tid < 32 ? decode_keys<0, false>(a, bad) : decode_keys<1, false>(a, bad);
+        reinterpret_cast<uint32_t *>(smem + kOffAct)[tid] = pack_input(keys);
+    }
     __syncthreads();
     {
         // W1: both agents stacked along N; player_2's columns permuted into player_1's feature order
@@ -206,12 +224,12 @@ __global__ void __launch_bounds__(kThreads, 1) pz_rollout_policy_kernel(const __
         for (int i = tid; i < 2 * P.h1 * P.k1; i += kThreads) {
             const int a = i / (P.h1 * P.k1), rem = i - a * (P.h1 * P.k1), n = rem / P.k1, k = rem - n * P.k1;
             const int kk = (a == 1 && k < 26) ? (k < 13 ? k + 13 : k - 13) : k, row = a * kHP + n;
-            w1s[((kk >> 3) * kW1KGroup + (row >> 3) * 128 + (row & 7) * 16 + (kk & 7) * 2) >> 1] = P.w1[i];
+            if (n < kHP) w1s[((kk >> 3) * kW1KGroup + (row >> 3) * 128 + (row & 7) * 16 + (kk & 7) * 2) >> 1] = P.w1[i];
         }
         __nv_bfloat16 *w2s = reinterpret_cast<__nv_bfloat16 *>(smem + kOffW2);
         for (int i = tid; i < 2 * NA * P.k2; i += kThreads) {
             const int a = i / (NA * P.k2), rem = i - a * (NA * P.k2), n = rem / P.k2, k = rem - n * P.k2;
-            w2s[(a * kW2Agent + (k >> 3) * kW2KGroup + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) >> 1] = P.w2[i];
+            if (k < kHP) w2s[(a * kW2Agent + (k >> 3) * kW2KGroup + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) >> 1] = P.w2[i];
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -287,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) pz_rollout_policy_kernel(const __
                 mma_commit(bar);
             }
             const uint32_t nbase = P.greedy ? 0u : pzp::noise_base(P.seed, P.step0 + (uint64_t)k, genv);
-            mbar_wait(bar, phase);
+            mbar_wait<PZ_RP_BACKOFF_NS>(bar, phase);
             phase ^= 1u;
             tc_fence_after();
             // ---- relu, round to bf16, back into TMEM as the A operands of layer 2 (H column j = hidden 2j, 2j+1)
@@ -320,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) pz_rollout_policy_kernel(const __
                                smem_desc(s_base + kOffW2 + a * kW2Agent + j * 2 * kW2KGroup, kW2KGroup, 128), kIdesc2, j > 0);
                 mma_commit(bar);
             }
-            mbar_wait(bar, phase);
+            mbar_wait<PZ_RP_BACKOFF_NS>(bar, phase);
             phase ^= 1u;
             tc_fence_after();
             // ---- both agents' logits into registers, then the slot goes back to the pool
@@ -385,16 +403,10 @@ __global__ void __launch_bounds__(kThreads, 1) pz_rollout_policy_kernel(const __
             // ---- one call of the env (pz_rollout semantics: auto-reset always on)
             const bool over = e.game_ended || (P.max_frames > 0 && e.ep_frames >= P.max_frames);
             if (valid && !over) {
-                bool b1, b2;
-                uint32_t k1, k2;
-                if (NA == 13) {
-                    k1 = decode_keys<0, true>(act[0], b1);
-                    k2 = decode_keys<1, true>(act[1], b2);
-                } else {
-                    k1 = decode_keys<0, false>(act[0], b1);
-                    k2 = decode_keys<1, false>(act[1], b2);
-                }
-                step_frame<0>(0xFFFFFFFFu, e, d, P.cfg, k1, k2, nullptr);
+                const uint32_t *acttab = reinterpret_cast<const uint32_t *>(smem + kOffAct);
+                const Input in1 = input_from_packed(e.p[0], acttab[act[0]]);
+                const Input in2 = input_from_packed(e.p[1], acttab[32 + act[1]]);
+                step_frame_inputs<0>(0xFFFFFFFFu, e, d, P.cfg, in1, in2, nullptr);
                 if (e.game_ended) {
                     st_ep += 1;
                     st_frames += (unsigned)e.ep_frames;
@@ -475,7 +487,7 @@ extern "C" int pz_rollout_policy(int32_t *state_dev, int64_t n, const pz_config 
     if (int rc = pz::check_config(cfg)) return rc;
     if (cfg->is_player1_computer || cfg->is_player2_computer) return PZ_E_BADCONFIG;  // the policy plays both sides
     if (n_actions != (cfg->simplify_action ? 13 : 18)) return PZ_E_BADARG;           // the env's action space
-    if (hidden_rows < 1 || hidden_rows > kHP || features < 36 || features > kKP || w2_cols < 1 || w2_cols > kHP)
+    if (hidden_rows < 1 || hidden_rows > PZ_POLICY_MAX_HIDDEN || features < 36 || features > kKP || w2_cols < 1 || w2_cols > PZ_POLICY_MAX_HIDDEN)
         return PZ_E_BADARG;
     if ((reinterpret_cast<uintptr_t>(state_dev) & 15u) || (reinterpret_cast<uintptr_t>(obs_dev) & 15u)) return PZ_E_ALIGN;
     if (n == 0) return 0;

@@ -51,6 +51,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // Bounded: a wrong descriptor must end in a launch failure, not in a hung device. try_wait suspends the thread up to
 // the hinted time before it returns (shorter hints and plain test_wait polling measured the same); a wait that has
 // polled 64 times starts watching the wall clock and traps after two seconds.
+template <int BACKOFF_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     unsigned long long t0 = 0;
@@ -60,6 +61,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity), "r"(0x989680u)
             : "memory");
+        if (BACKOFF_NS > 0 && !done) __nanosleep(BACKOFF_NS);  // issue-bound callers: give the slots to other warps
         if (!done && spins >= 64) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
