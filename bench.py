@@ -425,48 +425,68 @@ def run_b200_arm(args):
     stats_dict = {name: int(stats[i]) for i, name in enumerate(_lib.STAT_NAMES)}
 
     # ---- e2e: host buffers through the C ABI (pz_host_step): H2D actions + D2H obs/reward/done ----
-    def host_e2e(obs_dtype, act_dtype, label):
+    def host_e2e(obs_dtype, act_dtype, label, compact=False):
         L = _lib.load()
-        cfg = pikazoo_b200.make_config(obs_dtype=obs_dtype, action_dtype=act_dtype, **ENV_KW)
+        cfg = pikazoo_b200.make_config(obs_dtype=obs_dtype, action_dtype=act_dtype,
+                                       obs_layout="shared" if compact else "env_major", **ENV_KW)
         ctx = ctypes.c_void_p()
         first, _ = pikazoo_b200.shard_range(total, world, rank)
         _lib.check(L.pz_host_create(ctypes.byref(ctx), n, ctypes.byref(cfg), 2026, first, 8), "pz_host_create")
         h_act = [torch.randint(0, 18, (n, 2), dtype=act_dtype).pin_memory() for _ in range(2)]
-        h_obs = torch.empty((n, 2, 35), dtype=obs_dtype).pin_memory()
-        h_rew = torch.empty((n, 2), dtype=torch.float32).pin_memory()
-        h_done = torch.empty((n,), dtype=torch.uint8).pin_memory()
+        if compact:  # player_1's int16 row (player_2's is a permutation of it) + one status byte per env
+            h_obs = torch.empty((n, 35), dtype=obs_dtype).pin_memory()
+            h_status = torch.empty((n,), dtype=torch.uint8).pin_memory()
+            h_rew = h_done = None
+
+            def step(k):
+                _lib.check(L.pz_host_step_begin(ctx, h_act[k % 2].data_ptr(), h_obs.data_ptr(), None, None,
+                                                h_status.data_ptr()), "pz_host_step_begin")
+                _lib.check(L.pz_host_step_end(ctx), "pz_host_step_end")
+
+            d2h = n * (35 * h_obs.element_size() + 1)
+        else:
+            h_obs = torch.empty((n, 2, 35), dtype=obs_dtype).pin_memory()
+            h_rew = torch.empty((n, 2), dtype=torch.float32).pin_memory()
+            h_done = torch.empty((n,), dtype=torch.uint8).pin_memory()
+
+            def step(k):
+                _lib.check(L.pz_host_step(ctx, h_act[k % 2].data_ptr(), h_obs.data_ptr(), h_rew.data_ptr(),
+                                          h_done.data_ptr()), "pz_host_step")
+
+            d2h = n * (70 * h_obs.element_size() + 8 + 1)
         _lib.check(L.pz_host_reset(ctx, h_obs.data_ptr()), "pz_host_reset")
         E = max(1, args.e2e_steps)
         for k in range(3):
-            _lib.check(L.pz_host_step(ctx, h_act[k % 2].data_ptr(), h_obs.data_ptr(), h_rew.data_ptr(),
-                                      h_done.data_ptr()), "pz_host_step")
+            step(k)
         barrier()
         t0 = time.perf_counter()
         for k in range(E):
-            _lib.check(L.pz_host_step(ctx, h_act[k % 2].data_ptr(), h_obs.data_ptr(), h_rew.data_ptr(),
-                                      h_done.data_ptr()), "pz_host_step")
+            step(k)
         torch.cuda.synchronize()
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         L.pz_host_destroy(ctx)
-        h2d, d2h = n * 2 * h_act[0].element_size(), n * (70 * h_obs.element_size() + 8 + 1)
+        h2d = n * 2 * h_act[0].element_size()
         return {
             "value": total * E / float(te.item()), "unit": "env-steps/s",
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             # what bounds this number: the link, per GPU (PCIe Gen5 x16 delivers ~55 GB/s device-to-host)
             "pcie_gbs_per_gpu": (h2d + d2h) * E / float(te.item()) / 1e9,
             "steps": E, "dtypes": label,
-            "api": "pz_host_step (C ABI, pinned host buffers, 8 chunks on 8 streams; host-blocking call timed "
-                   "with perf_counter, max over ranks)",
+            "api": ("pz_host_step_begin / pz_host_step_end" if compact else "pz_host_step") +
+                   " (C ABI, pinned host buffers, 8 chunks on 8 streams; timed with perf_counter, max over ranks)",
         }
 
     e2e = e2e_compact = None
     if not args.no_e2e:
-        e2e = host_e2e(torch.int32, torch.int32, "obs int32 (the reference's declared dtype), actions int32")
-        # same call with the lossless compact API dtypes: half the PCIe bytes per env-step
+        e2e = host_e2e(torch.int32, torch.int32, "obs int32 [n,2,35] (the reference's declared dtype), actions int32, "
+                       "reward float32 [n,2], done uint8")
+        # the same information in a quarter of the bytes: player_1's int16 row (player_2's observation is a block
+        # permutation of it, pikazoo_env.py:585-586), one status byte (reward, terminated, truncated), uint8 actions
         try:
-            e2e_compact = host_e2e(torch.int16, torch.uint8, "obs int16, actions uint8 (lossless)")
+            e2e_compact = host_e2e(torch.int16, torch.uint8, "obs int16 [n,35] shared rows, status uint8 [n], actions "
+                                   "uint8 (lossless: 73 B per env-step instead of 305 B)", compact=True)
         except Exception as exc:  # noqa: BLE001
             e2e_compact = {"error": repr(exc)}
 

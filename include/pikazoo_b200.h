@@ -63,8 +63,14 @@ enum { PZ_OBS_I32 = 0, PZ_OBS_I16 = 1, PZ_OBS_F32 = 2, PZ_OBS_F16 = 3, PZ_OBS_BF
  *                 ((a * obs_feature_rows) + k) * n + i — the layout a device-side policy wants (every
  *                 feature a contiguous vector over envs: GEMM operands with leading dimension n, no
  *                 transposing pass). Rows >= 35 (padding up to a multiple of 8 for tensor-core GEMMs) are
- *                 never written; zero them once. Device pointers only (not pz_host_*). */
-enum { PZ_LAYOUT_ENV_MAJOR = 0, PZ_LAYOUT_FEATURE_MAJOR = 1 };
+ *                 never written; zero them once. Device pointers only (not pz_host_*).
+ *   ENV_MAJOR_SHARED [n][35], PZ_OBS_I32 / PZ_OBS_I16 only: player_1's row alone. player_2's observation holds the
+ *                 same 35 values with the two player blocks swapped (pikazoo_env.py:585-586):
+ *                 obs_p2[k] = row[pz_obs_player2_index(k)] = row[k + 13] (k < 13), row[k - 13] (13 <= k < 26), row[k].
+ *                 As int16 this is 70 B per env instead of the 280 B of int32 [n][2][35] with nothing lost — the
+ *                 format for callers behind PCIe (pz_host_*). */
+enum { PZ_LAYOUT_ENV_MAJOR = 0, PZ_LAYOUT_FEATURE_MAJOR = 1, PZ_LAYOUT_ENV_MAJOR_SHARED = 2 };
+int pz_obs_player2_index(int k); /* -1 outside [0, 35) */
 /* RewardInNormalState composition order relative to RewardByBallPosition */
 enum { PZ_RINS_OFF = 0, PZ_RINS_OUTER = 1 /* RewardInNormalState(RewardByBallPosition(env)) */,
        PZ_RINS_INNER = 2 /* RewardByBallPosition(RewardInNormalState(env)) */ };
@@ -182,6 +188,9 @@ typedef struct pz_episode_io {
     double *episode_return_dev;
     int32_t *episode_length_dev;
     uint8_t *truncated_dev;
+    uint8_t *status_dev; /* uint8 [n], out: (player_1's BASE reward + 1) | terminated << 2 | truncated << 3 — reward,
+                            done and truncation of an unshaped env in one byte (player_2's reward is the negative);
+                            on reset / frozen calls the reward field is 1 (reward 0) */
 } pz_episode_io;
 int pz_reset_ex(int32_t *state_dev, int64_t n, const pz_config *cfg, void *obs_dev, const pz_episode_io *episode,
                 void *stream); /* pz_reset that also zeroes episode_return_dev / episode_length_dev */
@@ -236,6 +245,15 @@ int pz_host_create(pz_host_ctx **out, int64_t n, const pz_config *cfg, uint64_t 
 int pz_host_reset(pz_host_ctx *ctx, void *obs_host);
 int pz_host_step(pz_host_ctx *ctx, const void *actions_host, void *obs_host, void *reward_host,
                  uint8_t *done_host);
+/* The same in two halves: _begin enqueues the copies and launches of every chunk and returns at once (the caller's
+ * thread is free while PCIe and the GPU work), _end waits for them; the host buffers must stay valid and untouched
+ * in between, and no other pz_host_* call on the context is allowed there (PZ_E_BADARG).
+ * status_host (optional, uint8 [n]): pz_episode_io.status_dev — reward, terminated and truncated of an unshaped env
+ * in ONE byte. With cfg->obs_layout = PZ_LAYOUT_ENV_MAJOR_SHARED, obs_dtype = PZ_OBS_I16, action_dtype = PZ_ACT_U8,
+ * reward_host = done_host = NULL a step moves 73 B per env over the link instead of 305 B, with nothing lost. */
+int pz_host_step_begin(pz_host_ctx *ctx, const void *actions_host, void *obs_host, void *reward_host,
+                       uint8_t *done_host, uint8_t *status_host);
+int pz_host_step_end(pz_host_ctx *ctx);
 size_t pz_obs_elem_bytes(int32_t obs_dtype); /* 0 for an unknown code */
 int pz_host_stats(pz_host_ctx *ctx, int64_t stats_host[PZ_NUM_STATS]);
 int32_t *pz_host_state_dev(pz_host_ctx *ctx);

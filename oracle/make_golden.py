@@ -176,8 +176,34 @@ def run_session(args):
     }
 
 
+def run_orders(out_path):
+    """Wrapper stacks in orders the fused kernel options do not cover (oracle/wrapper_orders.py): the reference's
+    own wrapper classes, stacked as listed, played with seeded actions -> tests/golden/wrapper_orders.json."""
+    from oracle import wrapper_orders as wo
+
+    pikazoo_v0, W = rh.load_reference()
+    out = {"generator": "oracle/make_golden.py --orders", "reference": "helpingstar/pika-zoo @ /root/reference "
+           "(unmodified), numpy " + np.__version__, "env": wo.ENV_KW, "action_seed": wo.ACTION_SEED, "stacks": {}}
+    for name, stack in wo.STACKS.items():
+        sessions = []
+        for seed in wo.SEEDS:
+            raw = pikazoo_v0.env(**wo.ENV_KW)
+            raw.np_random.bit_generator.state = np.random.PCG64(int(seed)).state  # protocol S0
+            env = wo.build_stack(raw, W, stack)
+            n_actions = env.action_space("player_1").n
+            res = wo.run_session(env, n_actions, lambda f, a: synth_action(wo.ACTION_SEED, seed, f, a, n_actions))
+            sessions.append(dict(seed=seed, **res))
+        out["stacks"][name] = {"stack": [list(map(lambda v: list(v) if isinstance(v, tuple) else v, item))
+                                         for item in stack], "sessions": sessions}
+        print(name, [len(s["episodes"]) for s in sessions], [s["calls"] for s in sessions], flush=True)
+    with open(out_path, "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    print(f"wrote {out_path}: {os.path.getsize(out_path) / 1024:.0f} KiB")
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--orders", action="store_true", help="odd wrapper orders -> tests/golden/wrapper_orders.json")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--wrappers", action="store_true", help="the wrapper-stack groups -> tests/golden/wrappers.json")
     ap.add_argument("--out", default=None)
@@ -186,6 +212,9 @@ def main():
     if not rh.reference_available():
         raise SystemExit("reference not present; golden fixtures can only be generated in the build container")
     po.build()
+    if a.orders:
+        run_orders(a.out or os.path.join(_ROOT, "tests", "golden", "wrapper_orders.json"))
+        return
     groups = GROUPS_WRAPPERS if a.wrappers else (GROUPS_QUICK if a.quick else GROUPS_FULL)
     if a.out is None:
         a.out = os.path.join(_ROOT, "tests", "golden", "wrappers.json" if a.wrappers else "sessions.json")

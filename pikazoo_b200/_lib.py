@@ -22,7 +22,7 @@ ACT_I32, ACT_I64, ACT_U8 = 0, 1, 2
 REW_F32, REW_F64 = 0, 1
 OBS_I32, OBS_I16, OBS_F32, OBS_F16, OBS_BF16, OBS_F64 = 0, 1, 2, 3, 4, 5
 RINS_OFF, RINS_OUTER, RINS_INNER = 0, 1, 2
-LAYOUT_ENV_MAJOR, LAYOUT_FEATURE_MAJOR = 0, 1
+LAYOUT_ENV_MAJOR, LAYOUT_FEATURE_MAJOR, LAYOUT_ENV_MAJOR_SHARED = 0, 1, 2
 ACTIONS_NOOP, ACTIONS_SYNTH = 0, 1
 FLAG_NO_TABLES = 1
 FLAG_NO_L2_HINTS = 2
@@ -78,6 +78,7 @@ class PzEpisodeIo(ctypes.Structure):
         ("episode_return_dev", ctypes.c_void_p),
         ("episode_length_dev", ctypes.c_void_p),
         ("truncated_dev", ctypes.c_void_p),
+        ("status_dev", ctypes.c_void_p),
     ]
 
 
@@ -140,6 +141,12 @@ def load() -> ctypes.CDLL:
     L.pz_host_reset.restype = ctypes.c_int
     L.pz_host_step.argtypes = [vp, vp, vp, vp, vp]
     L.pz_host_step.restype = ctypes.c_int
+    L.pz_host_step_begin.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.pz_host_step_begin.restype = ctypes.c_int
+    L.pz_host_step_end.argtypes = [vp]
+    L.pz_host_step_end.restype = ctypes.c_int
+    L.pz_obs_player2_index.argtypes = [ctypes.c_int]
+    L.pz_obs_player2_index.restype = ctypes.c_int
     L.pz_host_stats.argtypes = [vp, vp]
     L.pz_host_stats.restype = ctypes.c_int
     L.pz_host_state_dev.argtypes = [vp]

@@ -33,6 +33,7 @@ struct KParams {
     double2 *ep_return;   // RecordEpisodeStatistics running returns (in/out), may be null
     int32_t *ep_length;   // may be null
     uint8_t *truncated;   // may be null
+    uint8_t *status;      // may be null: (player_1 base reward + 1) | done << 2 | truncated << 3, one byte per env
     StepCfg cfg;
     int autoreset, simplify, shaped, act_dtype, rew_dtype, obs_dtype, normalize;
     int obs_layout, obs_rows;  // PZ_LAYOUT_*; FEATURE_MAJOR: rows per agent (leading dimension = n)
@@ -148,6 +149,44 @@ __device__ __forceinline__ bool emit_obs_as(const Env &e, bool valid, bool norma
     return false;
 }
 
+// ENV_MAJOR_SHARED: obs[n][35], player_1's row only (player_2's observation is the same 35 values with the two
+// player blocks swapped, pikazoo_env.py:585-586): a quarter of the int32 [n][2][35] bytes as int16. Whole warps
+// stage their 32 rows as the exact global image (2,240 or 4,480 contiguous bytes) and lane 0 issues one bulk copy.
+template <int DT>
+__device__ __forceinline__ void write_obs_row_shared(const Env &e, void *row) {
+    static_assert(DT == PZ_OBS_I32 || DT == PZ_OBS_I16, "shared rows are integer");
+    int u[35];
+    obs_values(e, u);
+    if (DT == PZ_OBS_I32) {
+        int *r = reinterpret_cast<int *>(row);
+#pragma unroll
+        for (int j = 0; j < 35; j++) r[j] = u[j];
+    } else {  // 70-byte rows: odd rows are only 2-byte aligned
+        short *r = reinterpret_cast<short *>(row);
+#pragma unroll
+        for (int j = 0; j < 35; j++) r[j] = (short)u[j];
+    }
+}
+template <int DT>
+__device__ __forceinline__ bool emit_obs_shared_as(const Env &e, bool valid, void *obs, int64_t env_idx, int64_t end,
+                                                   int *warp_stage, int lane, uint64_t policy) {
+    constexpr int row_bytes = PZ_OBS_WORDS * ObsType<DT>::bytes;
+    const int64_t warp_first = env_idx - lane;
+    char *g = reinterpret_cast<char *>(obs);
+    if (warp_stage != nullptr && warp_first + 32 <= end) {  // warp-uniform: full warp
+        write_obs_row_shared<DT>(e, reinterpret_cast<char *>(warp_stage) + lane * row_bytes);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            bulk_store_issue(g + warp_first * row_bytes, warp_stage, 32 * row_bytes, policy);
+            return true;
+        }
+    } else if (valid) {
+        write_obs_row_shared<DT>(e, g + env_idx * row_bytes);
+    }
+    return false;
+}
+
 // FEATURE_MAJOR: obs[((a * rows) + k) * ld + i]. Consecutive lanes hold consecutive envs, so every one of
 // the 70 stores of a warp is one contiguous 64 / 128 / 256-byte segment: no staging, no shared memory.
 // Streaming stores (st.global.cs): written once, read by the policy, never by the simulator.
@@ -238,6 +277,12 @@ __device__ __forceinline__ void emit_obs_feature_major(const Env &e, bool valid,
         case PZ_OBS_BF16: emit_obs_feature_major<PZ_OBS_BF16>(e, valid, normalize, obs, env_idx, ld, rows); break;
         default: emit_obs_feature_major<PZ_OBS_F64>(e, valid, normalize, obs, env_idx, ld, rows); break;
     }
+}
+
+__device__ __forceinline__ bool emit_obs_shared(const Env &e, bool valid, int obs_dtype, void *obs, int64_t env_idx,
+                                                int64_t end, int *warp_stage, int lane, uint64_t policy) {
+    if (obs_dtype == PZ_OBS_I32) return emit_obs_shared_as<PZ_OBS_I32>(e, valid, obs, env_idx, end, warp_stage, lane, policy);
+    return emit_obs_shared_as<PZ_OBS_I16>(e, valid, obs, env_idx, end, warp_stage, lane, policy);
 }
 
 __device__ __forceinline__ bool emit_obs(const Env &e, bool valid, int obs_dtype, bool normalize, void *obs,
@@ -365,6 +410,7 @@ template <int AI_MASK, int OBS_DT, int LAYOUT>
 constexpr int step_min_ctas() {
     if (AI_MASK != 0) return PZ_AI_MIN_CTAS;
     if (LAYOUT == PZ_LAYOUT_FEATURE_MAJOR) return OBS_DT == PZ_OBS_F64 ? 4 : PZ_FM_MIN_CTAS;
+    if (LAYOUT == PZ_LAYOUT_ENV_MAJOR_SHARED) return PZ_HALF_MIN_CTAS;
     return ObsType<OBS_DT>::bytes == 2 ? PZ_HALF_MIN_CTAS : (OBS_DT == PZ_OBS_F64 ? 4 : 6);
 }
 
@@ -373,9 +419,10 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
     pz_step_kernel(const __grid_constant__ KParams P) {
     // ENV_MAJOR stages the observation rows here (2-byte elements need half the room); FEATURE_MAJOR only
     // needs the computer players' scratch
-    constexpr int kRowInts = OBS_DT == PZ_OBS_F64 ? 0 : kObsRow * ObsType<OBS_DT>::bytes / 4;  // f64 rows are not staged
-    constexpr int kStageInts = LAYOUT == PZ_LAYOUT_ENV_MAJOR
-                                   ? (32 * kRowInts > kAiScratchInts ? 32 * kRowInts : kAiScratchInts)
+    constexpr int kRowElems = LAYOUT == PZ_LAYOUT_ENV_MAJOR_SHARED ? PZ_OBS_WORDS : kObsRow;
+    constexpr int kWarpRowInts = OBS_DT == PZ_OBS_F64 ? 0 : 32 * kRowElems * ObsType<OBS_DT>::bytes / 4;  // f64 rows are not staged
+    constexpr int kStageInts = LAYOUT != PZ_LAYOUT_FEATURE_MAJOR
+                                   ? (kWarpRowInts > kAiScratchInts ? kWarpRowInts : kAiScratchInts)
                                    : (AI_MASK != 0 ? kAiScratchInts : 4);
     __shared__ __align__(128) int stage[kWarps][kStageInts];
 #ifdef PZ_FM_NO_STAGING
@@ -438,6 +485,8 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
     if (P.obs) {
         if (LAYOUT == PZ_LAYOUT_ENV_MAJOR)
             pending = emit_obs_as<OBS_DT>(e, valid, P.normalize, P.obs, i, P.end, stage[warp], lane, P.out_policy);
+        else if constexpr (LAYOUT == PZ_LAYOUT_ENV_MAJOR_SHARED)
+            pending = emit_obs_shared_as<OBS_DT>(e, valid, P.obs, i, P.end, stage[warp], lane, P.out_policy);
         else {
             bool staged = false;
             if constexpr (kFmStaged) {
@@ -471,6 +520,7 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
         if (P.ep_length) P.ep_length[i] = e.ep_frames;
         if (P.done) P.done[i] = (uint8_t)(e.game_ended ? 1 : 0);  // a reset cleared it; frozen envs keep it
         if (P.truncated) P.truncated[i] = (uint8_t)(truncated ? 1 : 0);
+        if (P.status) P.status[i] = (uint8_t)((run ? base + 1 : 1) | (e.game_ended ? 4 : 0) | (truncated ? 8 : 0));
     }
     if (P.stats) {
         accumulate_stats(P.stats, e, run && e.game_ended, do_reset, bad, frozen, run && truncated, lane);

@@ -1,7 +1,10 @@
 // Host-buffer path of the C ABI (pz_host_*): what a numpy caller of the reference binds.
 // One context owns the device state and staging buffers of n envs; a step is split into
 // `chunks` env ranges, each on its own stream: H2D(actions) -> pz_step_kernel -> D2H(obs,
-// reward, done), so the PCIe copies of one chunk overlap the kernel and copies of the others.
+// reward, done, status), so the PCIe copies of one chunk overlap the kernel and copies of the others.
+// pz_host_step_begin enqueues all of it and returns; pz_host_step_end waits. The link is the bound
+// (DESIGN.md section 5), so the bytes are what matters: the shared-row int16 observation layout plus the one-byte
+// status (reward, done, truncated) is 71 B per env-step against 297 B for the reference's dtypes.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -20,19 +23,33 @@ struct pz_host_ctx {
     char *obs = nullptr;
     void *reward = nullptr;
     uint8_t *done = nullptr;
+    uint8_t *status = nullptr;
     int64_t *stats = nullptr;
     std::vector<cudaStream_t> streams;
     std::vector<int64_t> bounds;  // chunk c = [bounds[c], bounds[c+1])
     size_t act_elem = 4, rew_elem = 4, obs_row = 2 * PZ_OBS_WORDS * 4;  // obs_row: bytes per env
+    bool in_flight = false;
 };
 
 namespace {
 
-#define PZ_CUDA(x)                           \
-    do {                                     \
-        cudaError_t e_ = (x);                \
+#define PZ_CUDA(x)                             \
+    do {                                       \
+        cudaError_t e_ = (x);                  \
         if (e_ != cudaSuccess) return (int)e_; \
     } while (0)
+
+// Every entry point runs on the context's device whatever device is current in the calling thread.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
 
 int sync_all(pz_host_ctx *c) {
     for (cudaStream_t s : c->streams) PZ_CUDA(cudaStreamSynchronize(s));
@@ -53,11 +70,11 @@ int pz_host_create(pz_host_ctx **out, int64_t n, const pz_config *cfg, uint64_t 
     c->cfg = *cfg;
     c->act_elem = cfg->action_dtype == PZ_ACT_I64 ? 8 : (cfg->action_dtype == PZ_ACT_U8 ? 1 : 4);
     c->rew_elem = cfg->reward_dtype == PZ_REW_F64 ? 8 : 4;
-    if (pz_obs_elem_bytes(cfg->obs_dtype) == 0 || cfg->obs_layout != PZ_LAYOUT_ENV_MAJOR) {  // host rows are env-major
+    if (pz_obs_elem_bytes(cfg->obs_dtype) == 0 || cfg->obs_layout == PZ_LAYOUT_FEATURE_MAJOR) {  // host rows are per env
         delete c;
         return PZ_E_BADCONFIG;
     }
-    c->obs_row = 2 * PZ_OBS_WORDS * pz_obs_elem_bytes(cfg->obs_dtype);
+    c->obs_row = (cfg->obs_layout == PZ_LAYOUT_ENV_MAJOR_SHARED ? 1 : 2) * PZ_OBS_WORDS * pz_obs_elem_bytes(cfg->obs_dtype);
     if (chunks < 1) {  // automatic: one chunk per 128 Ki envs, at most 8 — small batches are bound by API calls, not PCIe
         const int64_t want = n / (128 * 1024);
         chunks = (int32_t)(want < 1 ? 1 : (want > 8 ? 8 : want));
@@ -79,14 +96,17 @@ int pz_host_create(pz_host_ctx **out, int64_t n, const pz_config *cfg, uint64_t 
         if ((rc = (int)cudaMalloc(&c->obs, (size_t)n * c->obs_row))) break;
         if ((rc = (int)cudaMalloc(&c->reward, (size_t)n * 2 * c->rew_elem))) break;
         if ((rc = (int)cudaMalloc(&c->done, (size_t)n))) break;
+        if ((rc = (int)cudaMalloc(&c->status, (size_t)n))) break;
         if ((rc = (int)cudaMalloc(&c->stats, PZ_NUM_STATS * sizeof(int64_t)))) break;
-        if ((rc = (int)cudaMemset(c->stats, 0, PZ_NUM_STATS * sizeof(int64_t)))) break;
         c->streams.resize(chunks);
         for (int k = 0; k < chunks && !rc; k++)
             rc = (int)cudaStreamCreateWithFlags(&c->streams[k], cudaStreamNonBlocking);
         if (rc) break;
+        // the statistics are zeroed and the envs seeded on stream 0; the device-wide synchronisation below orders
+        // both before anything the (non-blocking) chunk streams will ever do
+        if ((rc = (int)cudaMemsetAsync(c->stats, 0, PZ_NUM_STATS * sizeof(int64_t), c->streams[0]))) break;
         if ((rc = pz_seed(c->state, n, base_seed, first_env, c->streams[0]))) break;
-        rc = (int)cudaStreamSynchronize(c->streams[0]);
+        rc = (int)cudaDeviceSynchronize();
     } while (0);
     if (rc) {
         pz_host_destroy(c);
@@ -97,7 +117,8 @@ int pz_host_create(pz_host_ctx **out, int64_t n, const pz_config *cfg, uint64_t 
 }
 
 int pz_host_reset(pz_host_ctx *c, void *obs_host) {
-    if (!c) return PZ_E_BADARG;
+    if (!c || c->in_flight) return PZ_E_BADARG;
+    DeviceGuard guard(c->device);
     const int chunks = (int)c->streams.size();
     for (int k = 0; k < chunks; k++) {
         const int64_t b = c->bounds[k], e = c->bounds[k + 1];
@@ -111,11 +132,15 @@ int pz_host_reset(pz_host_ctx *c, void *obs_host) {
     return sync_all(c);
 }
 
-int pz_host_step(pz_host_ctx *c, const void *actions_host, void *obs_host, void *reward_host,
-                 uint8_t *done_host) {
-    if (!c) return PZ_E_BADARG;
+int pz_host_step_begin(pz_host_ctx *c, const void *actions_host, void *obs_host, void *reward_host,
+                       uint8_t *done_host, uint8_t *status_host) {
+    if (!c || c->in_flight) return PZ_E_BADARG;
     const bool both_ai = c->cfg.is_player1_computer && c->cfg.is_player2_computer;
     if (!actions_host && !both_ai) return PZ_E_BADARG;
+    DeviceGuard guard(c->device);
+    pz_episode_io ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.status_dev = status_host ? c->status : nullptr;
     const int chunks = (int)c->streams.size();
     for (int k = 0; k < chunks; k++) {
         const int64_t b = c->bounds[k], e = c->bounds[k + 1];
@@ -128,7 +153,7 @@ int pz_host_step(pz_host_ctx *c, const void *actions_host, void *obs_host, void 
                                     cudaMemcpyHostToDevice, s));
         int rc = pz::launch_step(c->state, c->n, b, e, &c->cfg, actions_host ? c->actions : nullptr,
                                  obs_host ? c->obs : nullptr, reward_host ? c->reward : nullptr,
-                                 done_host ? c->done : nullptr, c->stats, nullptr, s);
+                                 done_host ? c->done : nullptr, c->stats, status_host ? &ep : nullptr, s);
         if (rc) return rc;
         if (obs_host)
             PZ_CUDA(cudaMemcpyAsync((char *)obs_host + (size_t)b * c->obs_row, c->obs + (size_t)b * c->obs_row,
@@ -138,12 +163,28 @@ int pz_host_step(pz_host_ctx *c, const void *actions_host, void *obs_host, void 
                                     (const char *)c->reward + (size_t)b * 2 * c->rew_elem, cnt * 2 * c->rew_elem,
                                     cudaMemcpyDeviceToHost, s));
         if (done_host) PZ_CUDA(cudaMemcpyAsync(done_host + b, c->done + b, cnt, cudaMemcpyDeviceToHost, s));
+        if (status_host) PZ_CUDA(cudaMemcpyAsync(status_host + b, c->status + b, cnt, cudaMemcpyDeviceToHost, s));
     }
+    c->in_flight = true;
+    return 0;
+}
+
+int pz_host_step_end(pz_host_ctx *c) {
+    if (!c || !c->in_flight) return PZ_E_BADARG;
+    DeviceGuard guard(c->device);
+    c->in_flight = false;
     return sync_all(c);
 }
 
+int pz_host_step(pz_host_ctx *c, const void *actions_host, void *obs_host, void *reward_host,
+                 uint8_t *done_host) {
+    if (int rc = pz_host_step_begin(c, actions_host, obs_host, reward_host, done_host, nullptr)) return rc;
+    return pz_host_step_end(c);
+}
+
 int pz_host_stats(pz_host_ctx *c, int64_t stats_host[PZ_NUM_STATS]) {
-    if (!c || !stats_host) return PZ_E_BADARG;
+    if (!c || !stats_host || c->in_flight) return PZ_E_BADARG;
+    DeviceGuard guard(c->device);
     int rc = sync_all(c);
     if (rc) return rc;
     PZ_CUDA(cudaMemcpy(stats_host, c->stats, PZ_NUM_STATS * sizeof(int64_t), cudaMemcpyDeviceToHost));
@@ -154,13 +195,18 @@ int32_t *pz_host_state_dev(pz_host_ctx *c) { return c ? c->state : nullptr; }
 
 void pz_host_destroy(pz_host_ctx *c) {
     if (!c) return;
+    DeviceGuard guard(c->device);
     for (cudaStream_t s : c->streams)
-        if (s) cudaStreamDestroy(s);
+        if (s) {
+            cudaStreamSynchronize(s);
+            cudaStreamDestroy(s);
+        }
     cudaFree(c->state);
     cudaFree(c->actions);
     cudaFree(c->obs);
     cudaFree(c->reward);
     cudaFree(c->done);
+    cudaFree(c->status);
     cudaFree(c->stats);
     delete c;
 }

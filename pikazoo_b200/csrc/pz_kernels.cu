@@ -46,6 +46,7 @@ __device__ __noinline__ bool emit_obs_cold(int32_t *state, int64_t n, int64_t en
         emit_obs_feature_major(e, valid, obs_dtype, normalize, obs, env_idx, n, rows);
         return false;
     }
+    if (layout == PZ_LAYOUT_ENV_MAJOR_SHARED) return emit_obs_shared(e, valid, obs_dtype, obs, env_idx, end, warp_stage, lane, out_policy);
     return emit_obs(e, valid, obs_dtype, normalize, obs, env_idx, end, warp_stage, lane, out_policy);
 }
 
@@ -349,7 +350,9 @@ int check_config(const pz_config *c) {
     if (c->normalize_observation && (c->obs_dtype == PZ_OBS_I32 || c->obs_dtype == PZ_OBS_I16)) return PZ_E_BADCONFIG;
     if (c->reward_in_normal_state < PZ_RINS_OFF || c->reward_in_normal_state > PZ_RINS_INNER) return PZ_E_BADCONFIG;
     if (c->max_episode_frames < 0) return PZ_E_BADCONFIG;
-    if (c->obs_layout != PZ_LAYOUT_ENV_MAJOR && c->obs_layout != PZ_LAYOUT_FEATURE_MAJOR) return PZ_E_BADCONFIG;
+    if (c->obs_layout < PZ_LAYOUT_ENV_MAJOR || c->obs_layout > PZ_LAYOUT_ENV_MAJOR_SHARED) return PZ_E_BADCONFIG;
+    if (c->obs_layout == PZ_LAYOUT_ENV_MAJOR_SHARED && c->obs_dtype != PZ_OBS_I32 && c->obs_dtype != PZ_OBS_I16)
+        return PZ_E_BADCONFIG;  // shared rows are the integer observation
     if (c->obs_layout == PZ_LAYOUT_FEATURE_MAJOR && c->obs_feature_rows != 0 && c->obs_feature_rows < PZ_OBS_WORDS)
         return PZ_E_BADCONFIG;
     return 0;
@@ -475,6 +478,7 @@ int launch_step(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const
         P.ep_return = reinterpret_cast<double2 *>(ep->episode_return_dev);
         P.ep_length = ep->episode_length_dev;
         P.truncated = ep->truncated_dev;
+        P.status = ep->status_dev;
     }
     switch (am) {
         case 0: launch_step_kernel<0>(end - begin, st, P); break;
@@ -511,6 +515,11 @@ const char *pz_strerror(int code) {
 }
 
 size_t pz_config_bytes(void) { return sizeof(pz_config); }
+
+int pz_obs_player2_index(int k) {
+    if (k < 0 || k >= PZ_OBS_WORDS) return -1;
+    return k < 13 ? k + 13 : (k < 26 ? k - 13 : k);
+}
 
 int pz_config_init(pz_config *c, size_t caller_struct_bytes) {
     if (!c) return PZ_E_BADARG;

@@ -73,6 +73,7 @@ class raw_env:
         self._normal_state_first = False
         self._normalize_observation = False
         self._record_episode_statistics = False
+        self._stack: List[tuple] = []  # (kind, fused) of every wrapper constructed over this env, innermost first
         self._seed_value = int(np.random.SeedSequence().entropy % (2**63)) if seed is None else int(seed)
         self._vec: Optional[PikaVecEnv] = None
         self.scores: List[int] = [0, 0]
@@ -100,6 +101,30 @@ class raw_env:
         self._np_done = v.done_u8.numpy()
         self._np_state = v.state.numpy()
         self._sync = torch.cuda.current_stream(v.device).synchronize
+
+    # What the kernel can reproduce depends on WHERE a wrapper sits in the stack (wrappers are constructed inside
+    # out): RecordEpisodeStatistics records the rewards of what is below it, RewardByBallPosition reads the
+    # observation of what is below it (normalised values if NormalizeObservation is), two RewardByBallPosition add
+    # up, ... The fused options implement ONE order — SimplifyAction, RewardInNormalState / RewardByBallPosition in
+    # either order, NormalizeObservation, RecordEpisodeStatistics on top of the reward wrappers. A wrapper that
+    # does not fit does its work on the host, exactly as the reference's class does, and so does everything
+    # stacked on top of it.
+    _FUSABLE_OVER = {
+        "simplify": lambda below: "simplify" not in below,
+        "rbbp": lambda below: not ({"rbbp", "normalize", "record"} & below),
+        "rins": lambda below: not ({"rins", "record"} & below),
+        "normalize": lambda below: "normalize" not in below,
+        "record": lambda below: "record" not in below,
+    }
+
+    def _try_fuse(self, kind: str, **opts) -> bool:
+        """Called by a wrapper's constructor. True: the kernel option is switched on and the wrapper is a pass-through.
+        False: the wrapper must post-process on the host."""
+        fused = all(f for _, f in self._stack) and self._FUSABLE_OVER[kind]({k for k, _ in self._stack})
+        self._stack.append((kind, fused))
+        if fused:
+            self._configure(**opts)
+        return fused
 
     def _configure(self, **opts):
         """Used by the wrappers to fuse themselves into the kernel configuration."""

@@ -30,7 +30,12 @@ _REW_DTYPES = {torch.float32: _lib.REW_F32, torch.float64: _lib.REW_F64}
 _OBS_DTYPES = {torch.int32: _lib.OBS_I32, torch.int16: _lib.OBS_I16, torch.float32: _lib.OBS_F32,
                torch.float16: _lib.OBS_F16, torch.bfloat16: _lib.OBS_BF16, torch.float64: _lib.OBS_F64}
 
+_LAYOUTS = {"env_major": _lib.LAYOUT_ENV_MAJOR, "feature_major": _lib.LAYOUT_FEATURE_MAJOR,
+            "shared": _lib.LAYOUT_ENV_MAJOR_SHARED}
+
 AGENTS = ("player_1", "player_2")
+# obs_layout="shared": player_2's observation = row[PLAYER2_INDEX] (the two player blocks swapped, pikazoo_env.py:585-586)
+PLAYER2_INDEX = tuple(list(range(13, 26)) + list(range(0, 13)) + list(range(26, 35)))
 
 
 def make_config(
@@ -89,9 +94,11 @@ def make_config(
     if int(max_episode_frames) < 0:
         raise ValueError("max_episode_frames must be >= 0 (0 = never truncate)")
     c.max_episode_frames = int(max_episode_frames)
-    if obs_layout not in ("env_major", "feature_major"):
-        raise ValueError("obs_layout must be 'env_major' or 'feature_major'")
-    c.obs_layout = _lib.LAYOUT_FEATURE_MAJOR if obs_layout == "feature_major" else _lib.LAYOUT_ENV_MAJOR
+    if obs_layout not in _LAYOUTS:
+        raise ValueError("obs_layout must be 'env_major', 'feature_major' or 'shared'")
+    if obs_layout == "shared" and obs_dtype not in (torch.int32, torch.int16):
+        raise TypeError("obs_layout='shared' carries the integer observation: obs_dtype must be int32 or int16")
+    c.obs_layout = _LAYOUTS[obs_layout]
     if int(obs_feature_rows) < _lib.OBS_WORDS:
         raise ValueError("obs_feature_rows must be >= 35")
     c.obs_feature_rows = int(obs_feature_rows)
@@ -133,6 +140,7 @@ class PikaVecEnv:
         obs_feature_rows: int = 35,
         pdl: bool = True,
         host_mapped: bool = False,
+        status: bool = False,
     ):
         """Beyond the reference's constructor arguments:
 
@@ -141,6 +149,9 @@ class PikaVecEnv:
           layout a device-side policy consumes without a transposing pass (GEMM operand with leading
           dimension N). Rows 35.. of each agent (obs_feature_rows=40 pads K to a multiple of 8 for
           tensor-core GEMMs) stay zero.
+          "shared" — obs [N, 35] (int32 / int16): player_1's row only; player_2's observation is
+          `obs[:, PLAYER2_INDEX]` (the two player blocks swapped): a half (a quarter as int16) of the bytes.
+        status: also emit `self.status` uint8 [N] = (player_1's base reward + 1) | terminated << 2 | truncated << 3.
         obs_dtype: torch.int32 (the reference's declared dtype), int16 (same integers, half the bytes),
           or float32 / float16 / bfloat16 / float64 — `(float)value`, or with normalize_observation=True
           the NormalizeObservation wrapper's output (normalize_observation.py:18-32) computed in the
@@ -206,6 +217,8 @@ class PikaVecEnv:
             self.obs_layout = obs_layout
             if obs_layout == "feature_major":
                 self.obs = zeros((2, int(obs_feature_rows), n), obs_dtype)
+            elif obs_layout == "shared":
+                self.obs = zeros((n, _lib.OBS_WORDS), obs_dtype)
             else:
                 self.obs = zeros((n, 2, _lib.OBS_WORDS), obs_dtype)
             self.reward = zeros((n, 2), reward_dtype)
@@ -213,8 +226,12 @@ class PikaVecEnv:
             self.stats = torch.zeros(_lib.NUM_STATS, dtype=torch.int64, device=self.device) if track_stats else None
             self.episode_return = self.episode_length = self._truncated_u8 = None
             self._ep = None
-            if self.record_episode_statistics or self.max_episode_frames > 0:
+            self.status = None
+            if self.record_episode_statistics or self.max_episode_frames > 0 or status:
                 self._ep = _lib.PzEpisodeIo()
+                if status:
+                    self.status = zeros((n,), torch.uint8)
+                    self._ep.status_dev = self.status.data_ptr()
                 if self.record_episode_statistics:
                     self.episode_return = zeros((n, 2), torch.float64)
                     self.episode_length = zeros((n,), torch.int32)

@@ -15,4 +15,18 @@ class RewardByBallPosition(BaseParallelWrapper):
         self.x_line = x_line
         self.y_line = y_line
         self.additional_reward = additional_reward
-        env.unwrapped._configure(reward_by_ball_position=(tuple(additional_reward), int(x_line), int(y_line)))
+        self._fused = env.unwrapped._try_fuse(
+            "rbbp", reward_by_ball_position=(tuple(additional_reward), int(x_line), int(y_line)))
+
+    def step(self, actions):
+        res = self.env.step(actions)
+        if self._fused:
+            return res
+        # not fusable at this position (over NormalizeObservation, RecordEpisodeStatistics or another
+        # RewardByBallPosition): reward_by_ball_position.py:20-31 on the host, on the observation of the env below
+        obs, rews = res[0], res[1]
+        ball_x, ball_y = obs["player_1"][26], obs["player_1"][27]
+        zone = int(ball_y > self.y_line) + 2 * int(ball_x >= self.x_line)
+        for i, agent in enumerate(self.possible_agents):
+            rews[agent] += self.additional_reward[i * 4 + zone]
+        return res

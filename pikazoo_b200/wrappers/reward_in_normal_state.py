@@ -12,7 +12,15 @@ class RewardInNormalState(BaseParallelWrapper):
         super().__init__(env)
         self.reward = reward
         raw = env.unwrapped
-        if raw._reward_in_normal_state is not None:
-            raise NotImplementedError("only one RewardInNormalState wrapper can be fused")
         # constructed before any RewardByBallPosition => it is the inner wrapper of the two
-        raw._configure(reward_in_normal_state=reward, normal_state_first=raw._reward_by_ball_position is None)
+        self._fused = raw._try_fuse("rins", reward_in_normal_state=reward,
+                                    normal_state_first=raw._reward_by_ball_position is None)
+
+    def step(self, actions):
+        res = self.env.step(actions)
+        if not self._fused:  # over RecordEpisodeStatistics or another RewardInNormalState: on the host
+            rews = res[1]
+            for agent in self.possible_agents:
+                if rews[agent] == 0:
+                    rews[agent] = self.reward
+        return res

@@ -18,7 +18,12 @@ class SimplifyAction(BaseParallelWrapper):
         super().__init__(env)
         self.action_map = dict(ACTION_MAP)
         self.action_spaces = dict(zip(self.possible_agents, [spaces.Discrete(13)] * 2))
-        env.unwrapped._configure(simplify_action=True)
+        self._fused = env.unwrapped._try_fuse("simplify", simplify_action=True)
+
+    def step(self, actions):
+        if not self._fused:  # a second SimplifyAction over the first, ...: map on the host like the reference does
+            actions = {agent: self.action_map[agent][actions[agent]] for agent in self.possible_agents}
+        return self.env.step(actions)
 
     def action_space(self, agent):
         return self.action_spaces[agent]

@@ -264,3 +264,41 @@ def test_convert_single_agent(pz):
         total += r
         steps += 1
     assert term and total in (-1, 1) and sum(info["score"]) == 1
+
+
+def _orders_golden():
+    import json
+    import os
+
+    from tests.conftest import ROOT
+
+    with open(os.path.join(ROOT, "tests", "golden", "wrapper_orders.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", ["record_inside_rins", "record_inside_rbbp", "normalize_inside_rbbp", "rbbp_twice",
+                                  "rins_twice", "normalize_twice", "mixed", "canonical"])
+def test_facade_wrapper_orders_match_reference(pz, name):
+    """Wrapper stacks in orders the fused kernel options do not cover (RecordEpisodeStatistics below a reward
+    wrapper records unshaped rewards; RewardByBallPosition over NormalizeObservation reads normalised coordinates;
+    two RewardByBallPosition add up; ...): tests/golden/wrapper_orders.json holds what the reference's own classes
+    return for each stack (oracle/make_golden.py --orders); the facade, which fuses what the kernel reproduces at
+    that position and runs the rest on the host, must return the same observations, rewards, terminations and
+    episode statistics, hashed alike."""
+    from oracle import wrapper_orders as wo
+    from pikazoo_b200 import wrappers as W
+
+    g = _orders_golden()
+    assert g["env"] == wo.ENV_KW and g["action_seed"] == wo.ACTION_SEED
+    stack = wo.STACKS[name]
+    for sess in g["stacks"][name]["sessions"]:
+        seed = sess["seed"]
+        env = wo.build_stack(pz.pikazoo_v0.env(seed=seed, **wo.ENV_KW), W, stack)
+        n_actions = env.action_space("player_1").n
+        got = wo.run_session(env, n_actions, lambda f, a: po.synth_action(wo.ACTION_SEED, seed, f, a, n_actions))
+        assert got["episodes"] == sess["episodes"], (name, seed)
+        assert got["calls"] == sess["calls"] and got["sha256"] == sess["sha256"], (name, seed)
+    # which of these ran fused
+    raw = env.unwrapped
+    fused = [f for _, f in raw._stack]
+    assert all(fused) == (name == "canonical")
