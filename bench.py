@@ -361,11 +361,16 @@ def run_b200_arm(args):
         L = _lib.load()
         nbytes = 280 << 20
         bufs = [torch.empty(nbytes // 4, dtype=torch.int32, device=dev) for _ in range(2)]  # 2 x 280 MB >> 126 MB L2
-        out = {"bytes_per_launch": nbytes, "what": "pz_probe_write: 128-bit streaming stores over 280 MB (two buffers "
-               "alternating), CUDA events around 40 launches; torch_zero = tensor.zero_() on the same buffers"}
+        out = {"bytes_per_launch": nbytes, "what": "pz_probe_write: stores only, over 280 MB (two buffers alternating), CUDA events around "
+               "40 launches: 128-bit stores with the default / evict-first / streaming policy, and the step kernel's own "
+               "observation path (8,960-byte blocks staged in shared memory, one cp.async.bulk per warp, with and "
+               "without the evict-first policy); torch_zero = tensor.zero_() on the same buffers"}
         s_ = torch.cuda.current_stream().cuda_stream
-        for name, fn in (("evict_first_gbs", lambda b_: _lib.check(L.pz_probe_write(b_.data_ptr(), nbytes, 1, s_))),
-                         ("evict_normal_gbs", lambda b_: _lib.check(L.pz_probe_write(b_.data_ptr(), nbytes, 0, s_))),
+        def probe(mode):
+            return lambda b_: _lib.check(L.pz_probe_write(b_.data_ptr(), nbytes, mode, s_))
+
+        for name, fn in (("st_v4_gbs", probe(0)), ("st_v4_evict_first_gbs", probe(1)), ("st_cs_gbs", probe(2)),
+                         ("bulk_copy_evict_first_gbs", probe(3)), ("bulk_copy_gbs", probe(4)),
                          ("torch_zero_gbs", lambda b_: b_.zero_())):
             for k_ in range(4):
                 fn(bufs[k_ & 1])

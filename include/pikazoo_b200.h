@@ -223,10 +223,13 @@ size_t pz_tables_bytes(void);
 int pz_tables_ready(void); /* 1 if the current device holds built tables */
 void pz_tables_release(void);
 
-/* Measurement aid (bench.py `roofline.write_probe`): streams 128-bit stores over `bytes` (a multiple of 16) of
- * device memory, with the evict-first L2 policy of the step kernel's outputs if evict_first != 0 — the bandwidth
- * ceiling of a write-dominated kernel, which the read+write copy figure of MEASURED_PEAKS.json is not. */
-int pz_probe_write(void *dst_dev, size_t bytes, int32_t evict_first, void *stream);
+/* Measurement aid (bench.py `roofline.write_probe`): writes `bytes` (a multiple of 16) of device memory and nothing
+ * else — the bandwidth ceiling of a write-dominated kernel, which the read+write copy figure of MEASURED_PEAKS.json
+ * is not. mode 0: 128-bit stores, default cache policy; 1: with the evict-first L2 policy of the step kernel's
+ * outputs; 2: st.global.cs; 3: the step kernel's observation path itself (8,960-byte blocks staged in shared memory
+ * and written by cp.async.bulk with the evict-first policy, 128-thread CTAs with 35 KB of staging); 4: as 3 without
+ * the policy. */
+int pz_probe_write(void *dst_dev, size_t bytes, int32_t mode, void *stream);
 
 /* packed <-> unpacked (int32 [n][53]) conversions, for checkpoints, tests and debugging */
 int pz_export_state(const int32_t *state_dev, int64_t n, int32_t *unpacked_dev, void *stream);

@@ -238,13 +238,51 @@ __global__ void __launch_bounds__(kThreads) pz_import_kernel(int32_t *state, int
 
 // ---- measurement aid: write-only HBM probe ---------------------------------------------------------
 // The per-step kernel is ~87 % stores: the read+write copy bandwidth in MEASURED_PEAKS.json is
-// not the ceiling such a kernel sees. This streams 128-bit stores with the same L2 policy as the kernel's outputs.
-__global__ void __launch_bounds__(256) pz_probe_write_kernel(uint4 *dst, size_t n16, uint64_t policy, uint32_t v) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride)
-        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%1,%1,%1}, %2;" ::"l"(dst + i), "r"(v),
-                     "l"(policy)
-                     : "memory");
+// not the ceiling such a kernel sees. Modes (pz_probe_write `mode`):
+//   0  128-bit stores, default cache policy, four per thread, one pass over the buffer (a fill kernel)
+//   1  the same with the evict-first L2 policy and L1::no_allocate of the step kernel's reward / state stores
+//   2  st.global.cs (streaming)
+//   3  the step kernel's observation path: every warp fills 8,960 B of shared memory and lane 0 issues one
+//      cp.async.bulk shared -> global with the evict-first policy (128-thread CTAs, 35 KB of staging each)
+//   4  as 3 without the policy hint
+__global__ void __launch_bounds__(256) pz_probe_write_kernel(uint4 *dst, size_t n16, int mode, uint32_t v) {
+    const size_t base = (size_t)blockIdx.x * 1024 + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const size_t i = base + (size_t)k * 256;
+        if (i >= n16) break;
+        if (mode == 1)
+            asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%1,%1,%1}, %2;" ::"l"(dst + i), "r"(v),
+                         "l"(kL2EvictFirst)
+                         : "memory");
+        else if (mode == 2)
+            __stcs(dst + i, make_uint4(v, v, v, v));
+        else
+            dst[i] = make_uint4(v, v, v, v);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 6) pz_probe_bulk_kernel(char *dst, size_t n_blocks, int hint, uint32_t v) {
+    __shared__ __align__(128) int stage[kWarps][32 * kObsRow];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t blk = (size_t)blockIdx.x * kWarps + warp;  // one 8,960-byte block per warp
+    if (blk >= n_blocks) return;
+    int2 *row = reinterpret_cast<int2 *>(stage[warp]) + lane * (kObsRow / 2);
+#pragma unroll
+    for (int j = 0; j < kObsRow / 2; j++) row[j] = make_int2((int)v + j, lane);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        if (hint)
+            bulk_store_issue(dst + blk * kWarpObsBytes, stage[warp], kWarpObsBytes, kL2EvictFirst);
+        else {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + blk * kWarpObsBytes),
+                         "r"(smem_addr(stage[warp])), "r"((uint32_t)kWarpObsBytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        bulk_store_wait_read();
+    }
 }
 
 // ---- memoised trajectory tables ------------------------------------------------------------------
@@ -646,14 +684,20 @@ void pz_tables_release(void) {
     t.error = 0;
 }
 
-int pz_probe_write(void *dst_dev, size_t bytes, int32_t evict_first, void *stream) {
-    if (!dst_dev || (bytes & 15u)) return PZ_E_BADARG;
+int pz_probe_write(void *dst_dev, size_t bytes, int32_t mode, void *stream) {
+    if (!dst_dev || (bytes & 15u) || mode < 0 || mode > 4) return PZ_E_BADARG;
     if (!aligned16(dst_dev)) return PZ_E_ALIGN;
     if (bytes == 0) return 0;
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    pz_probe_write_kernel<<<(unsigned)(sms * 8), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<uint4 *>(dst_dev), bytes / 16, evict_first ? kL2EvictFirst : kL2EvictNormal, 0x5A5A5A5Au);
+    if (mode <= 2) {
+        const size_t n16 = bytes / 16;
+        pz_probe_write_kernel<<<(unsigned)((n16 + 1023) / 1024), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<uint4 *>(dst_dev), n16, mode, 0x5A5A5A5Au);
+    } else {
+        const size_t blocks = bytes / kWarpObsBytes;  // whole 8,960-byte blocks only
+        if (blocks == 0) return PZ_E_BADARG;
+        pz_probe_bulk_kernel<<<(unsigned)((blocks + kWarps - 1) / kWarps), kThreads, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<char *>(dst_dev), blocks, mode == 3, 0x5A5A5A5Au);
+    }
     return launch_status();
 }
 

@@ -157,3 +157,60 @@ def test_calls_follow_the_current_stream(pz):
     torch.cuda.synchronize()
     for a, b in zip(ref, side):
         assert torch.equal(a.state, b.state) and torch.equal(a.obs, b.obs) and torch.equal(a.stats, b.stats)
+
+
+def test_configs2_at_its_stated_size(pz):
+    """configs[2] as BASELINE.json states it: 65,536 envs with SimplifyAction + RewardByBallPosition fused into the
+    step kernel — every output compared with the oracle on a strided sample of envs (every 61st: 1,075 envs incl.
+    the last warp), invariants on the whole batch, 600 frames."""
+    n, steps = 65_536, 600
+    shaped = ((0.1, 0.2, 0.3, 0.4, -0.1, -0.2, -0.3, -0.4), 216, 176)
+    cfg = dict(winning_score=15, serve="winner", simplify_action=True, reward_by_ball_position=shaped)
+    idx = np.unique(np.concatenate([np.arange(0, n, 61), np.arange(n - 40, n)]))
+    tidx = torch.from_numpy(idx).cuda()
+    env = pz.PikaVecEnv(n, seed=4321, reward_dtype=torch.float64, **cfg)
+    orc = po.OracleVecEnv(len(idx), seeds=4321 + idx, **cfg)
+    assert np.array_equal(env.reset()[tidx].cpu().numpy(), orc.reset())
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    zones = set()
+    for t in range(steps):
+        a = torch.randint(0, 13, (n, 2), generator=gen, device="cuda", dtype=torch.int32)
+        obs, rew, done = env.step(a)
+        o_obs, o_rew, o_done = orc.step(a[tidx].cpu().numpy())
+        assert np.array_equal(obs[tidx].cpu().numpy(), o_obs), t
+        assert np.array_equal(rew[tidx].cpu().numpy(), o_rew), t   # float64 rewards: Python's int + float, bit for bit
+        assert np.array_equal(done[tidx].cpu().numpy(), o_done.astype(bool)), t
+        if t % 100 == 0:
+            _obs_invariants(obs)
+            zones |= set(torch.unique((rew[:, 0] * 10).round()).tolist())
+    assert np.array_equal(env.export_state()[tidx].cpu().numpy(), orc.state)
+    assert len(zones) >= 4 and env.stats_dict()["bad_actions"] == 0
+
+
+def test_configs4_two_kernel_loop_at_its_stated_size(pz):
+    """configs[4] per GPU as stated: 2,097,152 envs, winning_score 5, serve random, the MLP policy in the loop through
+    the two-kernel path (pz_policy_mlp_act -> pz_step on feature-major bf16 observations); the oracle replays the
+    sampled actions of a strided sample of envs."""
+    from pikazoo_b200.policy import FusedActor, MLPPolicy, policy_rollout
+
+    n, steps = 1 << 21, 150
+    cfg = dict(winning_score=5, serve="random")
+    env = pz.PikaVecEnv(n, seed=606, obs_dtype=torch.bfloat16, normalize_observation=True, action_dtype=torch.uint8,
+                        obs_layout="feature_major", obs_feature_rows=40, **cfg)
+    idx = np.unique(np.concatenate([np.arange(0, n, 4099), np.arange(n - 33, n)]))
+    tidx = torch.from_numpy(idx).cuda()
+    orc = po.OracleVecEnv(len(idx), seeds=606 + idx, **cfg)
+    env.reset(), orc.reset()
+    actor = FusedActor(MLPPolicy(device=env.device, seed=3), env, seed=12)
+
+    def mirror(t, actions, obs, reward, done):
+        orc.step(actions[tidx].cpu().numpy().astype(np.int32))
+        assert np.array_equal(done[tidx].cpu().numpy(), orc.done.astype(bool)), t
+        if t % 50 == 0 or t == steps - 1:
+            got = obs[:, :35, :][:, :, tidx].permute(2, 0, 1).contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
+            assert np.array_equal(got, orc.normalized_obs("bfloat16")), t
+
+    policy_rollout(env, actor, steps, on_step=mirror)
+    assert np.array_equal(env.export_state()[tidx].cpu().numpy(), orc.state)
+    st = env.stats_dict()
+    assert st["calls"] == n * steps and st["episodes"] > 0 and st["p1_wins"] + st["p2_wins"] == st["episodes"]
