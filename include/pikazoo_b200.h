@@ -292,6 +292,19 @@ int pz_policy_mlp_act(const void *obs_dev, int64_t n, int64_t ld, int32_t rows, 
                       int32_t w2_cols, uint64_t seed, uint64_t step, uint64_t first_env, void *actions_dev,
                       int32_t action_dtype, int32_t greedy, float *logits_dev, void *stream);
 
+/* ---- rgb_array rendering of selected envs ----
+ * raw_env.render() / draw() (pikazoo/env/pikazoo_env.py:250-384) for n_frames frames at once: the pixel work. The host
+ * (pikazoo_b200/render.py) derives, from consecutive simulation states, each frame's display list in the reference's draw
+ * order — pinned against the reference's own draw() — and this rasterises them, one thread per pixel.
+ *   atlas_dev       uint8 [texels][4] RGBA, every sprite variant (flipped / scaled on the host) back to back; alpha must
+ *                   be 0 or 255 (true of all of the reference's sprites): compositing is a select
+ *   sprites_dev     int32 [n_sprites][4] = (offset in texels, width, height, 0)
+ *   background_dev  uint8 [304][432][3], the static part of the scene (draw_background, :308-339) composited once
+ *   items_dev       int32 [n_frames][max_items][4] = (sprite variant, x, y, 0) back to front; variant < 0 = unused
+ *   out_dev         uint8 [n_frames][304][432][3], what render() returns for render_mode "rgb_array" */
+int pz_render(const uint8_t *atlas_dev, const int32_t *sprites_dev, int32_t n_sprites, const uint8_t *background_dev,
+              const int32_t *items_dev, int32_t n_frames, int32_t max_items, uint8_t *out_dev, void *stream);
+
 /* K frames of `observation -> MLP policy -> sampled actions -> raw_env.step` in ONE launch (csrc/pz_rollout_policy.cu):
  * pz_rollout with both players' actions sampled on the device from the policy above, evaluated on tcgen05 from
  * observation tiles that never leave the SM. HBM sees the packed state once per K frames.

@@ -201,8 +201,89 @@ def run_orders(out_path):
     print(f"wrote {out_path}: {os.path.getsize(out_path) / 1024:.0f} KiB")
 
 
+RENDER_SESSIONS = [
+    # (name, env kwargs, action mode, seed, cloud seed, frames)
+    ("random_ws3", dict(winning_score=3, serve="random"), "synth", 31, 900, 700),
+    ("ai_vs_ai_ws2", dict(winning_score=2, serve="winner", is_player1_computer=True, is_player2_computer=True), "noop",
+     32, 901, 1500),
+    ("ai_vs_random_ws12", dict(winning_score=12, serve="alternate", is_player2_computer=True), "synth", 33, 902, 2500),
+]
+
+
+def item_hash(items):
+    h = hashlib.sha256()
+    for name, flip, w, h_, x, y in items:
+        h.update(name.encode())
+        h.update(np.array([flip, w, h_, x, y], dtype="<i4").tobytes())
+    return h.hexdigest()[:16]
+
+
+def run_render(out_path):
+    """Display lists of the reference's own draw() (pikazoo_env.py:250-384) recorded through the pygame stand-in of
+    oracle/pygame_stub.py -> tests/golden/render.json. The clouds and the wave draw from their own generator
+    (env.np_random is swapped around every render() call, and the ten Cloud objects are re-created from it with the
+    reference's class), so that the game stream stays the S0 stream; zero-sized blits are dropped."""
+    from oracle import pygame_stub  # noqa: F401  (installed by ref_harness)
+
+    pikazoo_v0, _ = rh.load_reference()
+    import pikazoo.env.cloud_and_wave as caw  # the reference's module
+
+    out = {"generator": "oracle/make_golden.py --render", "reference": "helpingstar/pika-zoo @ /root/reference "
+           "(unmodified draw(), pygame replaced by oracle/pygame_stub.py), numpy " + np.__version__,
+           "item": "[sprite file, x-flipped, width, height, x, y]", "action_seed": ACTION_SEED, "sessions": []}
+    for name, kw, mode, seed, cloud_seed, frames in RENDER_SESSIONS:
+        env = pikazoo_v0.env(render_mode="rgb_array", **kw)
+        game_rng = env.np_random
+        game_rng.bit_generator.state = np.random.PCG64(int(seed)).state  # protocol S0
+        cloud_rng = np.random.Generator(np.random.PCG64(int(cloud_seed)))
+        env.cloud_array = [caw.Cloud(cloud_rng) for _ in range(env.NUM_OF_CLOUDS)]
+
+        def render():
+            env.np_random = cloud_rng
+            frame = env.render()
+            env.np_random = game_rng
+            assert frame.shape == (304, 432, 3)
+            log = [it for it in env.screen.log if it[2] > 0 and it[3] > 0]
+            del env.screen.log[:]
+            return log
+
+        env.reset()
+        first = render()
+        n_static = next(i for i, it in enumerate(first) if it[0] == "cloud.png")  # draw_background's blits
+        background = first[:n_static]
+        hashes, samples, lengths = [item_hash(first[n_static:])], {0: first[n_static:]}, [len(first) - n_static]
+        kinds = set()
+        for f in range(frames):
+            if mode == "noop":
+                a1 = a2 = 0
+            else:
+                a1, a2 = synth_action(ACTION_SEED, seed, f, 0, 18), synth_action(ACTION_SEED, seed, f, 1, 18)
+            _, _, term, _, _ = env.step({"player_1": a1, "player_2": a2})
+            if term["player_1"]:
+                env.reset()
+            log = render()
+            assert log[:n_static] == background
+            dyn = log[n_static:]
+            hashes.append(item_hash(dyn))
+            lengths.append(len(dyn))
+            new = {it[0] for it in dyn} - kinds
+            if new or (f + 1) % 250 == 0:   # keep the full list whenever a sprite appears for the first time
+                samples[f + 1] = dyn
+            kinds |= new
+        out["sessions"].append({"name": name, "config": kw, "action_mode": mode, "seed": seed, "cloud_seed": cloud_seed,
+                                "frames": frames, "scores": [int(v) for v in env.scores], "hashes": hashes,
+                                "lengths": lengths, "samples": {str(k): v for k, v in samples.items()},
+                                "sprites_seen": sorted(kinds)})
+        print(name, "frames", frames, "scores", env.scores, "sprites", len(kinds), "max items", max(lengths), flush=True)
+        out["background"] = background
+    with open(out_path, "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    print(f"wrote {out_path}: {os.path.getsize(out_path) / 1024:.0f} KiB")
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--render", action="store_true", help="display lists of draw() -> tests/golden/render.json")
     ap.add_argument("--orders", action="store_true", help="odd wrapper orders -> tests/golden/wrapper_orders.json")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--wrappers", action="store_true", help="the wrapper-stack groups -> tests/golden/wrappers.json")
@@ -212,6 +293,9 @@ def main():
     if not rh.reference_available():
         raise SystemExit("reference not present; golden fixtures can only be generated in the build container")
     po.build()
+    if a.render:
+        run_render(a.out or os.path.join(_ROOT, "tests", "golden", "render.json"))
+        return
     if a.orders:
         run_orders(a.out or os.path.join(_ROOT, "tests", "golden", "wrapper_orders.json"))
         return

@@ -142,7 +142,12 @@ def _install_stubs() -> None:
     pz_utils.env = pz_env
     pettingzoo.utils = pz_utils
 
-    pygame = types.ModuleType("pygame")
+    # pygame: the recording stand-in of oracle/pygame_stub.py (an empty module would do for render_mode=None; with a
+    # render mode the reference's draw() runs against it and its blits are logged as display lists)
+    if "pygame" not in sys.modules:
+        from oracle import pygame_stub
+
+        pygame_stub.install(sys.modules)
 
     for name, mod in {
         "gymnasium": gymnasium,
@@ -153,7 +158,6 @@ def _install_stubs() -> None:
         "pettingzoo": pettingzoo,
         "pettingzoo.utils": pz_utils,
         "pettingzoo.utils.env": pz_env,
-        "pygame": pygame,
     }.items():
         sys.modules.setdefault(name, mod)
 

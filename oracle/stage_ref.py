@@ -4,8 +4,8 @@ The reference (helpingstar/pika-zoo) is pure Python: there is nothing to compile
 *it* — not only the C port — on the GPU box's own host cores, in the same run as the GPU numbers
 (BASELINE.json north_star, BASELINE.md CPU-baseline plan). `/root/reference` does not exist there, while
 git-ignored build artefacts in the tree do travel (like the built `.so` files). This recipe copies the
-reference's Python sources (`pikazoo/**/*.py`, ~60 KB; no sprites are needed with render_mode=None)
-byte for byte from where they lie into `oracle/_ref/`, which is listed in `.gitignore` (never enters the
+reference's Python sources (`pikazoo/**/*.py`, ~60 KB) and its sprites (`pikazoo/env/img/*.png`, 320 KB: the
+renderer's GPU tests draw with them; the product never reads oracle/) byte for byte from where they lie into `oracle/_ref/`, which is listed in `.gitignore` (never enters the
 history) and not in `.gpurunignore` (travels). Nothing under `oracle/_ref/` is ever imported by the product;
 its only users are `oracle/ref_harness.py` (tests, golden generation) and `oracle/time_reference.py`
 (bench.py's CPU legs). `STAGED.json` records the sha256 of every staged file so that a run on the box can
@@ -42,7 +42,7 @@ def stage(verbose: bool = False) -> bool:
     manifest = {}
     for dirpath, _, files in os.walk(src_pkg):
         for f in sorted(files):
-            if not f.endswith(".py"):
+            if not f.endswith((".py", ".png")):  # the sprites too (320 KB): assets for tests/test_gpu_render.py
                 continue
             src = os.path.join(dirpath, f)
             rel = os.path.relpath(src, SOURCE)
@@ -55,7 +55,7 @@ def stage(verbose: bool = False) -> bool:
         if os.path.isfile(os.path.join(SOURCE, extra)):
             shutil.copyfile(os.path.join(SOURCE, extra), os.path.join(DEST, extra))
     with open(os.path.join(DEST, "STAGED.json"), "w") as fh:
-        json.dump({"source": SOURCE, "what": "unmodified .py files of helpingstar/pika-zoo, byte for byte",
+        json.dump({"source": SOURCE, "what": "unmodified .py and .png files of helpingstar/pika-zoo, byte for byte",
                    "files": manifest}, fh, indent=1, sort_keys=True)
     if verbose:
         print(f"staged {len(manifest)} reference files into {DEST}")

@@ -160,6 +160,8 @@ def load() -> ctypes.CDLL:
     L.pz_rollout_policy.restype = ctypes.c_int
     L.pz_observe.argtypes = [vp, i64, cfgp, vp, vp]
     L.pz_observe.restype = ctypes.c_int
+    L.pz_render.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp, vp]
+    L.pz_render.restype = ctypes.c_int
     L.pz_policy_select.argtypes = [i32]
     L.pz_policy_select.restype = ctypes.c_int
     if (L.pz_version() != VERSION or L.pz_state_words() != STATE_WORDS or L.pz_unpacked_words() != UNPACKED_WORDS

@@ -5,8 +5,10 @@ protocol and termination bookkeeping; observations come back as numpy arrays lik
 reference's. `parallel_env` does not exist upstream and is an alias of `env`.
 
 Differences, all deliberate: `reset(seed=...)` DOES seed the env (the reference ignores it,
-pikazoo_env.py:149); rendering is not provided (render_mode must be None); an out-of-range
-action raises IndexError (the reference lets numpy wrap negative indices).
+pikazoo_env.py:149); render_mode is None or "rgb_array" (no display; the sprites are the reference's
+assets: pass sprite_dir= or set PIKAZOO_SPRITE_DIR; clouds and waves animate on their own generator,
+so rendering does not change the game as it does upstream); an out-of-range action raises IndexError
+(the reference lets numpy wrap negative indices).
 """
 
 from __future__ import annotations
@@ -51,16 +53,23 @@ class raw_env:
         render_mode=None,
         device="cuda",
         seed: Optional[int] = None,
+        sprite_dir: Optional[str] = None,
+        cloud_seed: int = 0,
     ):
         assert serve in ("winner", "alternate", "random")  # pikazoo_env.py:104
-        if render_mode is not None:
-            raise NotImplementedError("rendering is out of scope of the batched simulator (DESIGN.md §7)")
+        if render_mode not in (None, "rgb_array"):
+            raise NotImplementedError("render_mode must be None or 'rgb_array' (there is no display here)")
         self.possible_agents: List[str] = list(AGENTS)
         self.agents: List[str] = self.possible_agents[:]
         self.action_spaces = dict(zip(self.agents, [spaces.Discrete(18)] * 2))
         self.winning_score = winning_score
         self.serve = serve
-        self.render_mode = None
+        self.render_mode = render_mode
+        self._sprite_dir, self._cloud_seed, self._sprites = sprite_dir, int(cloud_seed), None
+        if render_mode is not None:  # the reference loads its images in the constructor too (pikazoo_env.py:146-147)
+            from .render import SpriteSet
+
+            self._sprites = SpriteSet(sprite_dir)
         self._device = device
         self._kwargs = dict(
             winning_score=winning_score, serve=serve, is_player1_computer=is_player1_computer,
@@ -93,6 +102,8 @@ class raw_env:
             **self._kwargs,
         )
         v = self._vec
+        if self.render_mode is not None:
+            v.attach_renderer([0], cloud_seed=self._cloud_seed, sprites=self._sprites)
         self._actions = torch.zeros((1, 2), dtype=torch.int32).pin_memory()
         # numpy views of the mapped buffers, read after the synchronisation
         self._np_actions = self._actions.numpy()
@@ -211,7 +222,14 @@ class raw_env:
         return self.action_spaces[agent]
 
     def render(self):
-        raise NotImplementedError("rendering is out of scope of the batched simulator (DESIGN.md §7)")
+        """uint8 [304, 432, 3] like the reference's render_mode="rgb_array" (pikazoo_env.py:368-384); None without
+        a render mode. Clouds and waves animate on their own generator (cloud_seed): rendering never touches the
+        game's random stream (in the reference it does)."""
+        if self.render_mode is None:
+            return None
+        if self._vec is None:
+            raise RuntimeError("call reset() before render()")
+        return self._vec._renderer.render()[0].cpu().numpy()
 
     def close(self):
         self._vec = None

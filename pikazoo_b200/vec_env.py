@@ -257,6 +257,7 @@ class PikaVecEnv:
                                   f"{self.lib.pz_tables_bytes() / 1e9:.1f} GB needed): computer players run the "
                                   "iterative simulations (identical results, slower)", RuntimeWarning, stacklevel=2)
                 self.tables_ready = rc == 0
+        self._renderer = None
         self.frame = 0  # calls issued so far (drives the synthetic action stream of rollout())
         self._action_shape = torch.Size((n, 2))
         self._step_args = None
@@ -280,6 +281,20 @@ class PikaVecEnv:
         """[N] bool (None unless max_episode_frames > 0): the episode hit the frame cap on the last call."""
         return self._truncated_u8.view(torch.bool) if self._truncated_u8 is not None else None
 
+    # ---- rendering ---------------------------------------------------------------------------
+    def attach_renderer(self, indices, sprite_dir=None, cloud_seed: int = 0, sprites=None):
+        """rgb_array frames (raw_env.render(), pikazoo_env.py:250-384) for the envs `indices` of this batch:
+        returns a `pikazoo_b200.render.BatchRenderer` whose `render()` gives a uint8 CUDA tensor
+        [len(indices), 304, 432, 3]. While attached, every reset() / step() exports the selected envs' states to the
+        host (the render-only ball state is tracked there), so attach it for evaluation runs, not for training."""
+        from .render import BatchRenderer
+
+        self._renderer = BatchRenderer(self, indices, sprite_dir=sprite_dir, cloud_seed=cloud_seed, sprites=sprites)
+        return self._renderer
+
+    def detach_renderer(self) -> None:
+        self._renderer = None
+
     # ---- reference-shaped API --------------------------------------------------------------
     def reset(self) -> torch.Tensor:
         """reference reset() on every env; returns obs [N, 2, 35] int32 (a view reused by step)."""
@@ -291,6 +306,8 @@ class PikaVecEnv:
             )
             if self._truncated_u8 is not None:
                 self._truncated_u8.zero_()
+        if self._renderer is not None:
+            self._renderer.after_reset()
         return self.obs
 
     def step(self, actions: Optional[torch.Tensor]):
@@ -314,6 +331,8 @@ class PikaVecEnv:
             a_ptr = actions.data_ptr()
         else:
             a_ptr = None
+        if self._renderer is not None:
+            self._renderer.before_call()
         # the small-batch regime is bound by this host path: every constant argument is cached
         # (self._step_args), and the device guard is only entered when another device is current
         args = self._step_args
@@ -331,6 +350,8 @@ class PikaVecEnv:
         if rc != 0:
             _lib.check(rc, "pz_step")
         self.frame += 1
+        if self._renderer is not None:
+            self._renderer.after_step()
         return self._step_result
 
     def rollout(self, K: int, actions: str = "noop", action_seed: int = 0, write_obs: bool = False):
@@ -339,6 +360,8 @@ class PikaVecEnv:
         actions: "noop" (both 0; computer players decide for themselves) or "synth" (uniform
         actions from the counter-based device stream keyed by (action_seed, global env, frame)).
         """
+        if self._renderer is not None:
+            raise RuntimeError("a renderer follows the env call by call: detach it before a K-frame rollout")
         src = {"noop": _lib.ACTIONS_NOOP, "synth": _lib.ACTIONS_SYNTH}[actions]
         with torch.cuda.device(self.device):
             _lib.check(
