@@ -88,7 +88,7 @@ def test_rendering_does_not_touch_the_game(cuda_lib, sprites):
     f0 = b.render()
     assert f0.shape == (304, 432, 3) and f0.dtype == np.uint8 and a.render() is None
     rng = np.random.default_rng(0)
-    changed = 0
+    changed = steps = 0
     for t in range(300):
         if not a.agents:
             break
@@ -96,9 +96,10 @@ def test_rendering_does_not_touch_the_game(cuda_lib, sprites):
         ra, rb = a.step(act), b.step(act)
         assert np.array_equal(ra[0]["player_1"], rb[0]["player_1"]) and ra[1] == rb[1] and ra[2] == rb[2]
         f = b.render()
+        steps += 1
         changed += int(not np.array_equal(f, f0))
         f0 = f
-    assert changed > 250  # the scene animates
+    assert steps > 50 and changed == steps  # the scene animates (clouds and waves move every rendered frame)
     assert np.array_equal(a.state_words(), b.state_words())
     # player 1's sprite is where the state says: the 64x64 box around (x, y) differs from the background there
     st = b.state_words()
