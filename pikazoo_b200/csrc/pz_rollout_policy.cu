@@ -60,9 +60,17 @@ using pzp::tc::tmem_st8;
 using pzp::tc::tmem_st_wait;
 
 // Tiles in flight per SM. Measured on B200, configs[4] (2 M envs, K = 64): 3 groups 18.1 G env-steps/s (every group its
-// own slot, 170 registers), 4: 20.8, 5: 21.9 (96 registers, no spills), 6: 20.4 (80 registers, 420 B of spills).
+// own slot, 170 registers), 4: 20.8, 5: 21.9 (96 registers), 6: 20.4 (80 registers, 420 B of spills). With the PCG64
+// stream and the statistics parked in shared memory (DrawCtxParked): 5: 21.5, 6: 23.1 (150 B of spills), 7: 23.3 —
+// six it is; parking five more cold env fields (boldness, stand-by, landing point) measured slower (21.9 at six).
+// The profile (profiles/r02_ncu_full_rollout_policy.txt): 1,020 warp instructions per warp and frame, issue slots 67 %
+// busy with five warps per scheduler of which one or two sit in a barrier, a slot wait or an MMA wait at any time:
+// bound by how many warps can run, i.e. by registers. Tried and dropped: staggering the two agents' chains (layer 2 of
+// player_1 during player_2's epilogue, layer 2 of player_2 during player_1's sampling: one more barrier, the slot held
+// through a sampler, and the two samplers no longer interleave: 20.2 G); four slots of 128 columns (hidden padded to 64,
+// timing only: +3 %).
 #ifndef PZ_RP_GROUPS
-#define PZ_RP_GROUPS 5
+#define PZ_RP_GROUPS 6
 #endif
 #ifndef PZ_RP_BACKOFF_NS
 #define PZ_RP_BACKOFF_NS 100  // sleep between polls of the MMA barrier: the kernel is bound by instruction issue
@@ -97,8 +105,11 @@ constexpr int kLutPX = 0, kLutPY = kLutPX + 512, kLutPYV = kLutPY + 256, kLutDiv
               kLutBXV = kLutX432 + 512, kLutEntries = kLutBXV + 64;
 constexpr int kOffW1 = 0, kOffW2 = kOffW1 + kW1Bytes, kOffX = kOffW2 + 2 * kW2Agent, kOffLut = kOffX + kGroups * kXTile,
               kOffBar = (kOffLut + 2 * kLutEntries + 15) / 16 * 16, kOffSlot = kOffBar + 8 * kGroups,
-              kOffMask = kOffSlot + 4 * kGroups, kOffTmem = kOffMask + 4, kOffAct = kOffTmem + 4;  // [2][32] uint32
-constexpr size_t kSmemBytes = kOffAct + 2 * 32 * 4;
+              kOffMask = kOffSlot + 4 * kGroups, kOffTmem = kOffMask + 4, kOffAct = kOffTmem + 4,  // [2][32] uint32
+              kOffStats = (kOffAct + 2 * 32 * 4 + 7) / 8 * 8,                // uint64 [PZ_NUM_STATS]
+              kOffRng = kOffStats + 8 * PZ_NUM_STATS;                       // [group][9 words][128 threads] uint32
+constexpr int kRngWords = 9;
+constexpr size_t kSmemBytes = kOffRng + (size_t)kGroups * kRngWords * kGroupThreads * 4;
 
 struct Params {
     int32_t *state;
@@ -120,6 +131,53 @@ __device__ __forceinline__ void group_sync(int id) {
 __device__ __forceinline__ void group_arrive(int id) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(kGroupThreads) : "memory");
 }
+
+// The env's PCG64 stream parked in shared memory for the K frames: without computer players a frame draws only at a
+// round start and on the rare x_velocity == 0 collision, so the stream's nine words need not occupy registers across
+// the frame loop — registers are what bounds this kernel (tiles in flight per SM). Word w of thread t lies at
+// [w][t]: conflict-free.
+struct DrawCtxParked {
+    uint32_t *slot;  // this thread's column of [9][128]
+    __device__ __forceinline__ void fetch(Rng &r) const {
+        r.s_lo = (uint64_t)slot[0] | ((uint64_t)slot[kGroupThreads] << 32);
+        r.s_hi = (uint64_t)slot[2 * kGroupThreads] | ((uint64_t)slot[3 * kGroupThreads] << 32);
+        r.inc_lo = (uint64_t)slot[4 * kGroupThreads] | ((uint64_t)slot[5 * kGroupThreads] << 32);
+        r.inc_hi = (uint64_t)slot[6 * kGroupThreads] | ((uint64_t)slot[7 * kGroupThreads] << 32);
+        r.uinteger = slot[8 * kGroupThreads];
+        r.loaded = true;
+        r.dirty = false;
+    }
+    __device__ __forceinline__ void park(const Rng &r) const {  // (the increment never changes)
+        slot[0] = (uint32_t)r.s_lo, slot[kGroupThreads] = (uint32_t)(r.s_lo >> 32);
+        slot[2 * kGroupThreads] = (uint32_t)r.s_hi, slot[3 * kGroupThreads] = (uint32_t)(r.s_hi >> 32);
+        slot[8 * kGroupThreads] = r.uinteger;
+    }
+    __device__ __forceinline__ void park_all(const Rng &r) const {
+        park(r);
+        slot[4 * kGroupThreads] = (uint32_t)r.inc_lo, slot[5 * kGroupThreads] = (uint32_t)(r.inc_lo >> 32);
+        slot[6 * kGroupThreads] = (uint32_t)r.inc_hi, slot[7 * kGroupThreads] = (uint32_t)(r.inc_hi >> 32);
+    }
+    template <uint32_t HIGH>
+    __device__ __forceinline__ int integers(int &has32) {
+        Rng r;
+        fetch(r);
+        const int v = rng_integers<HIGH>(r, has32);
+        park(r);
+        return v;
+    }
+    __device__ __forceinline__ void computer_draws(int &has32, bool near, bool search, int &standby, int &y_first) {
+        Rng r;
+        fetch(r);
+        rng_computer_draws(r, has32, near, search, standby, y_first);
+        park(r);
+    }
+    __device__ __forceinline__ void integers5_twice(int &has32, int &a, int &b) {
+        Rng r;
+        fetch(r);
+        rng_integers5_twice(r, has32, a, b);
+        park(r);
+    }
+};
 
 // bf16 bits of feature K for raw value v, by the arithmetic of the step kernel's observation output
 // (obs_float<float, K> then round-to-nearest-even): the tables and the one computed feature share it.
@@ -188,6 +246,8 @@ __global__ void __launch_bounds__(kThreads, 1) pz_rollout_policy_kernel(const __
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (ctid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1u) : "memory");
+    unsigned long long *s_stats = reinterpret_cast<unsigned long long *>(smem + kOffStats);
+    if (tid < PZ_NUM_STATS) s_stats[tid] = 0ULL;
     if (tid == 0) {
         *slot_mask = (1u << kSlots) - 1u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -247,19 +307,21 @@ __global__ void __launch_bounds__(kThreads, 1) pz_rollout_policy_kernel(const __
     for (int64_t tile = blockIdx.x + (int64_t)gridDim.x * grp; tile < n_tiles; tile += (int64_t)gridDim.x * kGroups) {
         const int64_t i = tile * kTileEnvs + ctid;
         const bool valid = i < P.n;
-        DrawCtxT<false> d;
-        d.r.loaded = false;
-        d.r.dirty = false;
+        DrawCtxParked d;
+        d.slot = reinterpret_cast<uint32_t *>(smem + kOffRng) + grp * kRngWords * kGroupThreads + ctid;
         Env e;
         if (valid) {
             const StatePtrs sp = state_ptrs(P.state, P.n, P.state_policy);
             load_env(e, sp, i);
-            rng_load(d.r, sp, i);
+            Rng r;
+            rng_load(r, sp, i);
+            d.park_all(r);
         } else {
             fresh_env(e);
+            Rng r = {};
+            d.park_all(r);
         }
         const uint64_t genv = P.first_env + (uint64_t)i;
-        unsigned st_ep = 0, st_frames = 0, st_w1 = 0, st_s1 = 0, st_s2 = 0, st_resets = 0, st_trunc = 0;
 
 #pragma unroll 1
         for (int k = 0; k < P.K; k++) {
@@ -407,54 +469,36 @@ __global__ void __launch_bounds__(kThreads, 1) pz_rollout_policy_kernel(const __
                 const Input in1 = input_from_packed(e.p[0], acttab[act[0]]);
                 const Input in2 = input_from_packed(e.p[1], acttab[32 + act[1]]);
                 step_frame_inputs<0>(0xFFFFFFFFu, e, d, P.cfg, in1, in2, nullptr);
+                // episode-granular events (one in hundreds of frames per env): shared-memory atomics, no registers
                 if (e.game_ended) {
-                    st_ep += 1;
-                    st_frames += (unsigned)e.ep_frames;
-                    st_w1 += (e.score[0] > e.score[1]) ? 1u : 0u;
-                    st_s1 += (unsigned)e.score[0];
-                    st_s2 += (unsigned)e.score[1];
+                    const bool w1 = e.score[0] > e.score[1];
+                    atomicAdd(s_stats + PZ_STAT_EPISODES, 1ULL);
+                    atomicAdd(s_stats + PZ_STAT_EPISODE_FRAMES, (unsigned long long)e.ep_frames);
+                    atomicAdd(s_stats + (w1 ? PZ_STAT_P1_WINS : PZ_STAT_P2_WINS), 1ULL);
+                    atomicAdd(s_stats + PZ_STAT_P1_POINTS, (unsigned long long)e.score[0]);
+                    atomicAdd(s_stats + PZ_STAT_P2_POINTS, (unsigned long long)e.score[1]);
                 } else if (P.max_frames > 0 && e.ep_frames >= P.max_frames) {
-                    st_trunc += 1;
+                    atomicAdd(s_stats + PZ_STAT_TRUNCATED, 1ULL);
                 }
             } else if (valid) {
                 reset_env(e, d, P.cfg);
-                st_resets += 1;
+                atomicAdd(s_stats + PZ_STAT_RESETS, 1ULL);
             }
         }
 
         if (valid) {
             const StatePtrs sp = state_ptrs(P.state, P.n, P.state_policy);
             store_env(e, sp, i);
-            if (d.r.dirty) rng_store(d.r, sp, i);
+            Rng r;
+            d.fetch(r);
+            rng_store(r, sp, i);
         }
-        if (P.stats) {
-            const unsigned ep = __reduce_add_sync(0xFFFFFFFFu, st_ep);
-            const unsigned rs = __reduce_add_sync(0xFFFFFFFFu, st_resets);
-            const unsigned tr = __reduce_add_sync(0xFFFFFFFFu, st_trunc);
-            const unsigned cnt = __popc(__ballot_sync(0xFFFFFFFFu, valid));
-            if (lane == 0) {
-                if (tr) atomicAdd(P.stats + PZ_STAT_TRUNCATED, (unsigned long long)tr);
-                atomicAdd(P.stats + PZ_STAT_CALLS, (unsigned long long)cnt * (unsigned long long)P.K);
-            }
-            if (ep | rs) {
-                const unsigned fr = __reduce_add_sync(0xFFFFFFFFu, st_frames);
-                const unsigned w1 = __reduce_add_sync(0xFFFFFFFFu, st_w1);
-                const unsigned s1 = __reduce_add_sync(0xFFFFFFFFu, st_s1);
-                const unsigned s2 = __reduce_add_sync(0xFFFFFFFFu, st_s2);
-                if (lane == 0) {
-                    atomicAdd(P.stats + PZ_STAT_EPISODES, (unsigned long long)ep);
-                    atomicAdd(P.stats + PZ_STAT_EPISODE_FRAMES, (unsigned long long)fr);
-                    atomicAdd(P.stats + PZ_STAT_P1_WINS, (unsigned long long)w1);
-                    atomicAdd(P.stats + PZ_STAT_P2_WINS, (unsigned long long)(ep - w1));
-                    atomicAdd(P.stats + PZ_STAT_P1_POINTS, (unsigned long long)s1);
-                    atomicAdd(P.stats + PZ_STAT_P2_POINTS, (unsigned long long)s2);
-                    atomicAdd(P.stats + PZ_STAT_RESETS, (unsigned long long)rs);
-                }
-            }
-        }
+        const unsigned cnt = __popc(__ballot_sync(0xFFFFFFFFu, valid));
+        if (lane == 0) atomicAdd(s_stats + PZ_STAT_CALLS, (unsigned long long)cnt * (unsigned long long)P.K);
     }
     tc_fence_before();
     __syncthreads();
+    if (P.stats != nullptr && tid < PZ_NUM_STATS && s_stats[tid] != 0ULL) atomicAdd(P.stats + tid, s_stats[tid]);
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
 }
 
