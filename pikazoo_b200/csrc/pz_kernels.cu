@@ -79,8 +79,12 @@ __global__ void __maxnreg__(PZ_ROLLOUT_MAXNREG) pz_rollout_kernel(const __grid_c
     const uint32_t n_actions = P.simplify ? 13u : 18u;
     const uint64_t genv = P.first_env + (uint64_t)i;
 
-    // episode-granular statistics accumulated per thread, reduced once at the end
-    unsigned st_ep = 0, st_frames = 0, st_w1 = 0, st_s1 = 0, st_s2 = 0, st_resets = 0, st_trunc = 0;
+    // Episode-granular statistics (an event per env every few hundred frames): shared-memory atomics at the event, one
+    // flush per CTA — seven per-thread counters would sit in registers across the frame loop, and registers (the cap
+    // above) are what this kernel is short of.
+    __shared__ unsigned long long s_stats[PZ_NUM_STATS];
+    if (threadIdx.x < PZ_NUM_STATS) s_stats[threadIdx.x] = 0ULL;
+    __syncthreads();
 
 #pragma unroll 1
     for (int k = 0; k < P.K; k++) {
@@ -102,17 +106,17 @@ __global__ void __maxnreg__(PZ_ROLLOUT_MAXNREG) pz_rollout_kernel(const __grid_c
             }
             step_frame<AI_MASK>(mask, e, d, P.cfg, k1, k2, stage[warp]);
             if (e.game_ended) {
-                st_ep += 1;
-                st_frames += (unsigned)e.ep_frames;
-                st_w1 += (e.score[0] > e.score[1]) ? 1u : 0u;
-                st_s1 += (unsigned)e.score[0];
-                st_s2 += (unsigned)e.score[1];
+                atomicAdd(s_stats + PZ_STAT_EPISODES, 1ULL);
+                atomicAdd(s_stats + PZ_STAT_EPISODE_FRAMES, (unsigned long long)e.ep_frames);
+                atomicAdd(s_stats + (e.score[0] > e.score[1] ? PZ_STAT_P1_WINS : PZ_STAT_P2_WINS), 1ULL);
+                atomicAdd(s_stats + PZ_STAT_P1_POINTS, (unsigned long long)e.score[0]);
+                atomicAdd(s_stats + PZ_STAT_P2_POINTS, (unsigned long long)e.score[1]);
             } else if (episode_truncated(P, e)) {
-                st_trunc += 1;
+                atomicAdd(s_stats + PZ_STAT_TRUNCATED, 1ULL);
             }
         } else if (valid) {
             reset_env(e, d, P.cfg);
-            st_resets += 1;
+            atomicAdd(s_stats + PZ_STAT_RESETS, 1ULL);
         }
     }
 
@@ -125,26 +129,9 @@ __global__ void __maxnreg__(PZ_ROLLOUT_MAXNREG) pz_rollout_kernel(const __grid_c
     bool pending = false;
     if (P.obs) pending = emit_obs_cold(P.state, P.n, i, P.end, P.obs_dtype, P.normalize, P.obs, nullptr, P.state_policy,
                                        P.out_policy, P.obs_layout, P.obs_rows);
+    __syncthreads();
     if (P.stats) {
-        const unsigned ep = __reduce_add_sync(kFullMask, st_ep);
-        const unsigned rs = __reduce_add_sync(kFullMask, st_resets);
-        const unsigned tr = __reduce_add_sync(kFullMask, st_trunc);
-        if (lane == 0) stat_add(P.stats, PZ_STAT_TRUNCATED, tr);
-        if (ep | rs) {
-            const unsigned fr = __reduce_add_sync(kFullMask, st_frames);
-            const unsigned w1 = __reduce_add_sync(kFullMask, st_w1);
-            const unsigned s1 = __reduce_add_sync(kFullMask, st_s1);
-            const unsigned s2 = __reduce_add_sync(kFullMask, st_s2);
-            if (lane == 0) {
-                stat_add(P.stats, PZ_STAT_EPISODES, ep);
-                stat_add(P.stats, PZ_STAT_EPISODE_FRAMES, fr);
-                stat_add(P.stats, PZ_STAT_P1_WINS, w1);
-                stat_add(P.stats, PZ_STAT_P2_WINS, ep - w1);
-                stat_add(P.stats, PZ_STAT_P1_POINTS, s1);
-                stat_add(P.stats, PZ_STAT_P2_POINTS, s2);
-                stat_add(P.stats, PZ_STAT_RESETS, rs);
-            }
-        }
+        if (threadIdx.x < PZ_NUM_STATS && s_stats[threadIdx.x] != 0ULL) atomicAdd(P.stats + threadIdx.x, s_stats[threadIdx.x]);
         if (i == P.begin)
             atomicAdd(P.stats + PZ_STAT_CALLS, (unsigned long long)(P.end - P.begin) * (unsigned long long)P.K);
     }
