@@ -17,7 +17,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import pikazoo_b200  # noqa: E402
-from pikazoo_b200.policy import FusedActor, MLPPolicy, policy_rollout  # noqa: E402
+from pikazoo_b200.policy import FusedActor, MLPPolicy, policy_rollout, rollout_fused  # noqa: E402
 
 
 def main():
@@ -25,8 +25,11 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 21)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--stats-every", type=int, default=50)
-    ap.add_argument("--actor", choices=["fused", "eager"], default="fused",
-                    help="fused: the library's policy kernel (pz_policy_mlp_act); eager: MLPPolicy.act in PyTorch")
+    ap.add_argument("--actor", choices=["rollout", "fused", "eager"], default="rollout",
+                    help="rollout: the whole loop in one launch per K frames (pz_rollout_policy: env, observation tile, "
+                         "both layers on tcgen05 and the sample all on chip); fused: two launches per frame "
+                         "(pz_policy_mlp_act -> pz_step); eager: MLPPolicy.act in PyTorch -> pz_step")
+    ap.add_argument("--K", type=int, default=50, help="frames per launch of the rollout actor")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -36,19 +39,27 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     env = pikazoo_b200.make_sharded_env(a.envs_per_gpu * world, rank, world, dev, seed=5, winning_score=5,
                                         serve="random", obs_dtype=torch.bfloat16, normalize_observation=True,
-                                        action_dtype=torch.uint8 if a.actor == "fused" else torch.int64,
+                                        action_dtype=torch.int64 if a.actor == "eager" else torch.uint8,
                                         obs_layout="feature_major", obs_feature_rows=40)
     policy = MLPPolicy(device=dev)
     act = FusedActor(policy, env, seed=1) if a.actor == "fused" else policy.act
+
+    def run(frames):
+        if a.actor == "rollout":
+            for f0 in range(0, frames, a.K):
+                rollout_fused(env, policy, min(a.K, frames - f0), seed=1)
+        else:
+            policy_rollout(env, act, frames)
+
     env.reset()
-    policy_rollout(env, act, 10)
+    run(10)
     pikazoo_b200.allreduce_stats(env.stats.clone())  # NCCL communicator set-up happens on the first collective
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     done_steps = 0
     while done_steps < a.steps:
         k = min(a.stats_every, a.steps - done_steps)
-        policy_rollout(env, act, k)
+        run(k)
         done_steps += k
         stats = env.stats.clone()
         pikazoo_b200.allreduce_stats(stats)  # the one collective: 16 int64 over NVLink

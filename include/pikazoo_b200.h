@@ -191,6 +191,11 @@ typedef struct pz_episode_io {
     uint8_t *status_dev; /* uint8 [n], out: (player_1's BASE reward + 1) | terminated << 2 | truncated << 3 — reward,
                             done and truncation of an unshaped env in one byte (player_2's reward is the negative);
                             on reset / frozen calls the reward field is 1 (reward 0) */
+    uint32_t *seq_dev;   /* optional, batches of at most 128 envs (one CTA): after every output of the call is
+                            written, seq_value is stored here behind a system-scope fence. With host-mapped buffers
+                            (cudaHostAlloc) a host thread can spin on this word instead of synchronising the stream:
+                            the single-env facade's completion signal */
+    uint32_t seq_value;
 } pz_episode_io;
 int pz_reset_ex(int32_t *state_dev, int64_t n, const pz_config *cfg, void *obs_dev, const pz_episode_io *episode,
                 void *stream); /* pz_reset that also zeroes episode_return_dev / episode_length_dev */

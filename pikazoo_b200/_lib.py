@@ -79,6 +79,8 @@ class PzEpisodeIo(ctypes.Structure):
         ("episode_length_dev", ctypes.c_void_p),
         ("truncated_dev", ctypes.c_void_p),
         ("status_dev", ctypes.c_void_p),
+        ("seq_dev", ctypes.c_void_p),
+        ("seq_value", ctypes.c_uint32),
     ]
 
 

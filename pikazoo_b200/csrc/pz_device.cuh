@@ -34,6 +34,8 @@ struct KParams {
     int32_t *ep_length;   // may be null
     uint8_t *truncated;   // may be null
     uint8_t *status;      // may be null: (player_1 base reward + 1) | done << 2 | truncated << 3, one byte per env
+    uint32_t *seq;        // may be null (single-CTA launches only): completion word, see pz_episode_io.seq_dev
+    uint32_t seq_value;
     StepCfg cfg;
     int autoreset, simplify, shaped, act_dtype, rew_dtype, obs_dtype, normalize;
     int obs_layout, obs_rows;  // PZ_LAYOUT_*; FEATURE_MAJOR: rows per agent (leading dimension = n)
@@ -527,6 +529,15 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
         if (i == P.begin) atomicAdd(P.stats + PZ_STAT_CALLS, (unsigned long long)(P.end - P.begin));
     }
     if (pending) bulk_store_wait_read();
+    if (P.seq != nullptr) {  // launch-uniform; one CTA (checked on the host)
+        if (pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the rows have left, not only been read
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t *>(P.seq) = P.seq_value;
+        }
+    }
 }
 
 // Launches pz_step_kernel<AI_MASK, P.obs_dtype, P.obs_layout> over n envs; defined in pz_step_ai*.cu.

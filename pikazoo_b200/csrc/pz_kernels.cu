@@ -504,6 +504,11 @@ int launch_step(int32_t *state_dev, int64_t n, int64_t begin, int64_t end, const
         P.ep_length = ep->episode_length_dev;
         P.truncated = ep->truncated_dev;
         P.status = ep->status_dev;
+        if (ep->seq_dev) {
+            if (end - begin > kThreads) return PZ_E_BADARG;  // the completion word needs a single CTA
+            P.seq = ep->seq_dev;
+            P.seq_value = ep->seq_value;
+        }
     }
     switch (am) {
         case 0: launch_step_kernel<0>(end - begin, st, P); break;

@@ -99,6 +99,7 @@ class raw_env:
             normalize_observation=self._normalize_observation,
             obs_dtype=torch.float64 if self._normalize_observation else torch.int32,
             record_episode_statistics=self._record_episode_statistics, track_stats=False, host_mapped=True,
+            status=True,
             **self._kwargs,
         )
         v = self._vec
@@ -110,7 +111,7 @@ class raw_env:
         self._np_obs = v.obs.numpy()
         self._np_reward = v.reward.numpy()
         self._np_done = v.done_u8.numpy()
-        self._np_state = v.state.numpy()
+        self._np_status = v.status.numpy()
         self._sync = torch.cuda.current_stream(v.device).synchronize
 
     # What the kernel can reproduce depends on WHERE a wrapper sits in the stack (wrappers are constructed inside
@@ -146,12 +147,22 @@ class raw_env:
             self._build()
             self._vec.load_state_dict(state)
 
-    def _fetch(self):
+    def _fetch(self, stepped=False):
         """wait for the launch; the outputs are then in the mapped buffers"""
-        self._sync()
-        # scores live in the packed state's ENV word (csrc/pz_state.cuh: G1.w = score1:10 | score2:10 << 10 | ...)
-        env_word = int(self._np_state[7]) & 0xFFFFFFFF
-        self.scores[0], self.scores[1] = env_word & 1023, (env_word >> 10) & 1023
+        if stepped:
+            self._vec.wait()  # spins on the kernel's completion word in mapped memory
+        else:
+            self._sync()
+        # the scores follow from the status byte: its low two bits are player_1's BASE reward + 1 (whatever reward
+        # wrappers are fused), and a point is scored exactly when that is non-zero (pikazoo_env.py:190-223)
+        if stepped:
+            base = (int(self._np_status[0]) & 3) - 1
+            if base > 0:
+                self.scores[0] += 1
+            elif base < 0:
+                self.scores[1] += 1
+        else:
+            self.scores[0] = self.scores[1] = 0
 
     def _obs_dict(self) -> Dict[str, np.ndarray]:
         # the reference returns np.array of Python ints (int64); NormalizeObservation makes them float64
@@ -186,7 +197,7 @@ class raw_env:
                 raise IndexError(f"action {v} is out of range for Discrete({n})")
         self._np_actions[0, 0], self._np_actions[0, 1] = a[0], a[1]
         self._vec.step(self._actions)
-        self._fetch()
+        self._fetch(stepped=True)
         r = self._np_reward[0].tolist()
         terminated = bool(self._np_done[0])
         observations = self._obs_dict()

@@ -30,6 +30,17 @@ _REW_DTYPES = {torch.float32: _lib.REW_F32, torch.float64: _lib.REW_F64}
 _OBS_DTYPES = {torch.int32: _lib.OBS_I32, torch.int16: _lib.OBS_I16, torch.float32: _lib.OBS_F32,
                torch.float16: _lib.OBS_F16, torch.bfloat16: _lib.OBS_BF16, torch.float64: _lib.OBS_F64}
 
+# torch.cuda.current_stream() / current_device() walk several Python layers (3-5 us per call — more than the launch
+# they precede); the raw accessors behind them are one C call each
+try:
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+    _raw_device = torch._C._cuda_getDevice
+except AttributeError:  # pragma: no cover - other torch builds
+    def _raw_stream(index):
+        return torch.cuda.current_stream(index).cuda_stream
+
+    _raw_device = torch.cuda.current_device
+
 _LAYOUTS = {"env_major": _lib.LAYOUT_ENV_MAJOR, "feature_major": _lib.LAYOUT_FEATURE_MAJOR,
             "shared": _lib.LAYOUT_ENV_MAJOR_SHARED}
 
@@ -160,7 +171,7 @@ class PikaVecEnv:
           applied outside RewardByBallPosition, or inside it with normal_state_first=True.
         max_episode_frames: truncate episodes that reach this many step() calls (0 = never, like the
           reference); `self.truncated` [N] bool reports it and the next call resets the env.
-        host_mapped: every per-env buffer (state, obs, reward, done, episode statistics) is pinned host memory,
+        host_mapped: every per-call buffer (obs, reward, done, status, episode statistics) is pinned host memory,
           which the device addresses directly (unified addressing): the kernels read and write it over PCIe, so a
           host-driven step of a tiny batch is one launch and one stream synchronisation, no copies — the
           single-env facade's mode. `step()` then takes a pinned CPU action tensor and the returned tensors are
@@ -175,6 +186,7 @@ class PikaVecEnv:
             raise _lib.PikaLibraryError("PikaVecEnv runs on CUDA devices only (there is no CPU path)")
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
+        self._dev_index = self.device.index
         self.num_envs = int(num_envs)
         if self.num_envs < 1:
             raise ValueError("num_envs must be >= 1")
@@ -213,7 +225,9 @@ class PikaVecEnv:
 
         self._io_device = torch.device("cpu") if self.host_mapped else self.device
         with torch.cuda.device(self.device):
-            self.state = zeros(_lib.STATE_WORDS * n, torch.int32)
+            # the packed state stays in device memory in every mode (a mapped state would put two PCIe round trips
+            # in front of every frame); host_mapped maps the per-call inputs and outputs only
+            self.state = torch.zeros(_lib.STATE_WORDS * n, dtype=torch.int32, device=self.device)
             self.obs_layout = obs_layout
             if obs_layout == "feature_major":
                 self.obs = zeros((2, int(obs_feature_rows), n), obs_dtype)
@@ -240,6 +254,16 @@ class PikaVecEnv:
                 if self.max_episode_frames > 0:
                     self._truncated_u8 = zeros((n,), torch.uint8)
                     self._ep.truncated_dev = self._truncated_u8.data_ptr()
+            # host_mapped, at most one CTA of envs: the step kernel stores a completion word behind a system-scope
+            # fence, so the host can spin on it (`wait()`) instead of synchronising the stream — half of the latency
+            # of a host-driven single-env step
+            self._np_seq, self._seq_count = None, 0
+            if self.host_mapped and n <= 128:
+                if self._ep is None:
+                    self._ep = _lib.PzEpisodeIo()
+                self._seq = torch.zeros(1, dtype=torch.int32).pin_memory()
+                self._np_seq = self._seq.numpy()
+                self._ep.seq_dev = self._seq.data_ptr()
             _lib.check(
                 self.lib.pz_seed(self.state.data_ptr(), n, self.seed & (2**64 - 1), self.first_env, self._stream()),
                 "pz_seed",
@@ -258,6 +282,7 @@ class PikaVecEnv:
                                   "iterative simulations (identical results, slower)", RuntimeWarning, stacklevel=2)
                 self.tables_ready = rc == 0
         self._renderer = None
+        self._checked_actions, self._checked_ptr = object(), None
         self.frame = 0  # calls issued so far (drives the synthetic action stream of rollout())
         self._action_shape = torch.Size((n, 2))
         self._step_args = None
@@ -316,7 +341,9 @@ class PikaVecEnv:
         The returned tensors are the env's own output buffers, overwritten by the next call.
         `actions` may be None only when both players are computers.
         """
-        if actions is not None:
+        if actions is self._checked_actions:  # the same tensor object as last time (its storage cannot have moved)
+            a_ptr = self._checked_ptr
+        elif actions is not None:
             if actions.dtype != self.action_dtype:
                 raise TypeError(f"actions must be {self.action_dtype} (got {actions.dtype}); "
                                 "pass action_dtype= to the constructor")
@@ -329,10 +356,15 @@ class PikaVecEnv:
             if self.host_mapped and not actions.is_pinned():
                 raise ValueError("host_mapped: actions must live in pinned host memory (tensor.pin_memory())")
             a_ptr = actions.data_ptr()
+            if self.host_mapped:  # is_pinned() asks the driver (1-2 us): remember the verdict for this object
+                self._checked_actions, self._checked_ptr = actions, a_ptr
         else:
             a_ptr = None
         if self._renderer is not None:
             self._renderer.before_call()
+        if self._np_seq is not None:
+            self._seq_count = (self._seq_count + 1) & 0x7FFFFFFF
+            self._ep.seq_value = self._seq_count
         # the small-batch regime is bound by this host path: every constant argument is cached
         # (self._step_args), and the device guard is only entered when another device is current
         args = self._step_args
@@ -340,9 +372,9 @@ class PikaVecEnv:
             args = self._step_args = (self.state.data_ptr(), self.num_envs, self._cfg_ref(), self.obs.data_ptr(),
                                       self.reward.data_ptr(), self.done_u8.data_ptr(), self._stats_ptr(),
                                       self._ep_ref())
-        if torch.cuda.current_device() == self.device.index:
+        if _raw_device() == self._dev_index:
             rc = self.lib.pz_step_ex(args[0], args[1], args[2], a_ptr, args[3], args[4], args[5], args[6], args[7],
-                                     torch.cuda.current_stream().cuda_stream)
+                                     _raw_stream(self._dev_index))
         else:
             with torch.cuda.device(self.device):
                 rc = self.lib.pz_step_ex(args[0], args[1], args[2], a_ptr, args[3], args[4], args[5], args[6],
@@ -353,6 +385,16 @@ class PikaVecEnv:
         if self._renderer is not None:
             self._renderer.after_step()
         return self._step_result
+
+    def wait(self) -> None:
+        """Block until the last step() has written all of its outputs. host_mapped batches of at most 128 envs spin
+        on the kernel's completion word; everything else synchronises the stream."""
+        if self._np_seq is not None and self._seq_count:
+            seq, want = self._np_seq, self._seq_count
+            for _ in range(2_000_000):
+                if seq[0] == want:
+                    return
+        torch.cuda.current_stream(self.device).synchronize()
 
     def rollout(self, K: int, actions: str = "noop", action_seed: int = 0, write_obs: bool = False):
         """K frames in one launch with the state in registers (auto-reset always on).
