@@ -154,8 +154,11 @@ size_t pz_config_bytes(void); /* sizeof(pz_config) in this library */
  * ctypes: ctypes.sizeof(Cfg)): if it differs from pz_config_bytes() nothing is written and PZ_E_ABI returned. */
 int pz_config_init(pz_config *cfg, size_t caller_struct_bytes);
 
-/* Fresh env objects, generator of env i = numpy PCG64(SeedSequence(base_seed + first_env + i)).
- * reset() has not been called. */
+/* Fresh env objects, generator of env i = numpy PCG64(SeedSequence(base_seed + first_env + i)) — protocol S0 of the
+ * parity tests, and what makes trajectories independent of how a batch is sharded (first_env = the shard's first
+ * global index). Consecutive base seeds therefore give SHIFTED, almost identical batches (env i of seed s + 1 is env
+ * i + 1 of seed s): independent replicates must use base seeds at least the total batch size apart, or explicit
+ * per-env seeds (pz_seed_array). reset() has not been called. */
 int pz_seed(int32_t *state_dev, int64_t n, uint64_t base_seed, uint64_t first_env, void *stream);
 /* Same with explicit per-env seeds (device array of n uint64). */
 int pz_seed_array(int32_t *state_dev, int64_t n, const uint64_t *seeds_dev, void *stream);

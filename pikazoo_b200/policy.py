@@ -17,7 +17,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from .vec_env import PikaVecEnv
+from .vec_env import PikaVecEnv, _raw_device, _raw_stream
 
 _ACT_CODES = {torch.int32: _lib.ACT_I32, torch.int64: _lib.ACT_I64, torch.uint8: _lib.ACT_U8}
 
@@ -206,8 +206,8 @@ class FusedActor:
         else:
             dev = obs.device
             step = self.step & (2**64 - 1)
-            if torch.cuda.current_device() == dev.index:
-                rc = self._lib.pz_policy_mlp_act(*self._head, step, *self._tail, torch.cuda.current_stream().cuda_stream)
+            if _raw_device() == dev.index:
+                rc = self._lib.pz_policy_mlp_act(*self._head, step, *self._tail, _raw_stream(dev.index))
             else:
                 with torch.cuda.device(dev):
                     rc = self._lib.pz_policy_mlp_act(*self._head, step, *self._tail,

@@ -13,7 +13,9 @@ Semantics of one `step(actions)` call per env (NEXT-STEP auto-
   * env terminated by an earlier call and autoreset=True: exactly one reference `env.reset()`
     on the same object (carry-over semantics), obs = reset obs, reward 0, done False, action ignored;
   * env terminated and autoreset=False: no-op, obs re-emitted, reward 0, done True.
-Env i's random stream is numpy `Generator(PCG64(seed + first_env + i))` (protocol S0).
+Env i's random stream is numpy `Generator(PCG64(seed + first_env + i))` (protocol S0): seed s + 1 is the
+batch of seed s shifted by one env, so independent replicates must space their seeds by at least the total
+number of envs (e.g. seed = replicate * total_envs).
 """
 
 from __future__ import annotations
