@@ -758,9 +758,10 @@ def run_b200_arm(args):
             "traffic_source": traffic_note,
             "write_probe": wprobe,
             "note": "frac (425 B convention, SURVEY 8(d)) can exceed 1: the convention counts the 64 B of PCG64 words "
-                    "every frame, the kernel touches them only on frames that draw and moves 361 B; of those, the "
-                    "state lines largely stay resident in the 126 MB L2 between launches, so DRAM sees `traffic`. "
-                    "`peak` is a read+write copy; the kernel is 87 % stores: see write_probe for that ceiling",
+                    "every frame, the kernel touches them only on frames that draw and moves 361 B. `traffic` is the "
+                    "DRAM traffic of a launch between its neighbours (ncu --cache-control none, steady state): the state "
+                    "words do not survive in L2 between launches (3 % hit rate), so DRAM sees nearly everything. `peak` is "
+                    "a read+write copy; the kernel is 88 % stores: see write_probe for that ceiling",
             "peak_source": peak_src}
         line = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
