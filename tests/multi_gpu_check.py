@@ -30,7 +30,7 @@ def main():
     mine.reset(), whole.reset()
     for _ in range(96):
         acts = torch.randint(0, 18, (total, 2), generator=g, device=dev, dtype=torch.int32)
-        mine.step(acts[first:first + count].contiguous())
+        mine.step(acts[first:first + count].clone())  # (a fresh tensor: the library wants 16-byte aligned actions)
         whole.step(acts)
     for _ in range(3):
         mine.rollout(64, actions="synth", action_seed=5)
