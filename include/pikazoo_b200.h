@@ -265,6 +265,20 @@ int pz_host_step(pz_host_ctx *ctx, const void *actions_host, void *obs_host, voi
 int pz_host_step_begin(pz_host_ctx *ctx, const void *actions_host, void *obs_host, void *reward_host,
                        uint8_t *done_host, uint8_t *status_host);
 int pz_host_step_end(pz_host_ctx *ctx);
+/* Compact WIRE format, transparent to the caller: the context keeps delivering the arrays its config names (the
+ * reference's int32 — or int16 — obs [n][2][35], reward [n][2], done [n]), but what crosses the link per env is
+ * player_1's int16 row + the status byte (71 B instead of 289 B); `threads` host threads (<= 0: one per hardware
+ * thread) rebuild the caller's arrays chunk by chunk while the following chunks are still on the link (player_2's row
+ * is a block permutation of player_1's, pikazoo_env.py:585-586; reward / done follow from the status byte when no
+ * reward wrapper is fused — shaped rewards travel as they are). Needs an integer env-major observation config
+ * (PZ_E_BADCONFIG otherwise). Call between steps; PZ_WIRE_NATIVE switches back. Results are identical in both modes. */
+enum { PZ_WIRE_NATIVE = 0, PZ_WIRE_COMPACT = 1 };
+int pz_host_set_wire(pz_host_ctx *ctx, int32_t mode, int32_t threads);
+/* The host-side expansion by itself (pure host code, no device needed), for callers that receive the compact format
+ * themselves (cfg->obs_layout = PZ_LAYOUT_ENV_MAJOR_SHARED + status bytes): rows int16 [n][35], status uint8 [n] ->
+ * obs <int32|int16> [n][2][35], reward <f32|f64> [n][2], done uint8 [n]; any output may be NULL. */
+int pz_wire_expand(const int16_t *rows, const uint8_t *status, int64_t n, int32_t obs_dtype, void *obs,
+                   int32_t reward_dtype, void *reward, uint8_t *done);
 size_t pz_obs_elem_bytes(int32_t obs_dtype); /* 0 for an unknown code */
 int pz_host_stats(pz_host_ctx *ctx, int64_t stats_host[PZ_NUM_STATS]);
 int32_t *pz_host_state_dev(pz_host_ctx *ctx);

@@ -149,6 +149,10 @@ def load() -> ctypes.CDLL:
     L.pz_host_step_end.restype = ctypes.c_int
     L.pz_obs_player2_index.argtypes = [ctypes.c_int]
     L.pz_obs_player2_index.restype = ctypes.c_int
+    L.pz_host_set_wire.argtypes = [vp, i32, i32]
+    L.pz_host_set_wire.restype = ctypes.c_int
+    L.pz_wire_expand.argtypes = [vp, vp, i64, i32, vp, i32, vp, vp]
+    L.pz_wire_expand.restype = ctypes.c_int
     L.pz_host_stats.argtypes = [vp, vp]
     L.pz_host_stats.restype = ctypes.c_int
     L.pz_host_state_dev.argtypes = [vp]

@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_PATH = os.path.join(CSRC, "libpikazoo_b200.so")
-SOURCES = ["pz_kernels.cu", "pz_host.cu", "pz_policy.cu", "pz_policy_tc.cu", "pz_rollout_policy.cu", "pz_render.cu", "pz_step_ai0.cu", "pz_step_ai1.cu", "pz_step_ai2.cu", "pz_step_ai3.cu"]
+SOURCES = ["pz_kernels.cu", "pz_host.cu", "pz_policy.cu", "pz_policy_tc.cu", "pz_rollout_policy.cu", "pz_render.cu", "pz_wire.cpp", "pz_step_ai0.cu", "pz_step_ai1.cu", "pz_step_ai2.cu", "pz_step_ai3.cu"]
 HEADERS = ["pz_state.cuh", "pz_rng.cuh", "pz_physics.cuh", "pz_kernels.cuh", "pz_device.cuh", "pz_policy.cuh", "pz_tcgen05.cuh", "pz_step_inst.inc"]
 
 

@@ -114,3 +114,76 @@ def test_host_path_compact_two_phase(cuda_lib, n, chunks):
     _lib.check(L.pz_host_stats(ctx, stats), "pz_host_stats")
     assert stats[0] == n * steps
     L.pz_host_destroy(ctx)
+
+
+_SHAPED = ((0.1, 0.2, 0.3, 0.4, -0.1, -0.2, -0.3, -0.4), 216, 176)
+
+
+@pytest.mark.parametrize("n,chunks,threads,obs_dt,rew_dt,kw", [
+    (5003, 4, 3, torch.int32, torch.float32, dict(winning_score=2, serve="random")),
+    (300_000, 0, 0, torch.int32, torch.float32, dict(winning_score=1, serve="winner")),
+    (1000, 2, 2, torch.int16, torch.float64, dict(winning_score=3, serve="alternate", is_player2_computer=True)),
+    (777, 1, 5, torch.int32, torch.float64, dict(winning_score=2, serve="winner", reward_by_ball_position=_SHAPED)),
+    (9, 1, 16, torch.int32, torch.float32, dict(winning_score=1, serve="winner", max_episode_frames=40)),
+])
+def test_host_path_wire_compact_is_transparent(cuda_lib, n, chunks, threads, obs_dt, rew_dt, kw):
+    """pz_host_set_wire(PZ_WIRE_COMPACT): the caller's arrays keep the reference's dtypes and layout (int32 obs
+    [n,2,35], reward [n,2], done [n]) while 71 B per env cross the link; host threads rebuild them. Every array ==
+    the oracle's on every step (shaped rewards travel natively), switching the mode mid-run changes nothing."""
+    import pikazoo_b200
+    from pikazoo_b200 import _lib
+
+    cfg = pikazoo_b200.make_config(obs_dtype=obs_dt, reward_dtype=rew_dt, **kw)
+    L = _lib.load()
+    ctx = ctypes.c_void_p()
+    _lib.check(L.pz_host_create(ctypes.byref(ctx), n, ctypes.byref(cfg), 31, 0, chunks), "pz_host_create")
+    _lib.check(L.pz_host_set_wire(ctx, 1, threads), "pz_host_set_wire")
+    orc = po.OracleVecEnv(n, seed=31, **kw)
+    np_obs = np.int32 if obs_dt == torch.int32 else np.int16
+    obs_h = torch.full((n, 2, 35), -7, dtype=obs_dt).pin_memory()
+    rew_h = torch.full((n, 2), 9.0, dtype=rew_dt).pin_memory()
+    done_h = torch.full((n,), 9, dtype=torch.uint8).pin_memory()
+    st_h = torch.full((n,), 255, dtype=torch.uint8).pin_memory()
+    _lib.check(L.pz_host_reset(ctx, obs_h.data_ptr()), "pz_host_reset")
+    assert np.array_equal(obs_h.numpy(), orc.reset().astype(np_obs))
+    steps = 100 if n > 100_000 else 300
+    dones = 0
+    for t in range(steps):
+        if t == steps // 2:  # back to the native format for a while: the state lives in the context, not the format
+            _lib.check(L.pz_host_set_wire(ctx, 0, 0), "pz_host_set_wire")
+        if t == steps // 2 + 20:
+            _lib.check(L.pz_host_set_wire(ctx, 1, threads), "pz_host_set_wire")
+        a = synth_actions_numpy(6, 0, n, t, 18).astype(np.int32)
+        a_h = torch.from_numpy(a).pin_memory()
+        _lib.check(L.pz_host_step_begin(ctx, a_h.data_ptr(), obs_h.data_ptr(), rew_h.data_ptr(), done_h.data_ptr(),
+                                        st_h.data_ptr() if t % 3 == 0 else None), "pz_host_step_begin")
+        o_obs, o_rew, o_done = orc.step(a)
+        _lib.check(L.pz_host_step_end(ctx), "pz_host_step_end")
+        assert np.array_equal(obs_h.numpy(), o_obs.astype(np_obs)), t
+        assert np.array_equal(rew_h.numpy().view(np.uint8), o_rew.astype(rew_h.numpy().dtype).view(np.uint8)), t
+        assert np.array_equal(done_h.numpy(), o_done.astype(np.uint8)), t
+        if t % 3 == 0:
+            assert np.array_equal((st_h.numpy() >> 2) & 1, o_done), t
+        dones += int(o_done.sum())
+    assert dones > 0
+    # pz_host_step (one call) goes through the same path
+    a = synth_actions_numpy(6, 0, n, steps, 18).astype(np.int32)
+    a_h = torch.from_numpy(a).pin_memory()
+    _lib.check(L.pz_host_step(ctx, a_h.data_ptr(), obs_h.data_ptr(), rew_h.data_ptr(), done_h.data_ptr()), "pz_host_step")
+    o_obs, o_rew, o_done = orc.step(a)
+    assert np.array_equal(obs_h.numpy(), o_obs.astype(np_obs)) and np.array_equal(done_h.numpy(), o_done.astype(np.uint8))
+    L.pz_host_destroy(ctx)
+
+
+def test_host_wire_needs_integer_env_major_rows(cuda_lib):
+    import pikazoo_b200
+    from pikazoo_b200 import _lib
+
+    L = _lib.load()
+    for kw in (dict(obs_dtype=torch.float32, normalize_observation=True), dict(obs_dtype=torch.int16, obs_layout="shared")):
+        cfg = pikazoo_b200.make_config(**kw)
+        ctx = ctypes.c_void_p()
+        _lib.check(L.pz_host_create(ctypes.byref(ctx), 256, ctypes.byref(cfg), 1, 0, 1), "pz_host_create")
+        assert L.pz_host_set_wire(ctx, 1, 2) == -2
+        assert L.pz_host_set_wire(ctx, 7, 2) == -1
+        L.pz_host_destroy(ctx)
