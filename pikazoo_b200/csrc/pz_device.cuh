@@ -82,6 +82,18 @@ __device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
     return *reinterpret_cast<const uint32_t *>(&h);
 }
 
+// Element K of the distinct values as the 16 bits of a float16 / bfloat16. The twelve one-hot and flag elements
+// (states, power-hit key, ball power hit: bounds [0, 1], so normalised or not they are 0.0 or 1.0) are a select of
+// the constant — no int -> float -> 2-byte conversion chain.
+template <int DT, int K>
+__device__ __forceinline__ unsigned short obs_bits16(const int (&u)[35], bool normalize) {
+    static_assert(DT == PZ_OBS_F16 || DT == PZ_OBS_BF16, "2-byte floating-point rows");
+    constexpr bool flag = (K < 26 && (K % 13) >= 7) || K == 34;
+    if (flag) return (unsigned short)(u[K] ? (DT == PZ_OBS_F16 ? 0x3C00u : 0x3F80u) : 0u);
+    const float f = obs_float<float, K>(u, normalize);
+    return DT == PZ_OBS_F16 ? __half_as_ushort(__float2half_rn(f)) : __bfloat16_as_ushort(__float2bfloat16_rn(f));
+}
+
 // The 70 elements of one env's row, written with the widest naturally aligned stores
 // (row addresses are multiples of 70 * element size, so 8 / 4 / 16-byte aligned).
 template <int DT>
@@ -205,18 +217,14 @@ __device__ __forceinline__ void emit_obs_feature_major(const Env &e, bool valid,
     auto emit = [&](auto K) {
         constexpr int k = decltype(K)::value;
         T v;
-        if (DT == PZ_OBS_I32 || DT == PZ_OBS_I16) {
+        if constexpr (DT == PZ_OBS_I32 || DT == PZ_OBS_I16)
             v = (T)u[k];
-        } else if (DT == PZ_OBS_F64) {
+        else if constexpr (DT == PZ_OBS_F64)
             v = (T)obs_float<double, k>(u, normalize);
-        } else {
-            const float f = obs_float<float, k>(u, normalize);
-            if (DT == PZ_OBS_F32)
-                v = (T)f;
-            else
-                v = (T)(DT == PZ_OBS_F16 ? __half_as_ushort(__float2half_rn(f))
-                                         : __bfloat16_as_ushort(__float2bfloat16_rn(f)));
-        }
+        else if constexpr (DT == PZ_OBS_F32)
+            v = (T)obs_float<float, k>(u, normalize);
+        else
+            v = (T)obs_bits16<DT, k>(u, normalize);
         constexpr int k1 = k < 13 ? k + 13 : (k < 26 ? k - 13 : k);  // row of value k in agent 1's observation
         __stcs(p0 + (int64_t)k * ld, v);
         __stcs(p1 + (int64_t)k1 * ld, v);
@@ -242,30 +250,40 @@ __device__ __forceinline__ void emit_obs_feature_major_staged(const Env &e, bool
     auto put = [&](auto K) {
         constexpr int k = decltype(K)::value;
         T v;
-        if (DT == PZ_OBS_I32 || DT == PZ_OBS_I16) {
+        if constexpr (DT == PZ_OBS_I32 || DT == PZ_OBS_I16)
             v = (T)u[k];
-        } else {
-            const float f = obs_float<float, k>(u, normalize);
-            if (DT == PZ_OBS_F32)
-                v = (T)f;
-            else
-                v = (T)(DT == PZ_OBS_F16 ? __half_as_ushort(__float2half_rn(f))
-                                         : __bfloat16_as_ushort(__float2bfloat16_rn(f)));
-        }
+        else if constexpr (DT == PZ_OBS_F32)
+            v = (T)obs_float<float, k>(u, normalize);
+        else
+            v = (T)obs_bits16<DT, k>(u, normalize);
         stage[k][tid] = v;
     };
     [&]<int... K>(std::integer_sequence<int, K...>) { (put(std::integral_constant<int, K>{}), ...); }
     (std::make_integer_sequence<int, 35>{});
     __syncthreads();
     using V = typename std::conditional<sizeof(T) == 2, uint2, uint4>::type;  // four elements per lane
-    char *g = reinterpret_cast<char *>(obs);
-#pragma unroll 1
-    for (int k = warp; k < 35; k += kWarps) {
-        const V v = reinterpret_cast<const V *>(stage[k])[lane];
-        const int k1 = k < 13 ? k + 13 : (k < 26 ? k - 13 : k);  // row of value k in agent 1's observation
-        const int64_t col = cta_first + 4 * lane;
-        __stcs(reinterpret_cast<V *>(g + ((int64_t)k * ld + col) * sizeof(T)), v);
-        __stcs(reinterpret_cast<V *>(g + ((int64_t)(rows + k1) * ld + col) * sizeof(T)), v);
+    // Warp w writes rows w, w + 4, ...: row k = w + 4 j goes to agent 0's row k and to agent 1's row k + d(k), d = +13 /
+    // -13 / 0 for the own / opponent / ball block. Unrolled over j the offset d is a compile-time constant except in the
+    // two iterations that straddle a block boundary (k = 12..15, 24..27), and each address is ONE 32 x 32 + 64-bit
+    // multiply-add on a base computed once (the rolled loop with its 64-bit index arithmetic was 15 % of this kernel's
+    // instructions, 22 per row).
+    const char *srow = reinterpret_cast<const char *>(stage) + (size_t)warp * kThreads * sizeof(T) + lane * sizeof(V);
+    const uint32_t ldb = (uint32_t)ld * (uint32_t)sizeof(T);  // bytes per row (the caller checked ld <= 2^28)
+    uint64_t g = reinterpret_cast<uint64_t>(obs) + ((int64_t)warp * ld + cta_first + 4 * lane) * (int64_t)sizeof(T);
+    uint64_t g1 = g + (uint64_t)(uint32_t)rows * ldb;  // agent 1's copy
+    asm volatile("" : "+l"(g), "+l"(g1));  // two materialised bases: every address below is one IMAD.WIDE on one of them
+#pragma unroll
+    for (int j = 0; j < (35 + kWarps - 1) / kWarps; j++) {
+        const int k = warp + kWarps * j;
+        if (kWarps * j + kWarps - 1 >= 35 && k >= 35) break;  // only the last iteration is ragged
+        const V v = *reinterpret_cast<const V *>(srow + (size_t)j * kWarps * kThreads * sizeof(T));
+        int d;  // agent 1's row of value k, minus k
+        if (kWarps * j + kWarps - 1 < 13) d = 13;
+        else if (kWarps * j >= 13 && kWarps * j + kWarps - 1 < 26) d = -13;
+        else if (kWarps * j >= 26) d = 0;
+        else d = k < 13 ? 13 : (k < 26 ? -13 : 0);
+        __stcs(reinterpret_cast<V *>(g + (uint64_t)(uint32_t)(kWarps * j) * ldb), v);
+        __stcs(reinterpret_cast<V *>(g1 + (int64_t)(kWarps * j + d) * (int64_t)ldb), v);
     }
 }
 
@@ -450,14 +468,13 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
     d.r.dirty = false;
     Env e;
     int a1 = 0, a2 = 0;
-    if (valid) {
-        load_env(e, d.s, i);
-        if (P.actions) load_actions(P, i, a1, a2);
-        if (AI_MASK != 0) rng_load(d.r, d.s, i);  // computer players draw on most frames
-    } else {
-        fresh_env(e);
-        e.game_ended = 1;
-    }
+    // Lanes past the end of a ragged last warp read the last env of the range (a duplicate load) and do nothing with
+    // it — every effect below is gated by `valid`. (Giving them a fresh_env instead cost every warp the merge of its 45
+    // fields: 3 % of the kernel's instructions.)
+    const int64_t il = valid ? i : P.end - 1;
+    load_env(e, d.s, il);
+    if (P.actions) load_actions(P, il, a1, a2);
+    if (AI_MASK != 0) rng_load(d.r, d.s, il);  // computer players draw on most frames
 
     const bool over = e.game_ended || episode_truncated(P, e);
     const bool run = valid && !over;
@@ -468,16 +485,16 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
     bool bad = false;
     if (run) {
         bool bad1, bad2;
-        uint32_t k1, k2;
+        Input in1, in2;
         if (P.simplify) {
-            k1 = decode_keys<0, true>(a1, bad1);
-            k2 = decode_keys<1, true>(a2, bad2);
+            in1 = decode_input<0, true>(a1, e.p[0], bad1);
+            in2 = decode_input<1, true>(a2, e.p[1], bad2);
         } else {
-            k1 = decode_keys<0, false>(a1, bad1);
-            k2 = decode_keys<1, false>(a2, bad2);
+            in1 = decode_input<0, false>(a1, e.p[0], bad1);
+            in2 = decode_input<1, false>(a2, e.p[1], bad2);
         }
         bad = bad1 || bad2;
-        base = step_frame<AI_MASK>(mask, e, d, P.cfg, k1, k2, stage[warp]);
+        base = step_frame_inputs<AI_MASK>(mask, e, d, P.cfg, in1, in2, stage[warp]);
     } else if (do_reset) {
         reset_env(e, d, P.cfg);
     }
@@ -492,7 +509,8 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
         else {
             bool staged = false;
             if constexpr (kFmStaged) {
-                if ((i - threadIdx.x) + kThreads <= P.end && (P.n & 3) == 0) {  // CTA-uniform
+                // CTA-uniform: a full tile, 4-element-aligned rows, row pitch in bytes below 2^32
+                if ((i - threadIdx.x) + kThreads <= P.end && (P.n & 3) == 0 && P.n <= (int64_t(1) << 28)) {
                     emit_obs_feature_major_staged<OBS_DT>(e, P.normalize, P.obs, i - threadIdx.x, P.n, P.obs_rows, fm_stage);
                     staged = true;
                 }

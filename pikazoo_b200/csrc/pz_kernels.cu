@@ -91,20 +91,21 @@ __global__ void __maxnreg__(PZ_ROLLOUT_MAXNREG) pz_rollout_kernel(const __grid_c
         const bool run = valid && !e.game_ended && !episode_truncated(P, e);
         const unsigned mask = __ballot_sync(kFullMask, run);
         if (run) {
-            uint32_t k1 = 0, k2 = 0;
+            int a1 = 0, a2 = 0;  // PZ_ACTIONS_NOOP
             if (P.action_source == PZ_ACTIONS_SYNTH) {
-                bool b1, b2;
-                const int a1 = synth_action(P.action_seed, genv, P.frame0 + (uint64_t)k, 0, n_actions);
-                const int a2 = synth_action(P.action_seed, genv, P.frame0 + (uint64_t)k, 1, n_actions);
-                if (P.simplify) {
-                    k1 = decode_keys<0, true>(a1, b1);
-                    k2 = decode_keys<1, true>(a2, b2);
-                } else {
-                    k1 = decode_keys<0, false>(a1, b1);
-                    k2 = decode_keys<1, false>(a2, b2);
-                }
+                a1 = synth_action(P.action_seed, genv, P.frame0 + (uint64_t)k, 0, n_actions);
+                a2 = synth_action(P.action_seed, genv, P.frame0 + (uint64_t)k, 1, n_actions);
             }
-            step_frame<AI_MASK>(mask, e, d, P.cfg, k1, k2, stage[warp]);
+            bool b1, b2;
+            Input in1, in2;
+            if (P.simplify) {
+                in1 = decode_input<0, true>(a1, e.p[0], b1);
+                in2 = decode_input<1, true>(a2, e.p[1], b2);
+            } else {
+                in1 = decode_input<0, false>(a1, e.p[0], b1);
+                in2 = decode_input<1, false>(a2, e.p[1], b2);
+            }
+            step_frame_inputs<AI_MASK>(mask, e, d, P.cfg, in1, in2, stage[warp]);
             if (e.game_ended) {
                 atomicAdd(s_stats + PZ_STAT_EPISODES, 1ULL);
                 atomicAdd(s_stats + PZ_STAT_EPISODE_FRAMES, (unsigned long long)e.ep_frames);

@@ -99,6 +99,10 @@ __host__ __device__ constexpr uint64_t pack_keys_13(int agent) {
     return v;
 }
 
+struct Input {
+    int xdir, ydir, power;
+};
+
 // Returns the 5 key bits of `action` for player I; *bad is set when the action is outside
 // the action space (the reference would raise IndexError; here it is counted and treated as 0).
 template <int I, bool SIMPLIFY>
@@ -116,9 +120,6 @@ __device__ __forceinline__ uint32_t decode_keys(int action, bool &bad) {
     }
 }
 
-struct Input {
-    int xdir, ydir, power;
-};
 
 // PikaUserInput.get_input, physics.py:59-99 (rows are 5 wide: down_right_key is None)
 __device__ __forceinline__ Input get_input(Player &p, uint32_t keys) {
@@ -127,6 +128,35 @@ __device__ __forceinline__ Input get_input(Player &p, uint32_t keys) {
     in.ydir = (keys & kU) ? -1 : ((keys & kD) ? 1 : 0);
     int down = (keys & kP) ? 1 : 0;
     in.power = (down && !p.keyprev) ? 1 : 0;
+    p.keyprev = down;
+    return in;
+}
+
+// action -> Input in one go (action_key_map + get_input): five 18-bit masks, one per key, bit a = "action a holds
+// the key" — a shift and an AND per key instead of a 64-bit table shift, its select and the key-bit tests of
+// get_input (the two decodes were 6-7 % of a step kernel's instructions). No action holds left AND right or up AND
+// down, so the directions are differences of bits. Identical to get_input(p, decode_keys(action)) for every action,
+// in and out of range (tests/test_device_code_on_host.py).
+template <int I, bool SIMPLIFY>
+__host__ __device__ constexpr uint32_t action_mask(uint32_t key) {
+    uint32_t m = 0;
+    for (int a = 0; a < (SIMPLIFY ? 13 : 18); a++)
+        if (kKeyMap[SIMPLIFY ? kSimplify[I][a] : a] & key) m |= 1u << a;
+    return m;
+}
+template <int I, bool SIMPLIFY>
+__device__ __forceinline__ Input decode_input(int action, Player &p, bool &bad) {
+    constexpr int n_actions = SIMPLIFY ? 13 : 18;
+    constexpr uint32_t mL = action_mask<I, SIMPLIFY>(kL), mR = action_mask<I, SIMPLIFY>(kR),
+                       mU = action_mask<I, SIMPLIFY>(kU), mD = action_mask<I, SIMPLIFY>(kD),
+                       mP = action_mask<I, SIMPLIFY>(kP);
+    bad = (unsigned)action >= (unsigned)n_actions;
+    const uint32_t a = bad ? 0u : (uint32_t)action;  // out of range: counted, no key held
+    Input in;
+    in.xdir = (int)((mR >> a) & 1u) - (int)((mL >> a) & 1u);
+    in.ydir = (int)((mD >> a) & 1u) - (int)((mU >> a) & 1u);
+    const int down = (int)((mP >> a) & 1u);
+    in.power = down & (p.keyprev ^ 1);
     p.keyprev = down;
     return in;
 }

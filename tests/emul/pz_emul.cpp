@@ -54,8 +54,8 @@ struct Batch {
 };
 
 template <int AI_MASK>
-int step_one(Env &e, DrawCtx &d, const StepCfg &c, uint32_t k1, uint32_t k2, int *scratch) {
-    return step_frame<AI_MASK>(1u, e, d, c, k1, k2, scratch);
+int step_one(Env &e, DrawCtx &d, const StepCfg &c, Input in1, Input in2, int *scratch) {
+    return step_frame_inputs<AI_MASK>(1u, e, d, c, in1, in2, scratch);
 }
 
 }  // namespace
@@ -63,6 +63,27 @@ int step_one(Env &e, DrawCtx &d, const StepCfg &c, uint32_t k1, uint32_t k2, int
 extern "C" {
 
 int emul_state_words() { return 17; }
+
+// decode_input (the kernels' one-step decode) against get_input(decode_keys) (the table form the policy rollout
+// pre-decodes from): out[0..4] = xdir, ydir, power, keyprev after, bad of the former, out[5..9] of the latter
+void emul_decode_both(int agent, int simplify, int action, int keyprev, int32_t *out) {
+    for (int form = 0; form < 2; form++) {
+        Player p = {};
+        p.keyprev = keyprev;
+        bool bad = false;
+        Input in;
+        if (form == 0) {
+            in = agent == 0 ? (simplify ? decode_input<0, true>(action, p, bad) : decode_input<0, false>(action, p, bad))
+                            : (simplify ? decode_input<1, true>(action, p, bad) : decode_input<1, false>(action, p, bad));
+        } else {
+            const uint32_t keys = agent == 0 ? (simplify ? decode_keys<0, true>(action, bad) : decode_keys<0, false>(action, bad))
+                                             : (simplify ? decode_keys<1, true>(action, bad) : decode_keys<1, false>(action, bad));
+            in = get_input(p, keys);
+        }
+        int32_t *o = out + 5 * form;
+        o[0] = in.xdir, o[1] = in.ydir, o[2] = in.power, o[3] = p.keyprev, o[4] = bad;
+    }
+}
 
 // unpacked int32[n][53] -> packed SoA (same conversion as pz_import_state)
 void emul_import(int32_t *packed, int64_t n, const int32_t *unpacked) {
@@ -133,13 +154,13 @@ void emul_step(int32_t *packed, int64_t n, int winning_score, int serve, int ai_
         } else if (!e.game_ended) {
             const int a1 = actions ? actions[2 * i] : 0, a2 = actions ? actions[2 * i + 1] : 0;
             bool b1, b2;
-            uint32_t k1, k2;
+            Input k1, k2;  // the kernels' decode: action -> Input in one go
             if (simplify) {
-                k1 = decode_keys<0, true>(a1, b1);
-                k2 = decode_keys<1, true>(a2, b2);
+                k1 = decode_input<0, true>(a1, e.p[0], b1);
+                k2 = decode_input<1, true>(a2, e.p[1], b2);
             } else {
-                k1 = decode_keys<0, false>(a1, b1);
-                k2 = decode_keys<1, false>(a2, b2);
+                k1 = decode_input<0, false>(a1, e.p[0], b1);
+                k2 = decode_input<1, false>(a2, e.p[1], b2);
             }
             if (ai_mask != 0) rng_load(d.r, s, i);
             switch (ai_mask) {

@@ -317,3 +317,18 @@ def test_policy_gumbel_keys_match_numpy_restatement(emul):
         emul.emul_policy_gumbel_keys(n, 18, _p(logits), seed, step, first, _p(keys))
         want = logits + gumbel_noise_reference(seed, step, first, n, 18)
         assert np.abs(keys - want).max() < 2e-5
+
+
+def test_one_step_decode_equals_key_table_decode(emul):
+    """decode_input (five per-key action masks: what the step and rollout kernels run) == get_input(decode_keys(.))
+    (the 5-bit key table of action_key_map, pikazoo_env.py:119-141 + PikaUserInput.get_input, physics.py:59-99) for
+    every action in and out of range, both agents, with and without SimplifyAction, both previous key states."""
+    out = np.zeros(10, dtype=np.int32)
+    for agent in (0, 1):
+        for simplify in (0, 1):
+            for action in list(range(-3, 40)) + [2**31 - 1, -2**31, 255, 1000]:
+                for keyprev in (0, 1):
+                    emul.emul_decode_both(agent, simplify, ctypes.c_int(action), keyprev, _p(out))
+                    assert np.array_equal(out[:5], out[5:]), (agent, simplify, action, keyprev, out)
+                    n = 13 if simplify else 18
+                    assert out[4] == (0 if 0 <= action < n else 1)
