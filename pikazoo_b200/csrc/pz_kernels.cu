@@ -21,9 +21,14 @@
 // occupancy, and the frame loop is latency-bound (issue slots 65 % busy at 20 warps per SM): a tighter cap
 // with a few spills to L1 wins. Measured per 64 frames x 1 M envs, computer vs computer (B200):
 // 104 regs 2.69 ms | 96 (no spills, 20 warps) 2.36 | 88 2.53 | 80 2.36 | 72 (188 B of spill loads, 28 warps) 2.23 |
-// 64 2.23-2.26 | 56 2.43 | 48 3.09.
+// 64 2.23-2.26 | 56 2.43 | 48 3.09. Round 2, steady state, after the PLAIN specialisation and the straight-line
+// power-hit look-ups: 64 2.118 | 72 2.040 | 80 2.012 ms with two computer players, while the kernel without
+// computer players (synthetic actions) prefers 72 (1.027 against 1.054 ms at 80).
 #ifndef PZ_ROLLOUT_MAXNREG
 #define PZ_ROLLOUT_MAXNREG 72
+#endif
+#ifndef PZ_ROLLOUT_MAXNREG_AI
+#define PZ_ROLLOUT_MAXNREG_AI 80
 #endif
 
 namespace pz {
@@ -58,8 +63,10 @@ __device__ __noinline__ bool emit_obs_cold(int32_t *state, int64_t n, int64_t en
 #endif
 constexpr int kRolloutThreads = PZ_ROLLOUT_THREADS;
 
-template <int AI_MASK>
-__global__ void __maxnreg__(PZ_ROLLOUT_MAXNREG) pz_rollout_kernel(const __grid_constant__ KParams P) {
+// PLAIN: no-op actions and no frame cap (configs[3], and every pre-advance) — the frame loop then carries neither the
+// action stream and its decode nor the two truncation tests.
+template <int AI_MASK, bool PLAIN>
+__global__ void __maxnreg__(AI_MASK == 3 ? PZ_ROLLOUT_MAXNREG_AI : PZ_ROLLOUT_MAXNREG) pz_rollout_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(16) int stage[kRolloutThreads / 32][kAiScratchInts];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t i = P.begin + (int64_t)blockIdx.x * kRolloutThreads + threadIdx.x;
@@ -88,22 +95,28 @@ __global__ void __maxnreg__(PZ_ROLLOUT_MAXNREG) pz_rollout_kernel(const __grid_c
 
 #pragma unroll 1
     for (int k = 0; k < P.K; k++) {
-        const bool run = valid && !e.game_ended && !episode_truncated(P, e);
+        const bool run = valid && !e.game_ended && (PLAIN || !episode_truncated(P, e));
         const unsigned mask = __ballot_sync(kFullMask, run);
         if (run) {
-            int a1 = 0, a2 = 0;  // PZ_ACTIONS_NOOP
-            if (P.action_source == PZ_ACTIONS_SYNTH) {
-                a1 = synth_action(P.action_seed, genv, P.frame0 + (uint64_t)k, 0, n_actions);
-                a2 = synth_action(P.action_seed, genv, P.frame0 + (uint64_t)k, 1, n_actions);
-            }
-            bool b1, b2;
             Input in1, in2;
-            if (P.simplify) {
-                in1 = decode_input<0, true>(a1, e.p[0], b1);
-                in2 = decode_input<1, true>(a2, e.p[1], b2);
+            if (PLAIN) {  // action 0 holds no key (pikazoo_env.py:119-141; SimplifyAction maps 0 to 0)
+                in1.xdir = in1.ydir = in1.power = 0;
+                in2 = in1;
+                e.p[0].keyprev = e.p[1].keyprev = 0;
             } else {
-                in1 = decode_input<0, false>(a1, e.p[0], b1);
-                in2 = decode_input<1, false>(a2, e.p[1], b2);
+                int a1 = 0, a2 = 0;  // PZ_ACTIONS_NOOP
+                if (P.action_source == PZ_ACTIONS_SYNTH) {
+                    a1 = synth_action(P.action_seed, genv, P.frame0 + (uint64_t)k, 0, n_actions);
+                    a2 = synth_action(P.action_seed, genv, P.frame0 + (uint64_t)k, 1, n_actions);
+                }
+                bool b1, b2;
+                if (P.simplify) {
+                    in1 = decode_input<0, true>(a1, e.p[0], b1);
+                    in2 = decode_input<1, true>(a2, e.p[1], b2);
+                } else {
+                    in1 = decode_input<0, false>(a1, e.p[0], b1);
+                    in2 = decode_input<1, false>(a2, e.p[1], b2);
+                }
             }
             step_frame_inputs<AI_MASK>(mask, e, d, P.cfg, in1, in2, stage[warp]);
             if (e.game_ended) {
@@ -112,7 +125,7 @@ __global__ void __maxnreg__(PZ_ROLLOUT_MAXNREG) pz_rollout_kernel(const __grid_c
                 atomicAdd(s_stats + (e.score[0] > e.score[1] ? PZ_STAT_P1_WINS : PZ_STAT_P2_WINS), 1ULL);
                 atomicAdd(s_stats + PZ_STAT_P1_POINTS, (unsigned long long)e.score[0]);
                 atomicAdd(s_stats + PZ_STAT_P2_POINTS, (unsigned long long)e.score[1]);
-            } else if (episode_truncated(P, e)) {
+            } else if (!PLAIN && episode_truncated(P, e)) {
                 atomicAdd(s_stats + PZ_STAT_TRUNCATED, 1ULL);
             }
         } else if (valid) {
@@ -639,12 +652,21 @@ int pz_rollout(int32_t *state_dev, int64_t n, const pz_config *cfg, int32_t K, i
     P.frame0 = frame0;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned rollout_grid = (unsigned)((n + kRolloutThreads - 1) / kRolloutThreads);
+    const bool plain = action_source == PZ_ACTIONS_NOOP && P.max_frames <= 0;
+#define PZ_ROLLOUT_CASE(M)                                                                      \
+    case M:                                                                                     \
+        if (plain)                                                                              \
+            pz_rollout_kernel<M, true><<<rollout_grid, kRolloutThreads, 0, st>>>(P);            \
+        else                                                                                    \
+            pz_rollout_kernel<M, false><<<rollout_grid, kRolloutThreads, 0, st>>>(P);           \
+        break;
     switch (ai_mask(cfg)) {
-        case 0: pz_rollout_kernel<0><<<rollout_grid, kRolloutThreads, 0, st>>>(P); break;
-        case 1: pz_rollout_kernel<1><<<rollout_grid, kRolloutThreads, 0, st>>>(P); break;
-        case 2: pz_rollout_kernel<2><<<rollout_grid, kRolloutThreads, 0, st>>>(P); break;
-        default: pz_rollout_kernel<3><<<rollout_grid, kRolloutThreads, 0, st>>>(P); break;
+        PZ_ROLLOUT_CASE(0)
+        PZ_ROLLOUT_CASE(1)
+        PZ_ROLLOUT_CASE(2)
+        PZ_ROLLOUT_CASE(3)
     }
+#undef PZ_ROLLOUT_CASE
     return launch_status();
 }
 

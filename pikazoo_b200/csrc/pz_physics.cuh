@@ -424,49 +424,28 @@ __device__ __forceinline__ void computer_decide(unsigned mask, Env &e, Ctx &d, c
     const int y_first = search ? (y_draw == 0 ? -1 : 1) : 0;
     const int ayv = iabs(b.yv);
     bool found = false;
-    // memoised: one table load per (searcher, candidate) pair, the pairs of all searching lanes spread
-    // over the lanes of the warp — a searcher alone would run six dependent lookups with one or two lanes
-    // of the warp active. Inputs travel by shuffle, verdicts come back through a byte each in scratch.
+    // memoised: the six candidates are six INDEPENDENT 2-byte loads (x_direction 1, 0 x half_yv0 = +h, 0, -h with
+    // h = |ball yv| * y_first), issued back to back by the searching lane itself and scanned by selects. (Until round 2
+    // the (searcher, candidate) pairs were spread over the lanes of the warp like the iterative simulations below:
+    // five shuffles, a rank table in shared memory and three warp barriers per player and frame cost more than the
+    // 5 / 6 of a warp's lanes that idle through these ~60 straight-line instructions.)
     const bool tab_ok = cfg.tab_power != nullptr && search && ayv <= kTabYv && tab_pos_ok(b.x, b.y);
-    const unsigned tm = __ballot_sync(mask, tab_ok);
-    if (tm) {  // warp-uniform
-        const int lane = threadIdx.x & 31;
-        unsigned char *s_ok = reinterpret_cast<unsigned char *>(scratch);  // [32][8] verdict of candidate c
-        unsigned char *s_lane = s_ok + 256;                                 // [32] lane of the r-th searcher
-        const unsigned lt = (1u << lane) - 1u;
-        if (tab_ok) s_lane[__popc(tm & lt)] = (unsigned char)lane;  // (__fns is a ~40-instruction software loop)
-        __syncwarp(mask);
-        const int total = 6 * __popc(tm), workers = __popc(mask);
-        const int w = __popc(mask & lt);
-#pragma unroll 1
-        for (int base = 0; base < total; base += workers) {
-            const int q = base + w;
-            const bool act = q < total;
-            const int r = act ? q / 6 : 0, c = act ? q - 6 * r : 0;
-            const int src = s_lane[r];
-            const int sx = __shfl_sync(mask, b.x, src), sy = __shfl_sync(mask, b.y, src);
-            const int sa = __shfl_sync(mask, ayv, src), sf = __shfl_sync(mask, y_first, src);
-            const int so = __shfl_sync(mask, o.x, src);
-            if (act) {
-                const int lx = (int)(__ldg(cfg.tab_power + tab_power_index(sx, sy, (c < 3) ? 1 : 0,
-                                                                           sa * sf * (1 - (c % 3)))) & 0x7FFFu);
-                s_ok[src * 8 + c] =
-                    ((lx <= left_boundary || lx >= far_boundary) && iabs(lx - so) > kPlayerLength) ? 1 : 0;
-            }
-        }
-        __syncwarp(mask);
-        if (tab_ok) {
-            const uint2 v = *reinterpret_cast<const uint2 *>(s_ok + lane * 8);
-            const unsigned lo4 = v.x, hi2 = v.y & 0xFFFFu;  // candidates 0..3 | 4..5, one byte each
-            if (lo4 | hi2) {  // the first acceptable candidate in the reference's scan order
-                const int c = lo4 ? ((__ffs((int)lo4) - 1) >> 3) : (4 + ((__ffs((int)hi2) - 1) >> 3));
+    if (tab_ok) {
+        constexpr int kStrideH = kTabNy * kTabNx, kStrideXd = kTabNyv * kStrideH;
+        const uint16_t *t0 = cfg.tab_power + tab_power_index(b.x, b.y, 0, 0);
+        const uint16_t *t1 = t0 + kStrideXd;
+        const int h = ayv * y_first * kStrideH;
+        const int lx[6] = {__ldg(t1 + h) & 0x7FFF, __ldg(t1) & 0x7FFF, __ldg(t1 - h) & 0x7FFF,
+                           __ldg(t0 + h) & 0x7FFF, __ldg(t0) & 0x7FFF, __ldg(t0 - h) & 0x7FFF};
+#pragma unroll
+        for (int c = 5; c >= 0; c--) {  // the first acceptable candidate in the reference's scan order wins
+            if ((lx[c] <= left_boundary || lx[c] >= far_boundary) && iabs(lx[c] - o.x) > kPlayerLength) {
                 in.xdir = (c < 3) ? 1 : 0;
                 in.ydir = y_first * (1 - (c % 3));
                 found = true;
             }
-            search = false;
         }
-        __syncwarp(mask);  // scratch is reused below and by the other player
+        search = false;
     }
     const unsigned sm = __ballot_sync(mask, search);
     if (sm) {  // warp-uniform: lanes outside the memoised domain, or tables off
