@@ -27,6 +27,9 @@
 #ifndef PZ_ROLLOUT_MAXNREG
 #define PZ_ROLLOUT_MAXNREG 72
 #endif
+#ifndef PZ_ROLLOUT_ANIM_LUT
+#define PZ_ROLLOUT_ANIM_LUT true
+#endif
 #ifndef PZ_ROLLOUT_MAXNREG_AI
 #define PZ_ROLLOUT_MAXNREG_AI 80
 #endif
@@ -91,6 +94,9 @@ __global__ void __maxnreg__(AI_MASK == 3 ? PZ_ROLLOUT_MAXNREG_AI : PZ_ROLLOUT_MA
     // above) are what this kernel is short of.
     __shared__ unsigned long long s_stats[PZ_NUM_STATS];
     if (threadIdx.x < PZ_NUM_STATS) s_stats[threadIdx.x] = 0ULL;
+    // the players' sprite animation as a table (pz_physics.cuh:player_animate): 4 KB, filled once for K frames
+    __shared__ uint32_t s_anim[kAnimLutEntries];
+    anim_fill(s_anim, threadIdx.x, kRolloutThreads);
     __syncthreads();
 
 #pragma unroll 1
@@ -118,7 +124,7 @@ __global__ void __maxnreg__(AI_MASK == 3 ? PZ_ROLLOUT_MAXNREG_AI : PZ_ROLLOUT_MA
                     in2 = decode_input<1, false>(a2, e.p[1], b2);
                 }
             }
-            step_frame_inputs<AI_MASK>(mask, e, d, P.cfg, in1, in2, stage[warp]);
+            step_frame_inputs<AI_MASK, DrawCtxT<false>, PZ_ROLLOUT_ANIM_LUT>(mask, e, d, P.cfg, in1, in2, stage[warp], s_anim);
             if (e.game_ended) {
                 atomicAdd(s_stats + PZ_STAT_EPISODES, 1ULL);
                 atomicAdd(s_stats + PZ_STAT_EPISODE_FRAMES, (unsigned long long)e.ep_frames);

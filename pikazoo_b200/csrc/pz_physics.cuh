@@ -492,73 +492,96 @@ __device__ __forceinline__ void computer_decide(unsigned mask, Env &e, Ctx &d, c
 }
 
 // ---- player ------------------------------------------------------------------------------------
-// process_player_movement_and_set_player_position, physics.py:439-564 (after the AI override)
-template <int I>
-__device__ __forceinline__ void player_move(Player &p, const Input &in) {
+// The sprite animation at the end of process_player_movement_and_set_player_position (physics.py:524-552):
+// (state, frame_number, delay_before_next_frame, normal_status_arm_swing_direction) -> the same. A pure function of
+// 3 + 3 + 3 + 1 bits, so the K-frame kernels, where a table pays for its construction, read it from a 1,024-entry
+// table in shared memory that they fill with this very function (anim_entry / anim_lookup below).
+__device__ __forceinline__ void player_animate(int &state, int &frame, int &delay, int &arm) {
+    if (state == 1) {
+        frame = frame >= 2 ? frame - 2 : frame + 1;  // (frame + 1) % 3 for frame in 0..4
+    } else if (state == 2) {
+        if (delay < 1) {
+            frame += 1;
+            if (frame > 4) {
+                frame = 0;
+                state = 1;
+            }
+        } else {
+            delay -= 1;
+        }
+    } else if (state == 0) {
+        delay += 1;
+        if (delay > 3) {
+            delay = 0;
+            const int f = frame + arm;
+            if (f < 0 || f > 4) arm = -arm;
+            frame = frame + arm;
+        }
+    }
+}
+constexpr int kAnimLutEntries = 1024;
+__device__ __forceinline__ int anim_index(int state, int frame, int delay, int arm) {
+    return state + frame * 8 + delay * 64 + (arm + 1) * 256;  // every field is at most 7 (pz_state.cuh), arm is +-1
+}
+// entry = state | frame << 8 | delay << 16 | (int8) arm << 24: a byte each, one PRMT each to take apart
+__device__ __forceinline__ uint32_t anim_entry(int index) {
+    int state = index & 7, frame = (index >> 3) & 7, delay = (index >> 6) & 7, arm = (index & 512) ? 1 : -1;
+    player_animate(state, frame, delay, arm);
+    return (uint32_t)state | ((uint32_t)frame << 8) | ((uint32_t)delay << 16) | ((uint32_t)(arm & 0xFF) << 24);
+}
+__device__ __forceinline__ void anim_fill(uint32_t *lut, int tid, int nthreads) {  // caller synchronises
+    for (int k = tid; k < kAnimLutEntries; k += nthreads) lut[k] = anim_entry(k);
+}
+
+// process_player_movement_and_set_player_position, physics.py:439-564 (after the AI override). Written as selects:
+// the lanes of a warp are in different phases of play, so every side of a branch runs anyway and the branches
+// themselves (and the register moves at their joins) were a fifth of this function. ANIM_LUT: `anim` is the table
+// above in shared memory.
+template <int I, bool ANIM_LUT = false>
+__device__ __forceinline__ void player_move(Player &p, const Input &in, const uint32_t *anim = nullptr) {
     if (p.state == 4) {  // lying down: don't move (:458-462)
         p.lying -= 1;
         if (p.lying < -1) p.state = 0;
         return;
     }
-    const int vx = (p.state < 3) ? in.xdir * 6 : p.dive * 8;  // state < 5 always holds before termination
-    int x = p.x + vx;
     constexpr int lo = I ? kGroundHalfWidth + kPlayerHalfLength : kPlayerHalfLength;
     constexpr int hi = I ? kGroundWidth - kPlayerHalfLength : kGroundHalfWidth - kPlayerHalfLength;
-    p.x = min(max(x, lo), hi);
+    const int vx = (p.state < 3) ? in.xdir * 6 : p.dive * 8;  // state < 5 always holds before termination
+    p.x = min(max(p.x + vx, lo), hi);
 
-    if (p.state < 3 && in.ydir == -1 && p.y == kPlayerGroundY) {  // jump
-        p.yv = -16;
-        p.state = 1;
-        p.frame = 0;
+    const bool jump = p.state < 3 && in.ydir == -1 && p.y == kPlayerGroundY;
+    int state = jump ? 1 : p.state;
+    int yv = jump ? -16 : p.yv;
+    int frame = jump ? 0 : p.frame;
+    const int fy = p.y + yv;  // gravity
+    const bool air = fy < kPlayerGroundY, landing = fy > kPlayerGroundY;  // exactly on the ground: neither (:504-517)
+    yv = air ? yv + 1 : (landing ? 0 : yv);
+    p.y = landing ? kPlayerGroundY : fy;
+    frame = landing ? 0 : frame;
+    const bool dived = landing && state == 3;
+    state = landing ? (dived ? 4 : 0) : state;
+    p.lying = dived ? 3 : p.lying;
+    const bool hit = in.power == 1 && state == 1;                     // power hit
+    const bool dive = in.power == 1 && state == 0 && in.xdir != 0;    // dive
+    int delay = hit ? 5 : p.delay;
+    frame = (hit || dive) ? 0 : frame;
+    state = hit ? 2 : (dive ? 3 : state);
+    p.dive = dive ? in.xdir : p.dive;
+    p.yv = dive ? -5 : yv;
+    int arm = p.arm;
+    if (ANIM_LUT) {
+        const uint32_t v = anim[anim_index(state, frame, delay, arm)];
+        state = (int)(v & 0xFFu);
+        frame = (int)((v >> 8) & 0xFFu);
+        delay = (int)((v >> 16) & 0xFFu);
+        arm = (int)(int8_t)(v >> 24);
+    } else {
+        player_animate(state, frame, delay, arm);
     }
-    const int fy = p.y + p.yv;  // gravity
-    p.y = fy;
-    if (fy < kPlayerGroundY) {
-        p.yv += 1;
-    } else if (fy > kPlayerGroundY) {  // landing
-        p.yv = 0;
-        p.y = kPlayerGroundY;
-        p.frame = 0;
-        if (p.state == 3) {
-            p.state = 4;
-            p.lying = 3;
-        } else {
-            p.state = 0;
-        }
-    }
-    if (in.power == 1) {
-        if (p.state == 1) {  // power hit
-            p.delay = 5;
-            p.frame = 0;
-            p.state = 2;
-        } else if (p.state == 0 && in.xdir != 0) {  // dive
-            p.state = 3;
-            p.frame = 0;
-            p.dive = in.xdir;
-            p.yv = -5;
-        }
-    }
-    if (p.state == 1) {
-        p.frame = p.frame >= 2 ? p.frame - 2 : p.frame + 1;  // (frame + 1) % 3 for frame in 0..4
-    } else if (p.state == 2) {
-        if (p.delay < 1) {
-            p.frame += 1;
-            if (p.frame > 4) {
-                p.frame = 0;
-                p.state = 1;
-            }
-        } else {
-            p.delay -= 1;
-        }
-    } else if (p.state == 0) {
-        p.delay += 1;
-        if (p.delay > 3) {
-            p.delay = 0;
-            const int f = p.frame + p.arm;
-            if (f < 0 || f > 4) p.arm = -p.arm;
-            p.frame = p.frame + p.arm;
-        }
-    }
+    p.state = state;
+    p.frame = frame;
+    p.delay = delay;
+    p.arm = arm;
     // :554-564 (player.game_ended) cannot execute before the env terminates.
 }
 
@@ -599,9 +622,10 @@ __device__ __forceinline__ bool ball_player(Env &e, Ctx &d, const Input &in) {
 // AI_MASK != 0. Returns player_1's base reward (-1, 0, +1).
 // The same with the two players' inputs already decoded (get_input has run: it only touches
 // power_hit_key_is_down_previous, which the new-round block below does not, so the order is immaterial).
-template <int AI_MASK, class Ctx>
+// ANIM_LUT: `anim` is the sprite-animation table in shared memory (anim_fill; the K-frame kernels).
+template <int AI_MASK, class Ctx, bool ANIM_LUT = false>
 __device__ __forceinline__ int step_frame_inputs(unsigned mask, Env &e, Ctx &d, const StepCfg &c, Input in1, Input in2,
-                                                 int *scratch) {
+                                                 int *scratch, const uint32_t *anim = nullptr) {
     if (e.round_ended) {  // :176-180 (game_ended is false here)
         new_round(e, d, c);
         e.round_ended = 0;
@@ -621,9 +645,9 @@ __device__ __forceinline__ int step_frame_inputs(unsigned mask, Env &e, Ctx &d, 
         e.land_ok = 0;  // expected_landing_point_x is not maintained without computer players
     }
     if (AI_MASK & 1) computer_decide<0>(mask, e, d, c, in1, scratch);
-    player_move<0>(e.p[0], in1);
+    player_move<0, ANIM_LUT>(e.p[0], in1, anim);
     if (AI_MASK & 2) computer_decide<1>(mask, e, d, c, in2, scratch);
-    player_move<1>(e.p[1], in2);
+    player_move<1, ANIM_LUT>(e.p[1], in2, anim);
 
     bool recalc = ball_player<0>(e, d, in1);
     recalc |= ball_player<1>(e, d, in2);

@@ -22,12 +22,24 @@ __device__ __forceinline__ void pcg_step(uint64_t &lo, uint64_t &hi, uint64_t in
     hi = m_hi + inc_hi + carry;
 }
 
+// rotr64(x, rot), rot in [0, 63]: a rotation by 32 is a swap of the halves, the rest two funnel shifts (five
+// instructions against the nine of the shift-and-or form)
+__device__ __forceinline__ uint64_t rotr64(uint64_t x, unsigned rot) {
+#ifdef PZ_HOST_EMULATION
+    return (x >> rot) | (x << ((64u - rot) & 63u));
+#else
+    const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32);
+    const bool swap = (rot & 32u) != 0u;
+    const uint32_t a = swap ? xh : xl, b = swap ? xl : xh;
+    return (uint64_t)__funnelshift_r(a, b, rot) | ((uint64_t)__funnelshift_r(b, a, rot) << 32);
+#endif
+}
+
 // pcg64 "setseq XSL-RR 128/64": advance, then output rotr64(hi ^ lo, hi >> 58)
 __device__ __forceinline__ uint64_t pcg_next64(Rng &r) {
     pcg_step(r.s_lo, r.s_hi, r.inc_lo, r.inc_hi);
     uint64_t x = r.s_hi ^ r.s_lo;
-    unsigned rot = (unsigned)(r.s_hi >> 58);
-    return (x >> rot) | (x << ((64u - rot) & 63u));
+    return rotr64(x, (unsigned)(r.s_hi >> 58));
 }
 
 // numpy pcg64_next32: low half first, high half buffered across calls (part of env state)
@@ -79,29 +91,30 @@ __device__ __forceinline__ void rng_computer_draws(Rng &r, int &has32, bool near
     uint64_t lo = r.s_lo, hi = r.s_hi;
     pcg_step(lo, hi, r.inc_lo, r.inc_hi);
     const uint64_t x = hi ^ lo;
-    const unsigned rot = (unsigned)(hi >> 58);
-    const uint64_t n = (x >> rot) | (x << ((64u - rot) & 63u));
+    const uint64_t n = rotr64(x, (unsigned)(hi >> 58));
     const bool buffered = has32 != 0;
     const uint32_t h0 = buffered ? r.uinteger : (uint32_t)n;                // the next two 32-bit halves
     const uint32_t h1 = buffered ? (uint32_t)n : (uint32_t)(n >> 32);
     const uint64_t m1 = (uint64_t)h0 * 20u;
     const bool second = near && (uint32_t)(m1 >> 32) == 0u;
-    const int k = (near ? 1 : 0) + (second ? 1 : 0) + (search ? 1 : 0);  // halves consumed
-    if ((near && (uint32_t)m1 < 20u) || k == 3) {  // general path, from the untouched stream
+    // halves consumed: k = near + second + search, kept as predicates (second implies near)
+    if ((near && (uint32_t)m1 < 20u) || (second && search)) {  // rejection test applies, or k == 3: general path, from the untouched stream
         standby = -1;
         if (near && rng_integers<20>(r, has32) == 0) standby = rng_integers<2>(r, has32);
         if (search) y_first = rng_integers<2>(r, has32);
         return;
     }
+    const bool any = near || search;                // k != 0
+    const bool two = near && (second || search);    // k == 2 (k == 3 has left above)
     standby = second ? (int)(h1 >> 31) : -1;       // integers(0, 2) = (v * 2) >> 32, never rejects (threshold 0)
     y_first = (int)((near ? h1 : h0) >> 31);       // meaningful only if search (then `second` is false)
-    if (buffered ? (k == 2) : (k != 0)) {          // the new output was consumed (at least its low half)
+    if (buffered ? two : any) {                     // the new output was consumed (at least its low half)
         r.s_lo = lo;
         r.s_hi = hi;
         r.uinteger = (uint32_t)(n >> 32);
     }
-    has32 = (buffered ? 1 : 0) ^ (k & 1);
-    if (k != 0) r.dirty = true;
+    has32 = (buffered ? 1 : 0) ^ ((any && !two) ? 1 : 0);  // k & 1
+    if (any) r.dirty = true;
 }
 
 // `a = integers(0, 5); b = integers(0, 5)`  (physics.py:218 for player 1 then player 2)
@@ -109,8 +122,7 @@ __device__ __forceinline__ void rng_integers5_twice(Rng &r, int &has32, int &a, 
     uint64_t lo = r.s_lo, hi = r.s_hi;
     pcg_step(lo, hi, r.inc_lo, r.inc_hi);
     const uint64_t x = hi ^ lo;
-    const unsigned rot = (unsigned)(hi >> 58);
-    const uint64_t n = (x >> rot) | (x << ((64u - rot) & 63u));
+    const uint64_t n = rotr64(x, (unsigned)(hi >> 58));
     const bool buffered = has32 != 0;
     const uint64_t m1 = (uint64_t)(buffered ? r.uinteger : (uint32_t)n) * 5u;
     const uint64_t m2 = (uint64_t)(buffered ? (uint32_t)n : (uint32_t)(n >> 32)) * 5u;

@@ -109,7 +109,8 @@ constexpr int kOffW1 = 0, kOffW2 = kOffW1 + kW1Bytes, kOffX = kOffW2 + 2 * kW2Ag
               kOffStats = (kOffAct + 2 * 32 * 4 + 7) / 8 * 8,                // uint64 [PZ_NUM_STATS]
               kOffRng = kOffStats + 8 * PZ_NUM_STATS;                       // [group][9 words][128 threads] uint32
 constexpr int kRngWords = 9;
-constexpr size_t kSmemBytes = kOffRng + (size_t)kGroups * kRngWords * kGroupThreads * 4;
+constexpr int kOffAnim = kOffRng + kGroups * kRngWords * kGroupThreads * 4;  // uint32 [kAnimLutEntries]: player_animate
+constexpr size_t kSmemBytes = kOffAnim + (size_t)pz::kAnimLutEntries * 4;
 
 struct Params {
     int32_t *state;
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) pz_rollout_policy_kernel(const __
         fill_table<28>(lut + kLutX432, 512, 0, nz);
         fill_table<32>(lut + kLutBXV, 64, 32, nz);
     }
+    pz::anim_fill(reinterpret_cast<uint32_t *>(smem + kOffAnim), tid, kThreads);  // sprite animation as a table
     if (tid < 64) {  // action -> pre-decoded input of player tid / 32 (action_key_map, SimplifyAction folded in)
         const int a = tid & 31;
         bool bad;
@@ -468,7 +470,8 @@ __global__ void __launch_bounds__(kThreads, 1) pz_rollout_policy_kernel(const __
                 const uint32_t *acttab = reinterpret_cast<const uint32_t *>(smem + kOffAct);
                 const Input in1 = input_from_packed(e.p[0], acttab[act[0]]);
                 const Input in2 = input_from_packed(e.p[1], acttab[32 + act[1]]);
-                step_frame_inputs<0>(0xFFFFFFFFu, e, d, P.cfg, in1, in2, nullptr);
+                step_frame_inputs<0, DrawCtxParked, true>(0xFFFFFFFFu, e, d, P.cfg, in1, in2, nullptr,
+                                                          reinterpret_cast<const uint32_t *>(smem + kOffAnim));
                 // episode-granular events (one in hundreds of frames per env): shared-memory atomics, no registers
                 if (e.game_ended) {
                     const bool w1 = e.score[0] > e.score[1];
