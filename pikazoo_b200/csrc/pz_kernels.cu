@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(256) pz_build_power_table_kernel(uint16_t *tab
     const int xv0 = (x < kGroundHalfWidth) ? (xd + 1) * 10 : -(xd + 1) * 10;  // physics.py:841-844
     bool g;
     const int lx = simulate_landing_x<true>(kFullMask, x, y, xv0, 2 * half_yv0, true, g);
-    if (store) tab[idx] = (uint16_t)((unsigned)lx | (g ? 0x8000u : 0u));
+    if (store) tab[idx] = (uint16_t)lx;  // the landing x alone: the search (computer_decide) has no use for `g`
 }
 
 struct DeviceTables {

@@ -17,9 +17,9 @@ constexpr unsigned kFullMask = 0xFFFFFFFFu;
 
 __device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }
 
-// Memoised trajectory simulations (see simulate_landing_x): value = landing x | ended-on-ground << 15.
-//   land [yv + kTabYv][xv + 20][y][x]                        yv in [-kTabYv, kTabYv], xv in [-20, 20]
-//   power[x_direction][yv0 / 2 + kTabYv][y][x]               yv0 = |ball yv| * y_direction * 2
+// Memoised trajectory simulations (see simulate_landing_x).
+//   land [yv + kTabYv][xv + 20][y][x]      = landing x | ended-on-ground << 15    yv in [-kTabYv, kTabYv], xv in [-20, 20]
+//   power[x_direction][yv0 / 2 + kTabYv][y][x] = landing x                        yv0 = |ball yv| * y_direction * 2
 // with y in [0, 252] and x in [0, 432].
 constexpr int kTabYv = 100;
 constexpr int kTabNx = kGroundWidth + 1, kTabNy = kBallGroundY + 1, kTabNxv = 41, kTabNyv = 2 * kTabYv + 1;
@@ -374,7 +374,7 @@ __device__ __forceinline__ void update_landing(unsigned mask, Env &e, const Step
 // ---- computer player ---------------------------------------------------------------------------
 // let_computer_decide_user_input (physics.py:689-771) + decide_whether_input_power_hit (:774-817).
 // Warp-collective over `mask`.
-template <int I, class Ctx>
+template <int I, class Ctx, bool KFRAME = false>
 __device__ __forceinline__ void computer_decide(unsigned mask, Env &e, Ctx &d, const StepCfg &cfg, Input &in,
                                                 int *scratch) {
     Player &p = e.p[I];
@@ -416,34 +416,55 @@ __device__ __forceinline__ void computer_decide(unsigned mask, Env &e, Ctx &d, c
     // side effects, so all 6 are evaluated and then scanned in the reference's order: from the
     // memoised table when the ball is inside its domain, otherwise iteratively, spread over the
     // lanes of the warp (one (searcher, candidate) pair per lane and pass, through the warp's scratch).
+    // Memoised power-hit candidates: six INDEPENDENT 2-byte loads (x_direction 1, 0 x half_yv0 = +H, 0, -H with
+    // H = |ball yv|), issued by the searching lane itself BEFORE the draws: the draw (:795) only decides in which
+    // order +H and -H are scanned, not which entries are read, so the ~80 instructions of the draws hide the loads'
+    // latency. (Until round 2 the (searcher, candidate) pairs were spread over the lanes of the warp like the
+    // iterative simulations below: five shuffles, a rank table in shared memory and three warp barriers per player
+    // and frame cost more than the lanes that idle through these straight-line instructions.)
+    const int ayv = iabs(b.yv);
+    const bool tab_ok = cfg.tab_power != nullptr && search && ayv <= kTabYv && tab_pos_ok(b.x, b.y);
+    int lx_up[2] = {0, 0}, lx_mid[2] = {0, 0}, lx_dn[2] = {0, 0};  // [x_direction]
+    int y_first = 0;
+    auto load_candidates = [&]() {
+        constexpr int kStrideH = kTabNy * kTabNx, kStrideXd = kTabNyv * kStrideH;
+        const uint16_t *t0 = cfg.tab_power + tab_power_index(b.x, b.y, 0, 0);
+        const uint16_t *t1 = t0 + kStrideXd;
+        const int H = ayv * (KFRAME ? y_first : 1) * kStrideH;  // KFRAME: "up" is the side scanned first
+        lx_up[1] = __ldg(t1 + H), lx_mid[1] = __ldg(t1), lx_dn[1] = __ldg(t1 - H);
+        lx_up[0] = __ldg(t0 + H), lx_mid[0] = __ldg(t0), lx_dn[0] = __ldg(t0 - H);
+    };
+    // (the K-frame kernels hide latency with their six or seven CTAs per SM and are short of registers instead:
+    // there the six values are not kept live across the draws, and the draw can then choose the addresses instead
+    // of four selects — 1.82 against 1.84 ms per K = 64 launch)
+    if (!KFRAME && tab_ok) load_candidates();
+
     // This frame's draws in the reference's order: :728 `integers(0, 20) == 0` and then :729 `integers(0, 2)`
     // if near, :795 `integers(0, 2)` (scan order of y_direction) if a power hit is searched for.
     int standby_draw, y_draw;
     d.computer_draws(e.has32, near, search, standby_draw, y_draw);
     if (standby_draw >= 0) p.standby = standby_draw;
-    const int y_first = search ? (y_draw == 0 ? -1 : 1) : 0;
-    const int ayv = iabs(b.yv);
+    y_first = search ? (y_draw == 0 ? -1 : 1) : 0;
     bool found = false;
-    // memoised: the six candidates are six INDEPENDENT 2-byte loads (x_direction 1, 0 x half_yv0 = +h, 0, -h with
-    // h = |ball yv| * y_first), issued back to back by the searching lane itself and scanned by selects. (Until round 2
-    // the (searcher, candidate) pairs were spread over the lanes of the warp like the iterative simulations below:
-    // five shuffles, a rank table in shared memory and three warp barriers per player and frame cost more than the
-    // 5 / 6 of a warp's lanes that idle through these ~60 straight-line instructions.)
-    const bool tab_ok = cfg.tab_power != nullptr && search && ayv <= kTabYv && tab_pos_ok(b.x, b.y);
     if (tab_ok) {
-        constexpr int kStrideH = kTabNy * kTabNx, kStrideXd = kTabNyv * kStrideH;
-        const uint16_t *t0 = cfg.tab_power + tab_power_index(b.x, b.y, 0, 0);
-        const uint16_t *t1 = t0 + kStrideXd;
-        const int h = ayv * y_first * kStrideH;
-        const int lx[6] = {__ldg(t1 + h) & 0x7FFF, __ldg(t1) & 0x7FFF, __ldg(t1 - h) & 0x7FFF,
-                           __ldg(t0 + h) & 0x7FFF, __ldg(t0) & 0x7FFF, __ldg(t0 - h) & 0x7FFF};
+        if (KFRAME) load_candidates();
+        // acceptable (:806-811): lx <= left_boundary || lx >= far_boundary, and |lx - opponent x| > 64 — two unsigned
+        // range tests (lx is never negative). Scan order: x_direction 1 then 0; y_direction y_first, 0, -y_first.
+        constexpr unsigned side_lo = left_boundary + 1, side_span = far_boundary - left_boundary - 1;
+        const bool up_first = KFRAME || y_first > 0;
+        int first = -1;
 #pragma unroll
-        for (int c = 5; c >= 0; c--) {  // the first acceptable candidate in the reference's scan order wins
-            if ((lx[c] <= left_boundary || lx[c] >= far_boundary) && iabs(lx[c] - o.x) > kPlayerLength) {
-                in.xdir = (c < 3) ? 1 : 0;
-                in.ydir = y_first * (1 - (c % 3));
-                found = true;
-            }
+        for (int c = 5; c >= 0; c--) {
+            const int xd = c < 3 ? 1 : 0, r = c % 3;
+            const int lx = r == 1 ? lx_mid[xd] : ((r == 0) == up_first ? lx_up[xd] : lx_dn[xd]);
+            const bool ok = (unsigned)(lx - (int)side_lo) >= side_span &&
+                            (unsigned)(lx - o.x + kPlayerLength) > 2u * kPlayerLength;
+            first = ok ? c : first;  // the first acceptable candidate in the reference's scan order wins
+        }
+        if (first >= 0) {
+            in.xdir = (first < 3) ? 1 : 0;
+            in.ydir = y_first * (1 - (first < 3 ? first : first - 3));
+            found = true;
         }
         search = false;
     }
@@ -622,8 +643,9 @@ __device__ __forceinline__ bool ball_player(Env &e, Ctx &d, const Input &in) {
 // AI_MASK != 0. Returns player_1's base reward (-1, 0, +1).
 // The same with the two players' inputs already decoded (get_input has run: it only touches
 // power_hit_key_is_down_previous, which the new-round block below does not, so the order is immaterial).
-// ANIM_LUT: `anim` is the sprite-animation table in shared memory (anim_fill; the K-frame kernels).
-template <int AI_MASK, class Ctx, bool ANIM_LUT = false>
+// KFRAME (the K-frame kernels): `anim` is the sprite-animation table in shared memory (anim_fill), and the computer
+// players' table loads are not hoisted above the draws.
+template <int AI_MASK, class Ctx, bool KFRAME = false>
 __device__ __forceinline__ int step_frame_inputs(unsigned mask, Env &e, Ctx &d, const StepCfg &c, Input in1, Input in2,
                                                  int *scratch, const uint32_t *anim = nullptr) {
     if (e.round_ended) {  // :176-180 (game_ended is false here)
@@ -644,10 +666,10 @@ __device__ __forceinline__ int step_frame_inputs(unsigned mask, Env &e, Ctx &d, 
     } else {
         e.land_ok = 0;  // expected_landing_point_x is not maintained without computer players
     }
-    if (AI_MASK & 1) computer_decide<0>(mask, e, d, c, in1, scratch);
-    player_move<0, ANIM_LUT>(e.p[0], in1, anim);
-    if (AI_MASK & 2) computer_decide<1>(mask, e, d, c, in2, scratch);
-    player_move<1, ANIM_LUT>(e.p[1], in2, anim);
+    if (AI_MASK & 1) computer_decide<0, Ctx, KFRAME>(mask, e, d, c, in1, scratch);
+    player_move<0, KFRAME>(e.p[0], in1, anim);
+    if (AI_MASK & 2) computer_decide<1, Ctx, KFRAME>(mask, e, d, c, in2, scratch);
+    player_move<1, KFRAME>(e.p[1], in2, anim);
 
     bool recalc = ball_player<0>(e, d, in1);
     recalc |= ball_player<1>(e, d, in2);
