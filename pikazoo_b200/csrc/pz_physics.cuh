@@ -515,9 +515,9 @@ __device__ __forceinline__ void computer_decide(unsigned mask, Env &e, Ctx &d, c
 // ---- player ------------------------------------------------------------------------------------
 // The sprite animation at the end of process_player_movement_and_set_player_position (physics.py:524-552):
 // (state, frame_number, delay_before_next_frame, normal_status_arm_swing_direction) -> the same. A pure function of
-// 3 + 3 + 3 + 1 bits, so the K-frame kernels, where a table pays for its construction, read it from a 1,024-entry
-// table in shared memory that they fill with this very function (anim_entry / anim_lookup below).
-__device__ __forceinline__ void player_animate(int &state, int &frame, int &delay, int &arm) {
+// 3 + 3 + 3 + 1 bits: the K-frame kernels read it from a 1,024-entry table in shared memory that they fill with this
+// very function (anim_fill), most per-step kernels from the same table evaluated by the compiler (g_anim_table).
+__host__ __device__ constexpr void player_animate(int &state, int &frame, int &delay, int &arm) {
     if (state == 1) {
         frame = frame >= 2 ? frame - 2 : frame + 1;  // (frame + 1) % 3 for frame in 0..4
     } else if (state == 2) {
@@ -540,12 +540,15 @@ __device__ __forceinline__ void player_animate(int &state, int &frame, int &dela
         }
     }
 }
+#ifndef PZ_STEP_ANIM_LUT
+#define PZ_STEP_ANIM_LUT 1
+#endif
 constexpr int kAnimLutEntries = 1024;
 __device__ __forceinline__ int anim_index(int state, int frame, int delay, int arm) {
     return state + frame * 8 + delay * 64 + (arm + 1) * 256;  // every field is at most 7 (pz_state.cuh), arm is +-1
 }
 // entry = state | frame << 8 | delay << 16 | (int8) arm << 24: a byte each, one PRMT each to take apart
-__device__ __forceinline__ uint32_t anim_entry(int index) {
+__host__ __device__ constexpr uint32_t anim_entry(int index) {
     int state = index & 7, frame = (index >> 3) & 7, delay = (index >> 6) & 7, arm = (index & 512) ? 1 : -1;
     player_animate(state, frame, delay, arm);
     return (uint32_t)state | ((uint32_t)frame << 8) | ((uint32_t)delay << 16) | ((uint32_t)(arm & 0xFF) << 24);
@@ -553,6 +556,16 @@ __device__ __forceinline__ uint32_t anim_entry(int index) {
 __device__ __forceinline__ void anim_fill(uint32_t *lut, int tid, int nthreads) {  // caller synchronises
     for (int k = tid; k < kAnimLutEntries; k += nthreads) lut[k] = anim_entry(k);
 }
+// the same table evaluated by the compiler, in global memory, for the per-step kernels (read through L1)
+struct AnimTable {
+    uint32_t v[kAnimLutEntries];
+};
+__host__ __device__ constexpr AnimTable make_anim_table() {
+    AnimTable t{};
+    for (int k = 0; k < kAnimLutEntries; k++) t.v[k] = anim_entry(k);
+    return t;
+}
+static __device__ const AnimTable g_anim_table = make_anim_table();
 
 // process_player_movement_and_set_player_position, physics.py:439-564 (after the AI override). Written as selects:
 // the lanes of a warp are in different phases of play, so every side of a branch runs anyway and the branches
@@ -645,7 +658,7 @@ __device__ __forceinline__ bool ball_player(Env &e, Ctx &d, const Input &in) {
 // power_hit_key_is_down_previous, which the new-round block below does not, so the order is immaterial).
 // KFRAME (the K-frame kernels): `anim` is the sprite-animation table in shared memory (anim_fill), and the computer
 // players' table loads are not hoisted above the draws.
-template <int AI_MASK, class Ctx, bool KFRAME = false>
+template <int AI_MASK, class Ctx, bool KFRAME = false, bool ANIM_LUT = KFRAME>
 __device__ __forceinline__ int step_frame_inputs(unsigned mask, Env &e, Ctx &d, const StepCfg &c, Input in1, Input in2,
                                                  int *scratch, const uint32_t *anim = nullptr) {
     if (e.round_ended) {  // :176-180 (game_ended is false here)
@@ -667,9 +680,9 @@ __device__ __forceinline__ int step_frame_inputs(unsigned mask, Env &e, Ctx &d, 
         e.land_ok = 0;  // expected_landing_point_x is not maintained without computer players
     }
     if (AI_MASK & 1) computer_decide<0, Ctx, KFRAME>(mask, e, d, c, in1, scratch);
-    player_move<0, KFRAME>(e.p[0], in1, anim);
+    player_move<0, ANIM_LUT>(e.p[0], in1, anim);
     if (AI_MASK & 2) computer_decide<1, Ctx, KFRAME>(mask, e, d, c, in2, scratch);
-    player_move<1, KFRAME>(e.p[1], in2, anim);
+    player_move<1, ANIM_LUT>(e.p[1], in2, anim);
 
     bool recalc = ball_player<0>(e, d, in1);
     recalc |= ball_player<1>(e, d, in2);
