@@ -625,7 +625,9 @@ template <int I, class Ctx>
 __device__ __forceinline__ bool ball_player(Env &e, Ctx &d, const Input &in) {
     Player &p = e.p[I];
     Ball &b = e.b;
-    const bool hit = iabs(b.x - p.x) <= kPlayerHalfLength && iabs(b.y - p.y) <= kPlayerHalfLength;
+    // |dx| <= 32 and |dy| <= 32 (:340-356) as two unsigned range tests
+    const bool hit = (unsigned)(b.x - p.x + kPlayerHalfLength) <= 2u * kPlayerHalfLength &&
+                     (unsigned)(b.y - p.y + kPlayerHalfLength) <= 2u * kPlayerHalfLength;
     if (!hit) {
         p.coll = 0;
         return false;
