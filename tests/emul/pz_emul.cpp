@@ -187,6 +187,46 @@ void emul_step(int32_t *packed, int64_t n, int winning_score, int serve, int ai_
     }
 }
 
+// player_move with the sprite animation as a table (what the K-frame kernels read from shared memory after anim_fill,
+// and most per-step kernels from the compile-time g_anim_table) against the arithmetic form, over every animation
+// state x a grid of positions, velocities and inputs. Returns the number of combinations checked; *mismatches counts
+// the ones where any player field differs (between the three forms).
+int64_t emul_player_move_forms(int64_t *mismatches) {
+    static uint32_t filled[kAnimLutEntries];
+    anim_fill(filled, 0, 1);
+    int64_t checked = 0, bad = 0;
+    const int ys[] = {kPlayerGroundY, kPlayerGroundY - 1, kPlayerGroundY - 16, 108, kPlayerGroundY + 3};
+    const int yvs[] = {-16, -5, -1, 0, 1, 7, 16};
+    for (int state = 0; state < 5; state++)
+        for (int frame = 0; frame < 8; frame++)
+            for (int delay = 0; delay < 8; delay++)
+                for (int arm = -1; arm <= 1; arm += 2)
+                    for (int y : ys)
+                        for (int yv : yvs)
+                            for (int lying = -2; lying <= 3; lying++)
+                                for (int dive = -1; dive <= 1; dive++)
+                                    for (int inp = 0; inp < 18; inp++)
+                                        for (int x : {32, 100, 184, 248, 400}) {
+                                            Player p = {};
+                                            p.x = x, p.y = y, p.yv = yv, p.state = state, p.frame = frame, p.delay = delay;
+                                            p.arm = arm, p.dive = dive, p.lying = lying, p.bold = 3, p.standby = 1;
+                                            Input in;
+                                            in.xdir = inp % 3 - 1, in.ydir = (inp / 3) % 3 - 1, in.power = inp / 9;
+                                            Player a = p, b = p, c = p, a1 = p, b1 = p;
+                                            player_move<0, false>(a, in);
+                                            player_move<0, true>(b, in, filled);
+                                            player_move<0, true>(c, in, g_anim_table.v);
+                                            player_move<1, false>(a1, in);
+                                            player_move<1, true>(b1, in, filled);
+                                            checked++;
+                                            if (std::memcmp(&a, &b, sizeof a) || std::memcmp(&a, &c, sizeof a) ||
+                                                std::memcmp(&a1, &b1, sizeof a1))
+                                                bad++;
+                                        }
+    *mismatches = bad;
+    return checked;
+}
+
 // The two trajectory simulations alone (fast-forwarded device form), for exhaustive comparison
 // with the reference's plain loops. Returns landing x; *by_ground = ended on the ground.
 int emul_simulate(int x, int y, int xv, int yv, int power, int *by_ground) {

@@ -332,3 +332,14 @@ def test_one_step_decode_equals_key_table_decode(emul):
                     assert np.array_equal(out[:5], out[5:]), (agent, simplify, action, keyprev, out)
                     n = 13 if simplify else 18
                     assert out[4] == (0 if 0 <= action < n else 1)
+
+
+def test_player_move_table_forms_equal_arithmetic(emul):
+    """player_move reading the sprite animation (physics.py:524-552) from a table — the one the K-frame kernels fill in
+    shared memory (anim_fill) and the compile-time one of the per-step kernels (g_anim_table) — == player_move computing
+    it, for every (state, frame, delay, arm) x positions x velocities x lying / diving fields x all 18 inputs, both
+    players' court halves."""
+    emul.emul_player_move_forms.restype = ctypes.c_int64
+    bad = ctypes.c_int64(-1)
+    checked = emul.emul_player_move_forms(ctypes.byref(bad))
+    assert checked > 5_000_000 and bad.value == 0, (checked, bad.value)
