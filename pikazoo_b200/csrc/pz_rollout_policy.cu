@@ -226,8 +226,14 @@ __device__ __forceinline__ void pack_features(const Env &e, const uint16_t *lut,
     for (int j = 0; j < 18; j++) w[j] = h[2 * j] | (h[2 * j + 1] << 16);
 }
 
-template <int NA>
+// PLAIN: sampled actions, no frame cap, nothing exported (the training-loop configuration): the four launch-uniform
+// options are compiled out of the frame loop.
+template <int NA, bool PLAIN>
 __global__ void __launch_bounds__(kThreads, 1) pz_rollout_policy_kernel(const __grid_constant__ Params P) {
+    const bool opt_greedy = !PLAIN && P.greedy;
+    float *const opt_logits_out = PLAIN ? nullptr : P.logits_out;
+    unsigned char *const opt_actions_out = PLAIN ? nullptr : P.actions_out;
+    const int opt_max_frames = PLAIN ? 0 : P.max_frames;
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -368,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) pz_rollout_policy_kernel(const __
                            smem_desc(s_base + kOffW1 + ks * 2 * kW1KGroup, kW1KGroup, 128), kIdesc1, ks > 0);
                 mma_commit(bar);
             }
-            const uint32_t nbase = P.greedy ? 0u : pzp::noise_base(P.seed, P.step0 + (uint64_t)k, genv);
+            const uint32_t nbase = opt_greedy ? 0u : pzp::noise_base(P.seed, P.step0 + (uint64_t)k, genv);
             mbar_wait<PZ_RP_BACKOFF_NS>(bar, phase);
             phase ^= 1u;
             tc_fence_after();
@@ -440,8 +446,8 @@ __global__ void __launch_bounds__(kThreads, 1) pz_rollout_policy_kernel(const __
             } else {
                 group_arrive(id_free);
             }
-            if (P.logits_out != nullptr && valid) {
-                float *dst = P.logits_out + (((int64_t)k * P.n + i) * 2) * NA;
+            if (opt_logits_out != nullptr && valid) {
+                float *dst = opt_logits_out + (((int64_t)k * P.n + i) * 2) * NA;
 #pragma unroll
                 for (int a = 0; a < 2; a++)
 #pragma unroll
@@ -451,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) pz_rollout_policy_kernel(const __
             int act[2];
 #pragma unroll
             for (int a = 0; a < 2; a++) {
-                if (P.greedy) {
+                if (opt_greedy) {
                     float best = pzp::pack_key(-INFINITY, 31);
 #pragma unroll
                     for (int j = 0; j < NA; j++) best = fmaxf(best, pzp::pack_key(lg[a][j], j));
@@ -461,11 +467,11 @@ __global__ void __launch_bounds__(kThreads, 1) pz_rollout_policy_kernel(const __
                     act[a] = pzp::sample_inverse_cdf<NA>(lg[a], NA, nbase + (uint32_t)(32 * a) * 0x9E3779B9u);
                 }
             }
-            if (P.actions_out != nullptr && valid)
-                reinterpret_cast<uchar2 *>(P.actions_out)[(int64_t)k * P.n + i] =
+            if (opt_actions_out != nullptr && valid)
+                reinterpret_cast<uchar2 *>(opt_actions_out)[(int64_t)k * P.n + i] =
                     make_uchar2((unsigned char)act[0], (unsigned char)act[1]);
             // ---- one call of the env (pz_rollout semantics: auto-reset always on)
-            const bool over = e.game_ended || (P.max_frames > 0 && e.ep_frames >= P.max_frames);
+            const bool over = e.game_ended || (opt_max_frames > 0 && e.ep_frames >= opt_max_frames);
             if (valid && !over) {
                 const uint32_t *acttab = reinterpret_cast<const uint32_t *>(smem + kOffAct);
                 const Input in1 = input_from_packed(e.p[0], acttab[act[0]]);
@@ -480,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) pz_rollout_policy_kernel(const __
                     atomicAdd(s_stats + (w1 ? PZ_STAT_P1_WINS : PZ_STAT_P2_WINS), 1ULL);
                     atomicAdd(s_stats + PZ_STAT_P1_POINTS, (unsigned long long)e.score[0]);
                     atomicAdd(s_stats + PZ_STAT_P2_POINTS, (unsigned long long)e.score[1]);
-                } else if (P.max_frames > 0 && e.ep_frames >= P.max_frames) {
+                } else if (opt_max_frames > 0 && e.ep_frames >= opt_max_frames) {
                     atomicAdd(s_stats + PZ_STAT_TRUNCATED, 1ULL);
                 }
             } else if (valid) {
@@ -505,20 +511,20 @@ __global__ void __launch_bounds__(kThreads, 1) pz_rollout_policy_kernel(const __
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
 }
 
-template <int NA>
+template <int NA, bool PLAIN>
 static cudaError_t launch_one(const Params &P, unsigned grid, cudaStream_t stream, int dev) {
     static std::mutex mu;
     static bool attr_set[64] = {};
     {
         std::lock_guard<std::mutex> lock(mu);
         if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(pz_rollout_policy_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaError_t e = cudaFuncSetAttribute(pz_rollout_policy_kernel<NA, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)kSmemBytes);
             if (e != cudaSuccess) return e;
             attr_set[dev] = true;
         }
     }
-    pz_rollout_policy_kernel<NA><<<grid, kThreads, kSmemBytes, stream>>>(P);
+    pz_rollout_policy_kernel<NA, PLAIN><<<grid, kThreads, kSmemBytes, stream>>>(P);
     return cudaGetLastError();
 }
 
@@ -567,7 +573,9 @@ extern "C" int pz_rollout_policy(int32_t *state_dev, int64_t n, const pz_config 
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t tiles = (n + kTileEnvs - 1) / kTileEnvs;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-    const cudaError_t err = n_actions == 18 ? launch_one<18>(P, grid, st, dev) : launch_one<13>(P, grid, st, dev);
+    const bool plain = !P.greedy && P.max_frames <= 0 && P.actions_out == nullptr && P.logits_out == nullptr;
+    const cudaError_t err = n_actions == 18 ? (plain ? launch_one<18, true>(P, grid, st, dev) : launch_one<18, false>(P, grid, st, dev))
+                                            : (plain ? launch_one<13, true>(P, grid, st, dev) : launch_one<13, false>(P, grid, st, dev));
     if (err != cudaSuccess) return (int)err;
     if (obs_dev) return pz::launch_observe(state_dev, n, cfg, obs_dev, st);  // the observation after the last frame
     return 0;
