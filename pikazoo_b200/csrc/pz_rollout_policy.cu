@@ -63,6 +63,7 @@ using pzp::tc::tmem_st_wait;
 // own slot, 170 registers), 4: 20.8, 5: 21.9 (96 registers), 6: 20.4 (80 registers, 420 B of spills). With the PCG64
 // stream and the statistics parked in shared memory (DrawCtxParked): 5: 21.5, 6: 23.1 (150 B of spills), 7: 23.3 —
 // six it is; parking five more cold env fields (boldness, stand-by, landing point) measured slower (21.9 at six).
+// Again after the select-form player_move, the animation table and the PLAIN instantiation: 5: 24.3, 6: 26.05, 7: 25.9.
 // The profile (profiles/r02_ncu_full_rollout_policy.txt): 1,020 warp instructions per warp and frame, issue slots 67 %
 // busy with five warps per scheduler of which one or two sit in a barrier, a slot wait or an MMA wait at any time:
 // bound by how many warps can run, i.e. by registers. Tried and dropped: staggering the two agents' chains (layer 2 of
