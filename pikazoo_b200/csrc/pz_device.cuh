@@ -201,6 +201,12 @@ __device__ __forceinline__ bool emit_obs_shared_as(const Env &e, bool valid, voi
     return false;
 }
 
+// f(std::integral_constant<int, K>{}) for K = 0, 1, ... (a compile-time loop whose body sees K as a constant)
+template <class F, int... K>
+__device__ __forceinline__ void for_each_constant(F &&f, std::integer_sequence<int, K...>) {
+    (f(std::integral_constant<int, K>{}), ...);
+}
+
 // FEATURE_MAJOR: obs[((a * rows) + k) * ld + i]. Consecutive lanes hold consecutive envs, so every one of
 // the 70 stores of a warp is one contiguous 64 / 128 / 256-byte segment: no staging, no shared memory.
 // Streaming stores (st.global.cs): written once, read by the policy, never by the simulator.
@@ -229,8 +235,7 @@ __device__ __forceinline__ void emit_obs_feature_major(const Env &e, bool valid,
         __stcs(p0 + (int64_t)k * ld, v);
         __stcs(p1 + (int64_t)k1 * ld, v);
     };
-    [&]<int... K>(std::integer_sequence<int, K...>) { (emit(std::integral_constant<int, K>{}), ...); }
-    (std::make_integer_sequence<int, 35>{});
+    for_each_constant(emit, std::make_integer_sequence<int, 35>{});
 }
 
 // The same rows from a whole CTA of kThreads consecutive envs, transposed through shared memory: every thread
@@ -258,8 +263,7 @@ __device__ __forceinline__ void emit_obs_feature_major_staged(const Env &e, bool
             v = (T)obs_bits16<DT, k>(u, normalize);
         stage[k][tid] = v;
     };
-    [&]<int... K>(std::integer_sequence<int, K...>) { (put(std::integral_constant<int, K>{}), ...); }
-    (std::make_integer_sequence<int, 35>{});
+    for_each_constant(put, std::make_integer_sequence<int, 35>{});
     __syncthreads();
     using V = typename std::conditional<sizeof(T) == 2, uint2, uint4>::type;  // four elements per lane
     // Warp w writes rows w, w + 4, ...: row k = w + 4 j goes to agent 0's row k and to agent 1's row k + d(k), d = +13 /

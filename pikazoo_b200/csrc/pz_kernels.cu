@@ -71,7 +71,7 @@ constexpr int kRolloutThreads = PZ_ROLLOUT_THREADS;
 template <int AI_MASK, bool PLAIN>
 __global__ void __maxnreg__(AI_MASK == 3 ? PZ_ROLLOUT_MAXNREG_AI : PZ_ROLLOUT_MAXNREG) pz_rollout_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(16) int stage[kRolloutThreads / 32][kAiScratchInts];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5;
     const int64_t i = P.begin + (int64_t)blockIdx.x * kRolloutThreads + threadIdx.x;
     const bool valid = i < P.end;
 
@@ -161,7 +161,7 @@ __global__ void __maxnreg__(AI_MASK == 3 ? PZ_ROLLOUT_MAXNREG_AI : PZ_ROLLOUT_MA
 // ---- reset / seed / export / import -----------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) pz_reset_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(128) int stage[kWarps][32 * kObsRow];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5;
     const int64_t i = P.begin + (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const bool valid = i < P.end;
     DrawCtx d;
