@@ -438,7 +438,9 @@ constexpr int step_min_ctas() {
     return ObsType<OBS_DT>::bytes == 2 ? PZ_HALF_MIN_CTAS : (OBS_DT == PZ_OBS_F64 ? 4 : 6);
 }
 
-template <int AI_MASK, int OBS_DT, int LAYOUT>
+// PLAIN: none of the optional outputs (episode returns / lengths, truncated, status byte, completion word), no frame cap,
+// no shaped rewards — the launch-uniform tests of all of them are compiled out (instantiated without computer players).
+template <int AI_MASK, int OBS_DT, int LAYOUT, bool PLAIN = false>
 __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOUT>())
     pz_step_kernel(const __grid_constant__ KParams P) {
     // ENV_MAJOR stages the observation rows here (2-byte elements need half the room); FEATURE_MAJOR only
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
     if (P.actions) load_actions(P, il, a1, a2);
     if (AI_MASK != 0) rng_load(d.r, d.s, il);  // computer players draw on most frames
 
-    const bool over = e.game_ended || episode_truncated(P, e);
+    const bool over = e.game_ended || (!PLAIN && episode_truncated(P, e));
     const bool run = valid && !over;
     const bool do_reset = valid && over && P.autoreset;
     const bool frozen = valid && over && !P.autoreset;
@@ -527,16 +529,21 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
             if (!staged) emit_obs_feature_major<OBS_DT>(e, valid, P.normalize, P.obs, i, P.n, P.obs_rows);
         }
     }
-    const bool truncated = valid && episode_truncated(P, e);  // this call's step reached the cap, or frozen there
+    const bool truncated = !PLAIN && valid && episode_truncated(P, e);  // this call's step reached the cap, or frozen there
     if (valid) {
         if (run || do_reset) {
             store_env(e, d.s, i);
             if (d.r.dirty) rng_store(d.r, d.s, i);
         }
         double r1 = 0.0, r2 = 0.0;
-        if (run) step_rewards(P, e, base, r1, r2);
+        if (run) {
+            if (PLAIN)
+                r1 = (double)base, r2 = (double)(-base);
+            else
+                step_rewards(P, e, base, r1, r2);
+        }
         if (P.reward) store_reward(P, i, r1, r2);
-        if (P.ep_return) {  // record_episode_statistics.py:24-25 (reset zeroes), :32 (step adds)
+        if (!PLAIN && P.ep_return) {  // record_episode_statistics.py:24-25 (reset zeroes), :32 (step adds)
             if (do_reset) {
                 P.ep_return[i] = make_double2(0.0, 0.0);
             } else if (run) {
@@ -546,17 +553,17 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
                 P.ep_return[i] = acc;
             }
         }
-        if (P.ep_length) P.ep_length[i] = e.ep_frames;
+        if (!PLAIN && P.ep_length) P.ep_length[i] = e.ep_frames;
         if (P.done) P.done[i] = (uint8_t)(e.game_ended ? 1 : 0);  // a reset cleared it; frozen envs keep it
-        if (P.truncated) P.truncated[i] = (uint8_t)(truncated ? 1 : 0);
-        if (P.status) P.status[i] = (uint8_t)((run ? base + 1 : 1) | (e.game_ended ? 4 : 0) | (truncated ? 8 : 0));
+        if (!PLAIN && P.truncated) P.truncated[i] = (uint8_t)(truncated ? 1 : 0);
+        if (!PLAIN && P.status) P.status[i] = (uint8_t)((run ? base + 1 : 1) | (e.game_ended ? 4 : 0) | (truncated ? 8 : 0));
     }
     if (P.stats) {
         accumulate_stats(P.stats, e, run && e.game_ended, do_reset, bad, frozen, run && truncated, lane);
         if (i == P.begin) atomicAdd(P.stats + PZ_STAT_CALLS, (unsigned long long)(P.end - P.begin));
     }
     if (pending) bulk_store_wait_read();
-    if (P.seq != nullptr) {  // launch-uniform; one CTA (checked on the host)
+    if (!PLAIN && P.seq != nullptr) {  // launch-uniform; one CTA (checked on the host)
         if (pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the rows have left, not only been read
         __threadfence_system();
         __syncthreads();
