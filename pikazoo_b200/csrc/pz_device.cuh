@@ -390,8 +390,9 @@ __device__ __forceinline__ void step_rewards(const KParams &P, const Env &e, int
     }
 }
 
+template <bool F32_ONLY = false>
 __device__ __forceinline__ void store_reward(const KParams &P, int64_t i, double r1, double r2) {
-    if (P.rew_dtype == PZ_REW_F32) {
+    if (F32_ONLY || P.rew_dtype == PZ_REW_F32) {
         asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(
                          reinterpret_cast<float2 *>(P.reward) + i),
                      "f"((float)r1), "f"((float)r2), "l"(P.out_policy)
@@ -438,8 +439,11 @@ constexpr int step_min_ctas() {
     return ObsType<OBS_DT>::bytes == 2 ? PZ_HALF_MIN_CTAS : (OBS_DT == PZ_OBS_F64 ? 4 : 6);
 }
 
-// PLAIN: none of the optional outputs (episode returns / lengths, truncated, status byte, completion word), no frame cap,
-// no shaped rewards — the launch-uniform tests of all of them are compiled out (instantiated without computer players).
+// PLAIN: the configuration of a plain batched run — observations, float32 rewards, done flags and statistics all
+// written, auto-reset on, the full action set, and none of the options: no episode returns / lengths, truncated flags,
+// status byte or completion word, no frame cap, no shaped rewards, no SimplifyAction. The launch-uniform tests of all of
+// these are compiled out (launch_dt in pz_step_inst.inc decides; instantiated for no / two computer players). Worth
+// 1 % (int32 rows) to 10 % (bf16 feature-major rows): the options cost registers more than instructions.
 template <int AI_MASK, int OBS_DT, int LAYOUT, bool PLAIN = false>
 __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOUT>())
     pz_step_kernel(const __grid_constant__ KParams P) {
@@ -460,6 +464,8 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t i = P.begin + (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const bool valid = i < P.end;
+    // PLAIN float rows are normalised rows (launch_dt): the raw-float form of the row code is not even compiled
+    const bool normalize = PLAIN ? (OBS_DT != PZ_OBS_I32 && OBS_DT != PZ_OBS_I16) : (P.normalize != 0);
     // Programmatic dependent launch: let the next launch in the stream be scheduled into the SM slots
     // this grid's tail frees (it parks in its own cudaGridDependencySynchronize), and wait here for the
     // previous launch to have completed and flushed before the first read. Both are no-ops when the
@@ -479,20 +485,20 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
     // fields: 3 % of the kernel's instructions.)
     const int64_t il = valid ? i : P.end - 1;
     load_env(e, d.s, il);
-    if (P.actions) load_actions(P, il, a1, a2);
+    if (AI_MASK == 0 || P.actions) load_actions(P, il, a1, a2);  // (launch_step: only two computer players may omit them)
     if (AI_MASK != 0) rng_load(d.r, d.s, il);  // computer players draw on most frames
 
     const bool over = e.game_ended || (!PLAIN && episode_truncated(P, e));
     const bool run = valid && !over;
-    const bool do_reset = valid && over && P.autoreset;
-    const bool frozen = valid && over && !P.autoreset;
+    const bool do_reset = valid && over && (PLAIN || P.autoreset);
+    const bool frozen = !PLAIN && valid && over && !P.autoreset;
     const unsigned mask = __ballot_sync(kFullMask, run);
     int base = 0;
     bool bad = false;
     if (run) {
         bool bad1, bad2;
         Input in1, in2;
-        if (P.simplify) {
+        if (!PLAIN && P.simplify) {
             in1 = decode_input<0, true>(a1, e.p[0], bad1);
             in2 = decode_input<1, true>(a2, e.p[1], bad2);
         } else {
@@ -512,9 +518,9 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
 
     __syncwarp();  // the staging buffer doubled as the computer players' scratch
     bool pending = false;
-    if (P.obs) {
+    if (PLAIN || P.obs) {
         if (LAYOUT == PZ_LAYOUT_ENV_MAJOR)
-            pending = emit_obs_as<OBS_DT>(e, valid, P.normalize, P.obs, i, P.end, stage[warp], lane, P.out_policy);
+            pending = emit_obs_as<OBS_DT>(e, valid, normalize, P.obs, i, P.end, stage[warp], lane, P.out_policy);
         else if constexpr (LAYOUT == PZ_LAYOUT_ENV_MAJOR_SHARED)
             pending = emit_obs_shared_as<OBS_DT>(e, valid, P.obs, i, P.end, stage[warp], lane, P.out_policy);
         else {
@@ -522,11 +528,11 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
             if constexpr (kFmStaged) {
                 // CTA-uniform: a full tile, 4-element-aligned rows, row pitch in bytes below 2^32
                 if ((i - threadIdx.x) + kThreads <= P.end && (P.n & 3) == 0 && P.n <= (int64_t(1) << 28)) {
-                    emit_obs_feature_major_staged<OBS_DT>(e, P.normalize, P.obs, i - threadIdx.x, P.n, P.obs_rows, fm_stage);
+                    emit_obs_feature_major_staged<OBS_DT>(e, normalize, P.obs, i - threadIdx.x, P.n, P.obs_rows, fm_stage);
                     staged = true;
                 }
             }
-            if (!staged) emit_obs_feature_major<OBS_DT>(e, valid, P.normalize, P.obs, i, P.n, P.obs_rows);
+            if (!staged) emit_obs_feature_major<OBS_DT>(e, valid, normalize, P.obs, i, P.n, P.obs_rows);
         }
     }
     const bool truncated = !PLAIN && valid && episode_truncated(P, e);  // this call's step reached the cap, or frozen there
@@ -542,7 +548,7 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
             else
                 step_rewards(P, e, base, r1, r2);
         }
-        if (P.reward) store_reward(P, i, r1, r2);
+        if (PLAIN || P.reward) store_reward<PLAIN>(P, i, r1, r2);
         if (!PLAIN && P.ep_return) {  // record_episode_statistics.py:24-25 (reset zeroes), :32 (step adds)
             if (do_reset) {
                 P.ep_return[i] = make_double2(0.0, 0.0);
@@ -554,11 +560,11 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
             }
         }
         if (!PLAIN && P.ep_length) P.ep_length[i] = e.ep_frames;
-        if (P.done) P.done[i] = (uint8_t)(e.game_ended ? 1 : 0);  // a reset cleared it; frozen envs keep it
+        if (PLAIN || P.done) P.done[i] = (uint8_t)(e.game_ended ? 1 : 0);  // a reset cleared it; frozen envs keep it
         if (!PLAIN && P.truncated) P.truncated[i] = (uint8_t)(truncated ? 1 : 0);
         if (!PLAIN && P.status) P.status[i] = (uint8_t)((run ? base + 1 : 1) | (e.game_ended ? 4 : 0) | (truncated ? 8 : 0));
     }
-    if (P.stats) {
+    if (PLAIN || P.stats) {
         accumulate_stats(P.stats, e, run && e.game_ended, do_reset, bad, frozen, run && truncated, lane);
         if (i == P.begin) atomicAdd(P.stats + PZ_STAT_CALLS, (unsigned long long)(P.end - P.begin));
     }
