@@ -329,12 +329,12 @@ __device__ __forceinline__ void stat_add(unsigned long long *stats, int slot, un
 // Episode-granular events only (rare), aggregated per warp before touching L2 atomics.
 __device__ __forceinline__ void accumulate_stats(unsigned long long *stats, const Env &e, bool terminated,
                                                  bool was_reset, bool bad, bool frozen, bool truncated, int lane) {
+    if (!__any_sync(kFullMask, terminated || was_reset || bad || frozen || truncated)) return;  // nearly every frame
     const unsigned tm = __ballot_sync(kFullMask, terminated);
     const unsigned rm = __ballot_sync(kFullMask, was_reset);
     const unsigned bm = __ballot_sync(kFullMask, bad);
     const unsigned fm = __ballot_sync(kFullMask, frozen);
     const unsigned xm = __ballot_sync(kFullMask, truncated);
-    if ((tm | rm | bm | fm | xm) == 0) return;
     unsigned frames = 0, s1 = 0, s2 = 0, w1 = 0;
     if (tm) {
         frames = __reduce_add_sync(kFullMask, terminated ? (unsigned)e.ep_frames : 0u);
