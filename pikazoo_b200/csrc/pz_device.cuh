@@ -431,12 +431,15 @@ constexpr int kAiScratchInts = 320;  // computer_decide: 32 x int4 inputs + 32 x
 #ifndef PZ_HALF_MIN_CTAS
 #define PZ_HALF_MIN_CTAS 7  // 72 registers, 28 B of spill loads: 47.6 us per million envs (6: 80 registers, 49.6 us; 8: 64, 53.4 us)
 #endif
-template <int AI_MASK, int OBS_DT, int LAYOUT>
+template <int AI_MASK, int OBS_DT, int LAYOUT, bool PLAIN>
 constexpr int step_min_ctas() {
-    if (AI_MASK != 0) return PZ_AI_MIN_CTAS;
-    if (LAYOUT == PZ_LAYOUT_FEATURE_MAJOR) return OBS_DT == PZ_OBS_F64 ? 4 : PZ_FM_MIN_CTAS;
+    if (AI_MASK != 0) return PZ_AI_MIN_CTAS;  // (PLAIN at six CTAs / 80 registers: 81.5 against 74.9 us)
+    // the PLAIN instantiations need fewer registers: with 2-byte elements eight CTAs of 64 registers now beat seven of 72
+    // (fp16 rows 39.7 -> 38.9 us, bf16 feature-major 43.6 -> 42.8 us per million envs; the general ones lose at eight)
+    constexpr int two_byte = PLAIN && ObsType<OBS_DT>::bytes == 2 ? 1 : 0;
+    if (LAYOUT == PZ_LAYOUT_FEATURE_MAJOR) return OBS_DT == PZ_OBS_F64 ? 4 : PZ_FM_MIN_CTAS + two_byte;
     if (LAYOUT == PZ_LAYOUT_ENV_MAJOR_SHARED) return PZ_HALF_MIN_CTAS;
-    return ObsType<OBS_DT>::bytes == 2 ? PZ_HALF_MIN_CTAS : (OBS_DT == PZ_OBS_F64 ? 4 : 6);
+    return ObsType<OBS_DT>::bytes == 2 ? PZ_HALF_MIN_CTAS + two_byte : (OBS_DT == PZ_OBS_F64 ? 4 : 6);
 }
 
 // PLAIN: the configuration of a plain batched run — observations, float32 rewards, done flags and statistics all
@@ -445,7 +448,7 @@ constexpr int step_min_ctas() {
 // these are compiled out (launch_dt in pz_step_inst.inc decides; instantiated for no / two computer players). Worth
 // 1 % (int32 rows) to 10 % (bf16 feature-major rows): the options cost registers more than instructions.
 template <int AI_MASK, int OBS_DT, int LAYOUT, bool PLAIN = false>
-__global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOUT>())
+__global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOUT, PLAIN>())
     pz_step_kernel(const __grid_constant__ KParams P) {
     // ENV_MAJOR stages the observation rows here (2-byte elements need half the room); FEATURE_MAJOR only
     // needs the computer players' scratch
