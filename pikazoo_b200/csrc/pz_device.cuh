@@ -445,7 +445,7 @@ constexpr int step_min_ctas() {
 // PLAIN: the configuration of a plain batched run — observations, float32 rewards, done flags and statistics all
 // written, auto-reset on, the full action set, and none of the options: no episode returns / lengths, truncated flags,
 // status byte or completion word, no frame cap, no shaped rewards, no SimplifyAction. The launch-uniform tests of all of
-// these are compiled out (launch_dt in pz_step_inst.inc decides; instantiated for no / two computer players). Worth
+// these are compiled out (launch_dt in pz_step_inst.inc decides). Worth
 // 1 % (int32 rows) to 10 % (bf16 feature-major rows): the options cost registers more than instructions.
 template <int AI_MASK, int OBS_DT, int LAYOUT, bool PLAIN = false>
 __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOUT, PLAIN>())
