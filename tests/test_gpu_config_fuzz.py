@@ -97,3 +97,52 @@ def test_random_configuration_matches_oracle(cuda_lib, case):
         assert np.array_equal(env.export_state().cpu().numpy(), orc.state), label
         orc.current_obs()
         check_obs("rollout")
+
+
+_PLAIN_OBS = [(torch.int32, np.int32, False), (torch.int16, np.int16, False), (torch.float32, np.float32, True),
+              (torch.float16, np.float16, True), (torch.bfloat16, "bfloat16", True), (torch.float64, np.float64, True)]
+
+
+@pytest.mark.parametrize("case", range(40))
+def test_random_plain_configuration_matches_oracle(cuda_lib, case):
+    """The same fuzz restricted to what the PLAIN instantiations of the per-step kernels serve (no wrappers, no frame
+    cap, no episode statistics, auto-reset, float32 rewards, normalised rows iff floating point): every case above asks
+    for episode statistics and therefore runs the general kernels; these run the PLAIN ones."""
+    import pikazoo_b200
+
+    rng = np.random.default_rng(5000 + case)
+    cfg = dict(winning_score=int(rng.choice([1, 2, 3, 15])), serve=str(rng.choice(["winner", "alternate", "random"])),
+               is_player1_computer=bool(rng.integers(0, 2)), is_player2_computer=bool(rng.integers(0, 2)))
+    obs_t, obs_np, normalize = _PLAIN_OBS[int(rng.integers(0, len(_PLAIN_OBS)))]
+    layout = str(rng.choice(["env_major", "feature_major"]))
+    extra = dict(obs_dtype=obs_t, normalize_observation=normalize, obs_layout=layout,
+                 action_dtype=[torch.int32, torch.int64, torch.uint8][int(rng.integers(0, 3))],
+                 landing_tables=bool(rng.integers(0, 2)))
+    if layout == "feature_major":
+        extra["obs_feature_rows"] = int(rng.choice([35, 40]))
+    n = int(rng.choice([1, 31, 33, 128, 640, 1000, 4097]))
+    seed = int(rng.integers(0, 2**40))
+    env = pikazoo_b200.PikaVecEnv(n, seed=seed, **cfg, **extra)
+    orc = po.OracleVecEnv(n, seed=seed, **cfg)
+    label = (case, n, cfg, {k: str(v) for k, v in extra.items()})
+
+    def check_obs(t):
+        got = env.obs
+        if layout == "feature_major":
+            got = got[:, :35, :].permute(2, 0, 1).contiguous()
+        assert np.array_equal(_bits(got), po.convert_obs(orc.obs, obs_np, normalize)), (label, t)
+
+    env.reset(), orc.reset()
+    check_obs(-1)
+    steps = 300
+    for t in range(steps):
+        a = synth_actions_numpy(seed & 0xFFFF, 0, n, t, 18)
+        obs, rew, done = env.step(torch.from_numpy(a).to("cuda", dtype=extra["action_dtype"]))
+        orc.step(a)
+        assert np.array_equal(done.cpu().numpy(), orc.done.astype(bool)), (label, t)
+        if t % 25 == 0 or t == steps - 1:
+            check_obs(t)
+            assert np.array_equal(rew.cpu().numpy(), orc.reward.astype(np.float32)), (label, t)
+    assert np.array_equal(env.export_state().cpu().numpy(), orc.state), label
+    st = env.stats_dict()
+    assert st["bad_actions"] == 0 and st["frozen"] == 0 and st["truncated"] == 0
