@@ -126,25 +126,33 @@ def test_rollout_policy_observation_after_last_frame_and_loop_continuation(cuda_
 
 
 @pytest.mark.parametrize("simplify", [False, True])
-def test_rollout_policy_plain_instantiation_equals_the_exporting_one(cuda_lib, simplify):
-    """A launch that samples, has no frame cap and exports nothing runs the PLAIN instantiation of the kernel (those four
-    launch-uniform options compiled out of the frame loop); the oracle-checked tests all export their actions and so
-    run the general one. Same start, same seeds: both must end in the identical state, stream included, and count the
-    same episodes."""
+def test_rollout_policy_plain_instantiation_equals_the_general_one(cuda_lib, simplify):
+    """A launch that samples, has no frame cap and does not export its logits runs the PLAIN instantiation of the kernel
+    (those launch-uniform options compiled out of the frame loop); most oracle-checked tests export the logits and so
+    run the general one. Same start, same seeds: both must sample the same actions, end in the identical state, stream
+    included, and count the same episodes."""
     from pikazoo_b200.policy import MLPPolicy, rollout_fused
 
     n, K = 8192 + 77, 40
     ends = []
-    for export in (True, False):
+    for general in (True, False):
         env, _ = _make(n, 21, winning_score=2, serve="random", simplify_action=simplify)
         policy = MLPPolicy(device=env.device, seed=4, n_actions=13 if simplify else 18)
-        actions = torch.empty((K, n, 2), dtype=torch.uint8, device="cuda") if export else None
+        actions = torch.empty((K, n, 2), dtype=torch.uint8, device="cuda")
+        logits = torch.empty((K, n, 2, policy.n_actions), dtype=torch.float32, device="cuda") if general else None
         for _ in range(3):
-            rollout_fused(env, policy, K, seed=9, actions_out=actions)
+            rollout_fused(env, policy, K, seed=9, actions_out=actions, logits_out=logits)
         st = env.stats_dict()
-        ends.append((env.export_state().cpu().numpy(), {k: st[k] for k in ("episodes", "resets", "p1_points", "p2_points")}))
-    assert np.array_equal(ends[0][0], ends[1][0])
-    assert ends[0][1] == ends[1][1] and ends[0][1]["episodes"] > 0
+        ends.append((env.export_state().cpu().numpy(), actions.cpu().numpy(),
+                     {k: st[k] for k in ("episodes", "resets", "p1_points", "p2_points")}))
+    assert np.array_equal(ends[0][0], ends[1][0]) and np.array_equal(ends[0][1], ends[1][1])
+    assert ends[0][2] == ends[1][2] and ends[0][2]["episodes"] > 0
+    # and without the action export (the same instantiation, a null pointer): the same state again
+    env, _ = _make(n, 21, winning_score=2, serve="random", simplify_action=simplify)
+    policy = MLPPolicy(device=env.device, seed=4, n_actions=13 if simplify else 18)
+    for _ in range(3):
+        rollout_fused(env, policy, K, seed=9)
+    assert np.array_equal(env.export_state().cpu().numpy(), ends[0][0])
 
 
 def test_rollout_policy_agrees_with_the_two_kernel_loop(cuda_lib):
