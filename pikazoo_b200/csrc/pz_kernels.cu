@@ -68,7 +68,8 @@ constexpr int kRolloutThreads = PZ_ROLLOUT_THREADS;
 
 // PLAIN: no-op actions and no frame cap (configs[3], and every pre-advance) — the frame loop then carries neither the
 // action stream and its decode nor the two truncation tests.
-template <int AI_MASK, bool PLAIN>
+// TABLES (with PLAIN and computer players only): the memoised trajectory tables are known to be there.
+template <int AI_MASK, bool PLAIN, bool TABLES = false>
 __global__ void __maxnreg__(AI_MASK == 3 ? PZ_ROLLOUT_MAXNREG_AI : PZ_ROLLOUT_MAXNREG) pz_rollout_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(16) int stage[kRolloutThreads / 32][kAiScratchInts];
     const int warp = threadIdx.x >> 5;
@@ -124,7 +125,7 @@ __global__ void __maxnreg__(AI_MASK == 3 ? PZ_ROLLOUT_MAXNREG_AI : PZ_ROLLOUT_MA
                     in2 = decode_input<1, false>(a2, e.p[1], b2);
                 }
             }
-            step_frame_inputs<AI_MASK, DrawCtxT<false>, PZ_ROLLOUT_ANIM_LUT>(mask, e, d, P.cfg, in1, in2, stage[warp], s_anim);
+            step_frame_inputs<AI_MASK, DrawCtxT<false>, PZ_ROLLOUT_ANIM_LUT, PZ_ROLLOUT_ANIM_LUT, TABLES>(mask, e, d, P.cfg, in1, in2, stage[warp], s_anim);
             if (e.game_ended) {
                 atomicAdd(s_stats + PZ_STAT_EPISODES, 1ULL);
                 atomicAdd(s_stats + PZ_STAT_EPISODE_FRAMES, (unsigned long long)e.ep_frames);
@@ -661,7 +662,9 @@ int pz_rollout(int32_t *state_dev, int64_t n, const pz_config *cfg, int32_t K, i
     const bool plain = action_source == PZ_ACTIONS_NOOP && P.max_frames <= 0;
 #define PZ_ROLLOUT_CASE(M)                                                                      \
     case M:                                                                                     \
-        if (plain)                                                                              \
+        if (plain && M != 0 && P.cfg.tab_land != nullptr && P.cfg.tab_power != nullptr)         \
+            pz_rollout_kernel<M, true, M != 0><<<rollout_grid, kRolloutThreads, 0, st>>>(P);    \
+        else if (plain)                                                                         \
             pz_rollout_kernel<M, true><<<rollout_grid, kRolloutThreads, 0, st>>>(P);            \
         else                                                                                    \
             pz_rollout_kernel<M, false><<<rollout_grid, kRolloutThreads, 0, st>>>(P);           \

@@ -351,9 +351,10 @@ __device__ __forceinline__ int simulate_landing_x(unsigned mask, int x, int y, i
 }
 
 // expected landing x of the current ball for the lanes with `need`; memoised when possible.
+template <bool TABLES = false>  // TABLES: the caller knows the memoised tables are there (one launch-uniform test less)
 __device__ __forceinline__ void update_landing(unsigned mask, Env &e, const StepCfg &c, bool need) {
     const Ball &b = e.b;
-    if (c.tab_land != nullptr) {
+    if (TABLES || c.tab_land != nullptr) {
         if (need && iabs(b.yv) <= kTabYv && iabs(b.xv) <= 20 && tab_pos_ok(b.x, b.y)) {
             const unsigned v = __ldg(c.tab_land + tab_land_index(b.x, b.y, b.xv, b.yv));
             e.b.land = (int)(v & 0x7FFFu);
@@ -374,7 +375,7 @@ __device__ __forceinline__ void update_landing(unsigned mask, Env &e, const Step
 // ---- computer player ---------------------------------------------------------------------------
 // let_computer_decide_user_input (physics.py:689-771) + decide_whether_input_power_hit (:774-817).
 // Warp-collective over `mask`.
-template <int I, class Ctx, bool KFRAME = false>
+template <int I, class Ctx, bool KFRAME = false, bool TABLES = false>
 __device__ __forceinline__ void computer_decide(unsigned mask, Env &e, Ctx &d, const StepCfg &cfg, Input &in,
                                                 int *scratch) {
     Player &p = e.p[I];
@@ -423,7 +424,7 @@ __device__ __forceinline__ void computer_decide(unsigned mask, Env &e, Ctx &d, c
     // iterative simulations below: five shuffles, a rank table in shared memory and three warp barriers per player
     // and frame cost more than the lanes that idle through these straight-line instructions.)
     const int ayv = iabs(b.yv);
-    const bool tab_ok = cfg.tab_power != nullptr && search && ayv <= kTabYv && tab_pos_ok(b.x, b.y);
+    const bool tab_ok = (TABLES || cfg.tab_power != nullptr) && search && ayv <= kTabYv && tab_pos_ok(b.x, b.y);
     int lx_up[2] = {0, 0}, lx_mid[2] = {0, 0}, lx_dn[2] = {0, 0};  // [x_direction]
     int y_first = 0;
     auto load_candidates = [&]() {
@@ -660,7 +661,7 @@ __device__ __forceinline__ bool ball_player(Env &e, Ctx &d, const Input &in) {
 // power_hit_key_is_down_previous, which the new-round block below does not, so the order is immaterial).
 // KFRAME (the K-frame kernels): `anim` is the sprite-animation table in shared memory (anim_fill), and the computer
 // players' table loads are not hoisted above the draws.
-template <int AI_MASK, class Ctx, bool KFRAME = false, bool ANIM_LUT = KFRAME>
+template <int AI_MASK, class Ctx, bool KFRAME = false, bool ANIM_LUT = KFRAME, bool TABLES = false>
 __device__ __forceinline__ int step_frame_inputs(unsigned mask, Env &e, Ctx &d, const StepCfg &c, Input in1, Input in2,
                                                  int *scratch, const uint32_t *anim = nullptr) {
     if (e.round_ended) {  // :176-180 (game_ended is false here)
@@ -677,20 +678,20 @@ __device__ __forceinline__ int step_frame_inputs(unsigned mask, Env &e, Ctx &d, 
         // :314-315 is evaluated twice per frame on an unchanged ball; once is enough. And while the
         // ball free-flies along the trajectory that was simulated last frame (land_ok: that
         // simulation ended on the ground), the landing point of the advanced ball is the same.
-        update_landing(mask, e, c, !e.land_ok || touching || net192);
+        update_landing<TABLES>(mask, e, c, !e.land_ok || touching || net192);
     } else {
         e.land_ok = 0;  // expected_landing_point_x is not maintained without computer players
     }
-    if (AI_MASK & 1) computer_decide<0, Ctx, KFRAME>(mask, e, d, c, in1, scratch);
+    if (AI_MASK & 1) computer_decide<0, Ctx, KFRAME, TABLES>(mask, e, d, c, in1, scratch);
     player_move<0, ANIM_LUT>(e.p[0], in1, anim);
-    if (AI_MASK & 2) computer_decide<1, Ctx, KFRAME>(mask, e, d, c, in2, scratch);
+    if (AI_MASK & 2) computer_decide<1, Ctx, KFRAME, TABLES>(mask, e, d, c, in2, scratch);
     player_move<1, ANIM_LUT>(e.p[1], in2, anim);
 
     bool recalc = ball_player<0>(e, d, in1);
     recalc |= ball_player<1>(e, d, in2);
     if (AI_MASK != 0) {
         // :331-332 after each new collision; only the value for the final ball state survives.
-        if (__any_sync(mask, recalc)) update_landing(mask, e, c, recalc);
+        if (__any_sync(mask, recalc)) update_landing<TABLES>(mask, e, c, recalc);
     }
 
     // scoring, :190-210
