@@ -513,8 +513,9 @@ __global__ void __launch_bounds__(kThreads, step_min_ctas<AI_MASK, OBS_DT, LAYOU
         // L1) where that measured faster: 2-byte rows 46.4 -> 45.0 us, computer players 79.2 -> 78.4, int32 rows
         // 59.8 -> 59.5 us per million envs — but float32 rows 66.5 -> 67.7 us, which keep the arithmetic
         constexpr bool kAnimLut = PZ_STEP_ANIM_LUT && OBS_DT != PZ_OBS_F32 && OBS_DT != PZ_OBS_F64;
-        base = step_frame_inputs<AI_MASK, DrawCtxT<AI_MASK == 0>, false, kAnimLut>(mask, e, d, P.cfg, in1, in2, stage[warp],
-                                                                                  g_anim_table.v);
+        // (PLAIN with computer players implies the memoised tables: launch_dt)
+        base = step_frame_inputs<AI_MASK, DrawCtxT<AI_MASK == 0>, false, kAnimLut, PLAIN && AI_MASK != 0>(
+            mask, e, d, P.cfg, in1, in2, stage[warp], g_anim_table.v);
     } else if (do_reset) {
         reset_env(e, d, P.cfg);
     }
