@@ -66,7 +66,9 @@ def build(force: bool = False, verbose: bool = False, out: str | None = None) ->
             sys.stderr.write(f"---- {src}\n{r.stdout}{r.stderr}")
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.run([nvcc, "-Wno-deprecated-gpu-targets", "-shared", "-o", lib_path] + [obj for _, obj, _ in results], check=True)
+    # (the link step gets the architecture too: without it nvcc adds an empty device-link image for its default sm_52)
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib_path]
+                   + [obj for _, obj, _ in results], check=True)
     return lib_path
 
 
